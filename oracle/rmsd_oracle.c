@@ -1,0 +1,442 @@
+/* rmsd_oracle.c -- CPU restatement of cpptraj's best-fit RMSD hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library, and only as the checker or
+ * the timed CPU baseline; the product (cpptraj_b200/csrc) never calls it and
+ * fails loudly when its CUDA library is missing.
+ *
+ * Parity status: PINNED.  tests/test_oracle.py checks this file against
+ *   (1) the reference's own golden vectors (test/Test_2DRMS/{rmsd,rmsd.mass,
+ *       trp,nofit}.dat.save, test/Test_RMSD/NoMod.dat.save; copies of the
+ *       numbers under tests/golden/, generator tools/make_golden.py), and
+ *   (2) the reference's real Frame/Matrix_3x3/CompactFrameArray/Matrix<float>
+ *       code compiled into oracle/_ref/ (oracle/build_ref.sh), to <= 1e-12.
+ *
+ * Every function cites the reference file:line (relative to /root/reference)
+ * whose arithmetic it follows.  All arithmetic is double, inputs float32 AoS,
+ * outputs float32 (rms2d / pairwise cache) or double (rmsd action) exactly as
+ * in the reference.
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_SMALL 0.00000000000001 /* src/Constants.h:35 (Constants::SMALL) */
+#define ORC_JACOBI_SWEEPS 50       /* src/Matrix_3x3.cpp:97 */
+
+/* ---- a6: mask gather float32 -> double ----------------------------------
+ * src/CompactFrameArray.cpp:244-262 (GetToMaskDblPtr): position component at
+ * offset 0 of each frame, frame stride = whole frame incl. vel/box/etc. */
+static void orc_gather(const float *crd, size_t stride, long frame,
+                       const int *sel, int n, double *X)
+{
+    const float *fb = crd + (size_t)frame * stride;
+    for (int j = 0; j < n; j++) {
+        int s = 3 * sel[j];
+        X[3 * j + 0] = (double)fb[s + 0];
+        X[3 * j + 1] = (double)fb[s + 1];
+        X[3 * j + 2] = (double)fb[s + 2];
+    }
+}
+
+/* ---- a3: centre on origin ------------------------------------------------
+ * src/Frame.cpp:1043-1055 (CenterOnOrigin), src/Frame.h:373-391 (VCenterOfMass)
+ * and :418-431 (VGeometricCenter), :500-506 (NegTranslate).
+ * Returns centre in c[3]. */
+static void orc_center_on_origin(double *X, int n, const double *mass,
+                                 int useMass, double *c)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, sm = 0.0;
+    if (useMass) {
+        for (int i = 0; i < n; i++) {
+            sm += mass[i];
+            s0 += X[3 * i + 0] * mass[i];
+            s1 += X[3 * i + 1] * mass[i];
+            s2 += X[3 * i + 2] * mass[i];
+        }
+    } else {
+        for (int i = 0; i < n; i++) {
+            s0 += X[3 * i + 0];
+            s1 += X[3 * i + 1];
+            s2 += X[3 * i + 2];
+        }
+        sm = (double)n;
+    }
+    if (sm == 0.0) {
+        c[0] = c[1] = c[2] = 0.0;
+    } else {
+        c[0] = s0 / sm; c[1] = s1 / sm; c[2] = s2 / sm;
+    }
+    for (int i = 0; i < n; i++) {
+        X[3 * i + 0] -= c[0];
+        X[3 * i + 1] -= c[1];
+        X[3 * i + 2] -= c[2];
+    }
+}
+
+/* ---- a2: cyclic Jacobi on a symmetric 3x3 ----------------------------------
+ * src/Matrix_3x3.cpp:110-211 (Diagonalize).  a[9] row-major symmetric input
+ * (destroyed); V[9] receives eigenvectors in columns; d[3] eigenvalues.
+ * Returns 1 when the sweep limit is hit (reference then returns RMSD 0). */
+static void orc_jrot(double *m, int i1, int i2, double s, double tau)
+{
+    double g = m[i1], h = m[i2];
+    m[i1] = g - s * (h + g * tau);
+    m[i2] = h + s * (g - h * tau);
+}
+
+static int orc_jacobi3(double *a, double *V, double *d)
+{
+    double b[3], z[3];
+    for (int i = 0; i < 9; i++) V[i] = 0.0;
+    V[0] = V[4] = V[8] = 1.0;
+    for (int i = 0; i < 3; i++) { b[i] = d[i] = a[4 * i]; z[i] = 0.0; }
+    for (int sweep = 0; sweep < ORC_JACOBI_SWEEPS; sweep++) {
+        double sm = fabs(a[1]) + fabs(a[2]) + fabs(a[5]);
+        if (sm == 0.0) return 0;
+        double tresh = (sweep < 3) ? 0.2 * sm / 9 : 0.0;
+        for (int ip = 0; ip < 2; ip++) {
+            for (int iq = ip + 1; iq < 3; iq++) {
+                int pq = 3 * ip + iq;
+                double g = 100.0 * fabs(a[pq]);
+                if (sweep > 3 && fabs(d[ip]) + g == fabs(d[ip]) &&
+                                 fabs(d[iq]) + g == fabs(d[iq])) {
+                    a[pq] = 0.0;
+                } else if (fabs(a[pq]) > tresh) {
+                    double h = d[iq] - d[ip], t;
+                    if (fabs(h) + g == fabs(h)) {
+                        t = a[pq] / h;
+                    } else {
+                        double theta = 0.5 * h / a[pq];
+                        t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+                        if (theta < 0.0) t = -t;
+                    }
+                    double c = 1.0 / sqrt(1 + t * t);
+                    double s = t * c;
+                    double tau = s / (1.0 + c);
+                    h = t * a[pq];
+                    z[ip] -= h; z[iq] += h;
+                    d[ip] -= h; d[iq] += h;
+                    a[pq] = 0.0;
+                    for (int j = 0; j <= ip - 1; j++)  orc_jrot(a, 3 * j + ip, 3 * j + iq, s, tau);
+                    for (int j = ip + 1; j <= iq - 1; j++) orc_jrot(a, 3 * ip + j, 3 * j + iq, s, tau);
+                    for (int j = iq + 1; j < 3; j++)   orc_jrot(a, 3 * ip + j, 3 * iq + j, s, tau);
+                    for (int j = 0; j < 3; j++)        orc_jrot(V, 3 * j + ip, 3 * j + iq, s, tau);
+                }
+            }
+        }
+        for (int i = 0; i < 3; i++) { b[i] += z[i]; d[i] = b[i]; z[i] = 0.0; }
+    }
+    return 1;
+}
+
+/* src/Matrix_3x3.cpp:219-268 (Diagonalize_Sort): descending order, vectors in
+ * rows of E.  Order selection mirrors the reference's strict comparisons. */
+static int orc_diag_sort(double *a, double *E, double *ev)
+{
+    double V[9], d[3];
+    if (orc_jacobi3(a, V, d)) return 1;
+    int i1, i2, i3;
+    if (d[0] > d[1] && d[0] > d[2]) {
+        i1 = 0; if (d[1] > d[2]) { i2 = 1; i3 = 2; } else { i2 = 2; i3 = 1; }
+    } else if (d[1] > d[0] && d[1] > d[2]) {
+        i1 = 1; if (d[0] > d[2]) { i2 = 0; i3 = 2; } else { i2 = 2; i3 = 0; }
+    } else if (d[0] > d[1]) {
+        i1 = 2; i2 = 0; i3 = 1;
+    } else {
+        i1 = 2; i2 = 1; i3 = 0;
+    }
+    for (int c = 0; c < 3; c++) {
+        E[0 + c] = V[i1 + 3 * c];
+        E[3 + c] = V[i2 + 3 * c];
+        E[6 + c] = V[i3 + 3 * c];
+    }
+    ev[0] = d[i1]; ev[1] = d[i2]; ev[2] = d[i3];
+    return 0;
+}
+
+static void orc_unit3(double *v)
+{
+    double b = 1.0 / sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    v[0] *= b; v[1] *= b; v[2] *= b;
+}
+
+/* ---- a1: RMSD of target T to a pre-centred reference R --------------------
+ * src/Frame.cpp:1137-1273 (RMSD_CenteredRef).  T is translated in place.
+ * U[9] (rotation) and trans[3] (target -> origin translation) may be NULL.
+ * mass is the TARGET frame's mass array (src/Frame.cpp:1184). */
+double orc_rmsd_centered_ref(double *T, const double *R, int n,
+                             const double *mass, int useMass,
+                             double *U, double *trans)
+{
+    double tm, tr[3] = {0, 0, 0};
+    if (useMass) {
+        tm = 0.0;
+        for (int i = 0; i < n; i++) {
+            tm += mass[i];
+            tr[0] += T[3 * i + 0] * mass[i];
+            tr[1] += T[3 * i + 1] * mass[i];
+            tr[2] += T[3 * i + 2] * mass[i];
+        }
+    } else {
+        tm = (double)n;
+        for (int i = 0; i < n; i++) {
+            tr[0] += T[3 * i + 0]; tr[1] += T[3 * i + 1]; tr[2] += T[3 * i + 2];
+        }
+    }
+    if (tm < ORC_SMALL) return -1.0;            /* :1160-1163 */
+    tr[0] /= tm; tr[1] /= tm; tr[2] /= tm;
+    tr[0] = -tr[0]; tr[1] = -tr[1]; tr[2] = -tr[2];
+    for (int i = 0; i < n; i++) {               /* Translate(Trans) */
+        T[3 * i + 0] += tr[0]; T[3 * i + 1] += tr[1]; T[3 * i + 2] += tr[2];
+    }
+    if (trans) { trans[0] = tr[0]; trans[1] = tr[1]; trans[2] = tr[2]; }
+
+    double mwss = 0.0, rot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, am = 1.0;
+    for (int i = 0; i < n; i++) {               /* :1184-1208 */
+        double xt = T[3 * i], yt = T[3 * i + 1], zt = T[3 * i + 2];
+        double xr = R[3 * i], yr = R[3 * i + 1], zr = R[3 * i + 2];
+        if (useMass) am = mass[i];
+        mwss += am * ((xt * xt) + (yt * yt) + (zt * zt) + (xr * xr) + (yr * yr) + (zr * zr));
+        rot[0] += am * xt * xr; rot[1] += am * xt * yr; rot[2] += am * xt * zr;
+        rot[3] += am * yt * xr; rot[4] += am * yt * yr; rot[5] += am * yt * zr;
+        rot[6] += am * zt * xr; rot[7] += am * zt * yr; rot[8] += am * zt * zr;
+    }
+    mwss *= 0.5;
+    /* rot * rot^T (src/Matrix_3x3.cpp:421-433 TransposeMult) */
+    double rr[9], E[9], ev[3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            rr[3 * i + j] = rot[3 * i] * rot[3 * j] + rot[3 * i + 1] * rot[3 * j + 1] +
+                            rot[3 * i + 2] * rot[3 * j + 2];
+    if (orc_diag_sort(rr, E, ev)) return 0.0;   /* :1218 */
+    /* a3 = a1 x a2 */
+    E[6] = E[1] * E[5] - E[2] * E[4];
+    E[7] = E[2] * E[3] - E[0] * E[5];
+    E[8] = E[0] * E[4] - E[1] * E[3];
+    double b[9];
+    for (int k = 0; k < 3; k++) {               /* b_k = R . a_k, normalised */
+        b[3 * k + 0] = E[3 * k] * rot[0] + E[3 * k + 1] * rot[3] + E[3 * k + 2] * rot[6];
+        b[3 * k + 1] = E[3 * k] * rot[1] + E[3 * k + 1] * rot[4] + E[3 * k + 2] * rot[7];
+        b[3 * k + 2] = E[3 * k] * rot[2] + E[3 * k + 1] * rot[5] + E[3 * k + 2] * rot[8];
+        orc_unit3(b + 3 * k);
+    }
+    double cp[3];
+    cp[0] = b[1] * b[5] - b[2] * b[4];
+    cp[1] = b[2] * b[3] - b[0] * b[5];
+    cp[2] = b[0] * b[4] - b[1] * b[3];
+    double sig3 = ((cp[0] * b[6] + cp[1] * b[7] + cp[2] * b[8]) < 0.0) ? -1.0 : 1.0;
+    b[6] = cp[0]; b[7] = cp[1]; b[8] = cp[2];
+    if (U) {                                    /* :1246-1256 */
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 3; c++)
+                U[3 * r + c] = E[c] * b[r] + E[3 + c] * b[3 + r] + E[6 + c] * b[6 + r];
+    }
+    double e = mwss - sqrt(fabs(ev[0])) - sqrt(fabs(ev[1])) - (sig3 * sqrt(fabs(ev[2])));
+    if (e < 0) return 0.0;                      /* :1264-1266 */
+    return sqrt((2.0 * e) / tm);
+}
+
+/* ---- a4: no-fit RMSD  (src/Frame.cpp:1279-1307) -------------------------- */
+double orc_rmsd_nofit(const double *T, const double *R, int n,
+                      const double *mass, int useMass)
+{
+    double acc = 0.0, tm = 0.0, am = 1.0;
+    for (int i = 0; i < n; i++) {
+        double xx = R[3 * i] - T[3 * i], yy = R[3 * i + 1] - T[3 * i + 1], zz = R[3 * i + 2] - T[3 * i + 2];
+        if (useMass) am = mass[i];
+        tm += am;
+        acc += am * (xx * xx + yy * yy + zz * zz);
+    }
+    if (tm < ORC_SMALL) return -1.0;
+    if (acc < 0) return 0.0;
+    return sqrt(acc / tm);
+}
+
+/* ---- a11: output indexers  (src/Matrix.h:94-96,110-122) ------------------- */
+size_t orc_tri_index(size_t n, size_t x, size_t y)
+{
+    size_t i = x < y ? x : y, j = x < y ? y : x;
+    size_t i1 = i + 1;
+    return ((n * i) - ((i1 * i) / 2)) + j - i1;
+}
+size_t orc_full_index(size_t ncols, size_t x, size_t y) { return y * ncols + x; }
+
+/* ---- a7: rms2d pair enumeration -------------------------------------------
+ * src/Analysis_Rms2d.cpp:196-295 (Calculate_2D), triangle branch: reference =
+ * frame nref (centred once per row, :263-266), target = ntgt > nref (:272-283).
+ * frameIdx (nullable) selects/permutes frames like the cluster path's
+ * framesToCache.  mass NULL => unit masses (useMass false).
+ * out: float[nF(nF-1)/2] in calcTriIndex order.  Returns 0 / nonzero. */
+int orc_rms2d_tri(const float *crd, size_t stride, const int *frameIdx, int nF,
+                  const int *sel, int n, const double *mass, int fit, float *out)
+{
+    int useMass = (mass != NULL);
+    int err = 0;
+#pragma omp parallel
+    {
+        double *R = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *T = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double c[3];
+        if (!R || !T) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic)
+            for (int r = 0; r < nF; r++) {
+                orc_gather(crd, stride, frameIdx ? frameIdx[r] : r, sel, n, R);
+                if (fit) orc_center_on_origin(R, n, mass, useMass, c);
+                for (int t = r + 1; t < nF; t++) {
+                    orc_gather(crd, stride, frameIdx ? frameIdx[t] : t, sel, n, T);
+                    double v = fit ? orc_rmsd_centered_ref(T, R, n, mass, useMass, NULL, NULL)
+                                   : orc_rmsd_nofit(T, R, n, mass, useMass);
+                    out[orc_tri_index((size_t)nF, (size_t)r, (size_t)t)] = (float)v;
+                }
+            }
+        }
+        free(R); free(T);
+    }
+    return err;
+}
+
+/* Cluster flavour: src/Cluster/Metric_RMS.cpp:44-63 (FrameDist) called from
+ * src/Cluster/MetricArray.cpp:766-801: frm1 = frame f1 is "this" (target),
+ * frm2 = frame f2 is re-centred per pair (src/Frame.cpp:1102-1109), result is
+ * a double stored to a float cache (src/DataSet_PairwiseCache_MEM.h:28). */
+int orc_cluster_tri(const float *crd, size_t stride, const int *frameIdx, int nF,
+                    const int *sel, int n, const double *mass, int fit, float *out)
+{
+    int useMass = (mass != NULL);
+    int err = 0;
+#pragma omp parallel
+    {
+        double *A = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *B = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double c[3];
+        if (!A || !B) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic)
+            for (int f1 = 0; f1 < nF - 1; f1++) {
+                for (int f2 = f1 + 1; f2 < nF; f2++) {
+                    orc_gather(crd, stride, frameIdx ? frameIdx[f1] : f1, sel, n, A);
+                    orc_gather(crd, stride, frameIdx ? frameIdx[f2] : f2, sel, n, B);
+                    double v;
+                    if (fit) {
+                        orc_center_on_origin(B, n, mass, useMass, c);
+                        v = orc_rmsd_centered_ref(A, B, n, mass, useMass, NULL, NULL);
+                    } else
+                        v = orc_rmsd_nofit(A, B, n, mass, useMass);
+                    out[orc_tri_index((size_t)nF, (size_t)f1, (size_t)f2)] = (float)v;
+                }
+            }
+        }
+        free(A); free(B);
+    }
+    return err;
+}
+
+/* Full-matrix branch of Calculate_2D (reftraj or differing masks):
+ * Allocate2D(totalref,totaltgt) => ncols = nRef, element (x=nref,y=ntgt) at
+ * ntgt*nRef + nref  (src/Analysis_Rms2d.cpp:208-209, src/Matrix.h:94-96).
+ * massTgt weights the covariance and total mass (target frame's Mass_);
+ * massRef is used only to centre the reference (SelectedRef.CenterOnOrigin). */
+int orc_rms2d_full(const float *crdT, size_t strideT, int nT, const int *selT,
+                   const float *crdR, size_t strideR, int nR, const int *selR,
+                   int n, const double *massTgt, const double *massRef, int fit,
+                   float *out)
+{
+    int useMass = (massTgt != NULL);
+    int err = 0;
+#pragma omp parallel
+    {
+        double *R = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *T = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double c[3];
+        if (!R || !T) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic)
+            for (int r = 0; r < nR; r++) {
+                orc_gather(crdR, strideR, r, selR, n, R);
+                if (fit) orc_center_on_origin(R, n, massRef, useMass, c);
+                for (int t = 0; t < nT; t++) {
+                    orc_gather(crdT, strideT, t, selT, n, T);
+                    double v = fit ? orc_rmsd_centered_ref(T, R, n, massTgt, useMass, NULL, NULL)
+                                   : orc_rmsd_nofit(T, R, n, massTgt, useMass);
+                    out[orc_full_index((size_t)nR, (size_t)r, (size_t)t)] = (float)v;
+                }
+            }
+        }
+        free(R); free(T);
+    }
+    return err;
+}
+
+/* ---- a10: one-vs-many (rmsd action) ----------------------------------------
+ * src/Action_Rmsd.cpp:361-392 (DoAction) with a fixed reference
+ * (ReferenceAction FIRST/FRAME modes, src/ReferenceAction.cpp:155-169):
+ * ref = selected atoms, centred once when fitting (refTrans returned).
+ * Input frames are double (cpptraj Frame) or float (COORDS set); both offered.
+ * rmsdOut[nF] double; rotOut (nullable) 9 per frame; transOut (nullable)
+ * 3 per frame = target -> origin translation (tgtTrans_). */
+int orc_rmsd_1vN(const float *crd, size_t stride, int nF, const int *sel, int n,
+                 const double *refSel /*3n, NOT yet centred*/, const double *mass,
+                 int fit, double *rmsdOut, double *rotOut, double *transOut,
+                 double *refTrans /*3, nullable*/)
+{
+    int useMass = (mass != NULL);
+    double *R = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+    if (!R) return 1;
+    memcpy(R, refSel, sizeof(double) * 3 * (size_t)n);
+    double c[3] = {0, 0, 0};
+    if (fit) orc_center_on_origin(R, n, mass, useMass, c);
+    if (refTrans) { refTrans[0] = c[0]; refTrans[1] = c[1]; refTrans[2] = c[2]; }
+    int err = 0;
+#pragma omp parallel
+    {
+        double *T = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        if (!T) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(static)
+            for (int f = 0; f < nF; f++) {
+                orc_gather(crd, stride, f, sel, n, T);
+                if (fit)
+                    rmsdOut[f] = orc_rmsd_centered_ref(T, R, n, mass, useMass,
+                                                       rotOut ? rotOut + 9 * (size_t)f : NULL,
+                                                       transOut ? transOut + 3 * (size_t)f : NULL);
+                else
+                    rmsdOut[f] = orc_rmsd_nofit(T, R, n, mass, useMass);
+            }
+        }
+        free(T);
+    }
+    free(R);
+    return err;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
