@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py -- fitted pair-RMSDs/s of the rms2d hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...           (one rank per GPU)
+
+Workload (synthetic, cpptraj_b200.synth, seeds from SURVEY.md 8d):
+    N == 1 : BASELINE configs[1]  rms2d fit, 10,000 frames x 1,000 atoms (49,995,000 pairs)
+    N  > 1 : BASELINE configs[4]  rms2d fit, 100,000 frames x 1,000 atoms, the upper triangle
+             sharded into contiguous, pair-balanced row bands over the ranks (strong scaling,
+             no data-path collective: every rank packs the frames it needs itself).
+A "step" is one pass over all pairs of the rank's shard.
+
+One JSON line is printed by rank 0:
+    value      pairs/s, whole job, inputs (raw float32 COORDS) resident in HBM, timed with CUDA
+               events on the stream the kernels are launched on: pack + pair-tile kernels,
+               result triangle left in HBM.
+    e2e        same metric through the C ABI (b200_rms2d_tri_shard) with pinned HOST buffers:
+               H2D of the COORDS, kernels, D2H of the float triangle all inside the timed region.
+    roofline   pair-tile kernel: algorithmic flop (18*N per fitted pair) / CUDA-event kernel time,
+               against this device's FP64 tensor (DMMA) peak measured live by a register-only
+               mma.sync probe (MEASURED_PEAKS.json has no FP64 figure; the bf16 fraction is
+               reported beside it for context).
+    cpu_baseline  the reference's own Frame::RMSD_CenteredRef loop (oracle/_ref, OpenMP, all host
+               threads) on a bounded prefix of the same trajectory (N == 1, rank 0 only).
+
+--impl reference times that CPU implementation alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fitted pair-RMSDs/sec (rms2d FxN)"
+UNIT = "pair-RMSDs/s"
+SEEDS = {"cfg2": 20261017, "cfg5": 20261020}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=0, help="override frame count")
+    ap.add_argument("--atoms", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU seconds for the bounded baseline sample")
+    return ap.parse_args()
+
+
+def workload(args):
+    if args.frames:
+        return "custom", args.frames, args.atoms, 20261017
+    if args.gpus > 1:
+        return "cfg5", 100000, args.atoms, SEEDS["cfg5"]
+    return "cfg2", 10000, args.atoms, SEEDS["cfg2"]
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_evt = threading.Event()
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+             0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+             0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self.stop_evt.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.NAMES.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self.stop_evt.wait(0.1)
+
+    def result(self):
+        self.stop_evt.set()
+        if self.is_alive():
+            self.join(2.0)
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "nvml unavailable"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "power_w_max": max(self.power) if self.power else None}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_pairs_rate(crd, sel, target_seconds, threads=None):
+    """Time the reference's own pair loop (oracle/_ref) on a bounded prefix of crd.
+    Returns dict(value, cores, kind, sample, seconds)."""
+    from oracle.pyoracle import Oracle, Reference, have_reference
+    if have_reference():
+        impl, kind = Reference(), "reference"
+    else:
+        impl, kind = Oracle(), "port"
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    if threads:
+        cores = threads
+    impl.set_threads(cores)
+
+    def run(nf):
+        t0 = time.perf_counter()
+        impl.rms2d_tri(crd[:nf], sel)
+        dt = time.perf_counter() - t0
+        if kind == "reference":
+            dt = impl.last_loop_seconds()   # pair loop only, what cpptraj's TIME: line covers
+        return dt
+
+    nf = min(crd.shape[0], 400)
+    dt = max(run(nf), 1e-4)
+    rate = nf * (nf - 1) / 2 / dt
+    nf2 = int(min(crd.shape[0], max(nf, (2 * rate * target_seconds) ** 0.5)))
+    return impl, kind, cores, nf2, rate
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from cpptraj_b200.synth import make_trajectory
+    name, nF, nA, seed = workload(args)
+    # a bounded prefix is all the CPU can do in minutes; cost is exactly linear in pairs
+    nGen = min(nF, 12000)
+    crd, _ = make_trajectory(seed, nGen, nA)
+    sel = np.arange(nA, dtype=np.int32)
+    steps_total = max(1, args.steps + args.warmup)
+    per_step = max(2.0, min(20.0, 150.0 / steps_total))
+    impl, kind, cores, nf, _ = cpu_pairs_rate(crd, sel, per_step)
+    pairs = nf * (nf - 1) / 2
+
+    def step():
+        t0 = time.perf_counter()
+        impl.rms2d_tri(crd[:nf], sel)
+        dt = time.perf_counter() - t0
+        return impl.last_loop_seconds() if kind == "reference" else dt
+
+    for _ in range(args.warmup):
+        step()
+    tot = sum(step() for _ in range(args.steps))
+    value = pairs * args.steps / tot
+    sample = "rms2d fit on the first %d of %d frames x %d atoms (%d pairs/step), %d OpenMP threads" % (nf, nF, nA, pairs, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: rms2d fit, %d frames x %d atoms (CPU arm times a %d-frame prefix per step)" % (name, nF, nA, nf)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import cpptraj_b200 as b
+    from cpptraj_b200.synth import make_trajectory
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    b.init(devices=[local])
+
+    name, nF, nA, seed = workload(args)
+    stride = 3 * nA
+    # ---- synthetic COORDS in pinned host memory (every rank generates the same trajectory)
+    t_gen = time.perf_counter()
+    h_crd = torch.empty((nF, stride), dtype=torch.float32, pin_memory=True)
+    make_trajectory(seed, nF, nA, out=h_crd.numpy())
+    t_gen = time.perf_counter() - t_gen
+    sel = np.arange(nA, dtype=np.int32)
+    r0, r1 = b.shard_rows(nF, rank, world)
+    first = nF * r0 - r0 * (r0 + 1) // 2
+    nelt = (nF * r1 - r1 * (r1 + 1) // 2) - first
+    total_pairs = nF * (nF - 1) // 2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # =================== value: device-resident ===================
+    d_crd = h_crd.cuda(non_blocking=False)
+    d_sel = torch.from_numpy(sel).cuda()
+    d_out = torch.empty(max(nelt, 1), dtype=torch.float32, device="cuda")
+    # the ABI indexes the whole triangle; hand it a base pointer such that base[first] is d_out[0]
+    d_out_base = d_out.data_ptr() - 4 * first
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def dev_step():
+        b.dev_rms2d_tri(d_crd, stride, nF, d_sel, nA, d_out_base, fit=True, rank=rank, count=world, stream=stream)
+
+    b.set_profiling(False)
+    for _ in range(args.warmup):
+        dev_step()
+    barrier()
+    b.set_profiling(True)
+    b.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        dev_step()
+    ev1.record()
+    barrier()
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.result()
+    st = b.get_stats()
+    b.set_profiling(False)
+    value = total_pairs * args.steps / (dev_ms * 1e-3)
+    # checksum so that the timed work is demonstrably the real work
+    chk = float(d_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
+
+    # roofline of the dominant (pair-tile) kernel on this rank
+    launches = max(1, st["pair_launches"])
+    pair_ms_per_launch = st["pair_ms"] / launches
+    flop_per_launch = 18.0 * nA * (st["pairs"] / launches)
+    achieved = flop_per_launch / (pair_ms_per_launch * 1e-3) / 1e12 if pair_ms_per_launch > 0 else 0.0
+    peak = max(b.measure_fp64_mma_peak(0), b.measure_fp64_mma_peak(3))
+    peaks_file = {}
+    try:
+        peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    roofline = {
+        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "frac": achieved / peak if peak > 0 else None, "traffic": None,
+        "kernel": "pair_kernel<fit,tri> (FP64 DMMA.8x8x4, 32x32 frame tiles)",
+        "peak_source": "FP64 tensor (DMMA) issue peak measured live by b200_measure_fp64_mma_peak; "
+                       "MEASURED_PEAKS.json holds no FP64 figure",
+        "launches": int(st["pair_launches"]), "avg_launch_ms": pair_ms_per_launch,
+        "kernel_share_of_step": st["pair_ms"] / (ev0.elapsed_time(ev1)) if dev_ms > 0 else None,
+        "frac_of_bf16_measured": (achieved / peaks_file["bf16_tflops_sustained"]) if peaks_file.get("bf16_tflops_sustained") else None,
+    }
+    gpu_launches = int(st["kernel_launches"])
+    del d_out
+    torch.cuda.empty_cache()
+
+    # =================== e2e: host buffers through the C ABI ===================
+    h_out = torch.empty(max(nelt, 1), dtype=torch.float32, pin_memory=True)
+    h_out_base = h_out.data_ptr() - 4 * first
+    L = b.lib()
+    p_crd = C.c_void_p(h_crd.data_ptr())
+    p_sel = sel.ctypes.data_as(C.c_void_p)
+    fe, ne = C.c_size_t(0), C.c_size_t(0)
+
+    def e2e_step():
+        rc = L.b200_rms2d_tri_shard(p_crd, stride, nF, None, nF, p_sel, nA, None, 1, rank, world,
+                                    C.c_void_p(h_out_base), C.byref(fe), C.byref(ne))
+        if rc:
+            raise RuntimeError(L.b200_last_error().decode())
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    b.reset_stats()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    st2 = b.get_stats()
+    e2e_value = total_pairs * args.steps / e2e_s
+    h2d = max_over_ranks(st2["h2d_bytes"] / args.steps)
+    d2h = max_over_ranks(st2["d2h_bytes"] / args.steps)
+    chk2 = float(h_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
+    if abs(chk - chk2) > 1e-3 * max(1.0, abs(chk)):
+        raise RuntimeError("device-resident and host-path results disagree: %r vs %r" % (chk, chk2))
+
+    # =================== CPU baseline (rank 0, N == 1 only) ===================
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            impl, kind, cores, nf, _ = cpu_pairs_rate(h_crd.numpy(), sel, args.cpu_seconds)
+            t0 = time.perf_counter()
+            ref_out = impl.rms2d_tri(h_crd.numpy()[:nf], sel)
+            dt = time.perf_counter() - t0
+            if kind == "reference":
+                dt = impl.last_loop_seconds()
+            cpu = {"value": nf * (nf - 1) / 2 / dt, "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "rms2d fit on the first %d of %d frames x %d atoms (%d pairs), %.1f s" % (nf, nF, nA, nf * (nf - 1) // 2, dt)}
+            # the bounded sample doubles as a parity spot check (rows < nf of shard 0)
+            n_chk = min(nf, r1)
+            if n_chk > 1:
+                idx = [nF * i - (i + 1) * i // 2 + np.arange(i + 1, nf) - i - 1 for i in range(min(n_chk, 64))]
+                got = np.concatenate([h_out.numpy()[ix - first] for ix in idx])
+                want = np.concatenate([ref_out[nf * i - (i + 1) * i // 2 + np.arange(i + 1, nf) - i - 1] for i in range(min(n_chk, 64))])
+                cpu["parity_max_abs_diff_A"] = float(np.abs(got.astype(np.float64) - want).max())
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the bench line
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%s: rms2d fit, %d frames x %d atoms, %d pairs" % (name, nF, nA, total_pairs),
+                       "sharding": "upper-triangle row bands, %d rank(s), no collective" % world,
+                       "l2": "inputs larger than L2 (packed planes %.0f MB, output %.0f MB per rank)" % (
+                           nF * round((nA + 15) // 16 * 16) * 24 / 1e6, nelt * 4 / 1e6),
+                       "seed": seed, "gen_seconds": round(t_gen, 2)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": 1e3 * e2e_s / args.steps, "api": "b200_rms2d_tri_shard, pinned host COORDS in, pinned host triangle out"},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "gpu_launches": gpu_launches,
+            "checksum": chk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    b.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

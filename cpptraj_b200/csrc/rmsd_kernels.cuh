@@ -1,0 +1,635 @@
+// rmsd_kernels.cuh -- sm_100a device code of the B200 best-fit RMSD path.
+//
+// Kernels (see DESIGN.md for the roofline of each):
+//   pack_kernel     float32 AoS COORDS -> centred, sqrt(mass)-scaled FP64 planes in a
+//                   fragment-major layout + per-frame G = sum m|x-c|^2.
+//                   Replaces CompactFrameArray::GetToMaskDblPtr (src/CompactFrameArray.cpp:244-262)
+//                   + Frame::CenterOnOrigin (src/Frame.cpp:1043-1055) + the target centring
+//                   of Frame::RMSD_CenteredRef (src/Frame.cpp:1141-1171), once per frame
+//                   instead of once per pair.
+//   pair_kernel     32x32 frame-pair tiles: the nine F x N . N x F covariance products
+//                   (src/Frame.cpp:1184-1208) as FP64 tensor-core MMAs fed by bulk-async
+//                   (TMA engine) copies through an mbarrier pipeline, with the per-pair
+//                   eigen-solve (src/Frame.cpp:1215-1268, src/Matrix_3x3.cpp:110-268)
+//                   fused into the tile epilogue and the float result stored straight
+//                   into cpptraj's Matrix<float> layout (src/Matrix.h:94-122).
+//   onevn_kernel    one-vs-many rmsd action body (src/Action_Rmsd.cpp:361-392): single
+//                   streaming pass, 13 FP64 accumulators per frame, optional U / Trans.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+// ----------------------------------------------------------------------------
+// Layout of the packed planes in HBM ("fragment-major"):
+//   element(frame f, atom k, plane p) lives at
+//     ((rg*nKb + kb)*3 + p)*128 + r*4 + kk      [doubles]
+//   rg = f/32, r = f%32, kb = k/4, kk = k%4, nKb = Kpad/4.
+// One (rg,kb) block is 3 planes x 32 frames x 4 atoms = 384 doubles = 3072 B and
+// contains, for every group of 8 frames, the 8x4 FP64 MMA operand fragment as
+// 256 contiguous bytes (lane l of a warp reads double l).  For a fixed rg the
+// blocks of consecutive kb are contiguous, so one K-chunk of a 32-frame tile is
+// a single contiguous 12 KB run: one cp.async.bulk per operand per stage.
+// ----------------------------------------------------------------------------
+constexpr int ROWG = 32;                 // frames per row group
+constexpr int KBLK = 4;                  // atoms per k-block (MMA k granularity)
+constexpr int KC = 16;                   // atoms per pipeline stage
+constexpr int KB_PER_CHUNK = KC / KBLK;  // 4
+constexpr int BLK_DBL = 3 * ROWG * KBLK; // 384 doubles per (rg,kb) block
+constexpr int RG_CHUNK_DBL = KB_PER_CHUNK * BLK_DBL;  // 1536 doubles = 12288 B
+constexpr int RG_CHUNK_BYTES = RG_CHUNK_DBL * 8;
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_THREADS = 128;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * 2 * RG_CHUNK_BYTES + 64;  // + mbarriers
+
+__host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+__host__ __device__ inline size_t plane_doubles(int Fpad, int Kpad) {
+  return (size_t)(Fpad / ROWG) * (size_t)(Kpad / KBLK) * BLK_DBL;
+}
+/// Triangle offset of row i's first element (i,i+1): src/Matrix.h:110-122.
+__host__ __device__ inline size_t tri_row_start(size_t n, size_t i) {
+  return n * i - (i * (i + 1)) / 2;
+}
+
+// ----------------------------------------------------------------------------
+// PTX helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+/// 1-D bulk asynchronous copy global -> shared through the TMA engine (SASS: UBLKCP),
+/// completion signalled on an mbarrier as transaction bytes.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// FP64 tensor-core MMAs.  Fragment layouts (g = lane/4, t = lane%4):
+//   m8n8k4 : a = A[g][t]; b = B[t][g]; c{0,1} = C[g][2t+{0,1}]
+//   m16n8kK: a[v0+2*v1] = A[g+8*v0][t+4*v1]; b[v1] = B[t+4*v1][g];
+//            c[e+2*h] = C[g+8*h][2t+e]
+__device__ __forceinline__ void mma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void mma_1684(double* c, double a0, double a1, double b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a0), "d"(a1), "d"(b0));
+}
+__device__ __forceinline__ void mma_1688(double* c, const double* a, const double* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+}
+__device__ __forceinline__ void mma_16816(double* c, const double* a, const double* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, "
+      "{%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+      : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]),
+        "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+// ----------------------------------------------------------------------------
+// Per-pair solve.
+// cpptraj: rms = sqrt(2*(E0 - sqrt|mu1| - sqrt|mu2| - sig3*sqrt|mu3|)/M) with mu the
+// eigenvalues of R R^T by Jacobi and sig3 the sign of det (src/Frame.cpp:1215-1268).
+// sigma1+sigma2+sig3*sigma3 is the largest eigenvalue of the 4x4 quaternion key
+// matrix of S, i.e. the largest root of
+//     P(l) = l^4 + c2 l^2 + c1 l + c0,
+//     c2 = -2 ||S||_F^2,  c1 = -8 det S,  c0 = 2 tr((S^T S)^2) - (tr S^T S)^2
+// (roots are s1+s2+s3', s1-s2-s3', -s1+s2-s3', -s1-s2+s3').  Newton from the upper
+// bound l0 = E0 converges monotonically; all arithmetic FP64.
+// ----------------------------------------------------------------------------
+struct Quartic {
+  double c2, c1, c0;
+};
+__device__ __forceinline__ Quartic quartic_of(const double* S) {
+  const double m00 = S[0] * S[0] + S[3] * S[3] + S[6] * S[6];
+  const double m11 = S[1] * S[1] + S[4] * S[4] + S[7] * S[7];
+  const double m22 = S[2] * S[2] + S[5] * S[5] + S[8] * S[8];
+  const double m01 = S[0] * S[1] + S[3] * S[4] + S[6] * S[7];
+  const double m02 = S[0] * S[2] + S[3] * S[5] + S[6] * S[8];
+  const double m12 = S[1] * S[2] + S[4] * S[5] + S[7] * S[8];
+  const double p1 = m00 + m11 + m22;
+  const double trM2 = m00 * m00 + m11 * m11 + m22 * m22 + 2.0 * (m01 * m01 + m02 * m02 + m12 * m12);
+  const double det = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) +
+                     S[2] * (S[3] * S[7] - S[4] * S[6]);
+  Quartic q;
+  q.c2 = -2.0 * p1;
+  q.c1 = -8.0 * det;
+  q.c0 = 2.0 * trM2 - p1 * p1;
+  return q;
+}
+__device__ __forceinline__ double largest_root(const Quartic& q, double e0) {
+  double lam = e0;
+#pragma unroll 1
+  for (int it = 0; it < 50; ++it) {
+    const double l2 = lam * lam;
+    const double b = (l2 + q.c2) * lam;
+    const double a = b + q.c1;
+    const double P = a * lam + q.c0;
+    const double dP = 2.0 * l2 * lam + b + a;
+    if (dP == 0.0) break;
+    const double d = P / dP;
+    lam -= d;
+    if (fabs(d) <= 1e-14 * fabs(lam)) break;
+  }
+  return lam;
+}
+/// Best-fit RMSD from the 3x3 covariance S, E0 = (Ga+Gb)/2 and total mass M.
+__device__ __forceinline__ double rmsd_fit_from_cov(const double* S, double e0, double invM) {
+  const Quartic q = quartic_of(S);
+  const double lam = largest_root(q, e0);
+  const double e = e0 - lam;
+  return (e < 0.0) ? 0.0 : sqrt(2.0 * e * invM);  // clamp: src/Frame.cpp:1264-1268
+}
+/// No-fit RMSD (src/Frame.cpp:1279-1307) from G's and the covariance trace.
+__device__ __forceinline__ double rmsd_nofit_from_trace(double tr, double ga, double gb, double invM) {
+  const double s = ga + gb - 2.0 * tr;
+  return (s < 0.0) ? 0.0 : sqrt(s * invM);
+}
+
+// ----------------------------------------------------------------------------
+// pack_kernel
+// One CTA per 32-frame row group, 8 warps x 4 frames.  Per frame a warp makes
+// two passes over the selected atoms (second pass hits L1/L2): centre (FP64
+// shuffle reduction), then centred/scaled values are written into the
+// fragment-major planes; padding atoms (k >= nAtoms) and padding frames are
+// written as zeros so the pair kernel needs no bounds checks in its main loop.
+// ----------------------------------------------------------------------------
+struct PackArgs {
+  const float* crd;        // device COORDS
+  size_t stride;           // floats per source frame
+  const int* frameIdx;     // nullable: source frame of output frame f
+  long srcBase;            // source row = frameIdx ? frameIdx[f] - srcBase : f - srcBase
+  int nFrames;             // valid output frames F
+  int f0;                  // first output frame of this launch (multiple of 32)
+  const int* atomIdx;      // nullable => identity
+  int nAtoms;
+  int Kpad;
+  const double* centerMass;  // nullable: weights for the centre
+  const double* covMass;     // nullable: planes scaled by sqrt(covMass)
+  const double* shift;       // 3 doubles (device); used when !fit
+  int fit;
+  double* planes;
+  double* G;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rg = a.f0 / ROWG + blockIdx.x;
+  const int nKb = a.Kpad / KBLK;
+  double* rgBase = a.planes + (size_t)rg * nKb * BLK_DBL;
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    const int f = rg * ROWG + r;
+    const bool valid = f < a.nFrames;
+    const float* src = nullptr;
+    if (valid) {
+      const long row = (a.frameIdx ? (long)a.frameIdx[f] : (long)f) - a.srcBase;
+      src = a.crd + (size_t)row * a.stride;
+    }
+    double cx = 0.0, cy = 0.0, cz = 0.0;
+    if (valid) {
+      if (a.fit) {
+        double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
+        for (int k = lane; k < a.nAtoms; k += 32) {
+          const int at = a.atomIdx ? a.atomIdx[k] : k;
+          const double m = a.centerMass ? a.centerMass[k] : 1.0;
+          const double x = (double)src[3 * (size_t)at], y = (double)src[3 * (size_t)at + 1],
+                       z = (double)src[3 * (size_t)at + 2];
+          sx += x * m; sy += y * m; sz += z * m; sm += m;
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sz = warp_sum(sz); sm = warp_sum(sm);
+        if (sm != 0.0) { cx = sx / sm; cy = sy / sm; cz = sz / sm; }
+      } else {
+        cx = a.shift[0]; cy = a.shift[1]; cz = a.shift[2];
+      }
+    }
+    double g = 0.0;
+    for (int k = lane; k < a.Kpad; k += 32) {
+      double x = 0.0, y = 0.0, z = 0.0;
+      if (valid && k < a.nAtoms) {
+        const int at = a.atomIdx ? a.atomIdx[k] : k;
+        const double w = a.covMass ? sqrt(a.covMass[k]) : 1.0;
+        x = ((double)src[3 * (size_t)at] - cx) * w;
+        y = ((double)src[3 * (size_t)at + 1] - cy) * w;
+        z = ((double)src[3 * (size_t)at + 2] - cz) * w;
+        g += x * x + y * y + z * z;
+      }
+      double* blk = rgBase + (size_t)(k >> 2) * BLK_DBL + r * KBLK + (k & 3);
+      blk[0] = x;
+      blk[ROWG * KBLK] = y;
+      blk[2 * ROWG * KBLK] = z;
+    }
+    g = warp_sum(g);
+    if (lane == 0) a.G[f] = g;
+  }
+}
+
+/// shift[0..2] = position of the first selected atom of the first frame (no-fit mode:
+/// a common origin keeps |x| small so G_i + G_j - 2 tr(S) loses no digits).
+__global__ void shift_kernel(const float* crd, size_t stride, const int* frameIdx, long srcBase, int fFirst,
+                             const int* atomIdx, double* shift) {
+  const long row = (frameIdx ? (long)frameIdx[fFirst] : (long)fFirst) - srcBase;
+  const int at = atomIdx ? atomIdx[0] : 0;
+  const float* s = crd + (size_t)row * stride + 3 * (size_t)at;
+  shift[0] = (double)s[0]; shift[1] = (double)s[1]; shift[2] = (double)s[2];
+}
+/// totalMass[0] = sum of mass (or nAtoms)
+__global__ void mass_sum_kernel(const double* mass, int n, double* total) {
+  double s = 0.0;
+  for (int k = threadIdx.x; k < n; k += 32) s += mass ? mass[k] : 1.0;
+  s = warp_sum(s);
+  if (threadIdx.x == 0) total[0] = s;
+}
+
+// ----------------------------------------------------------------------------
+// pair_kernel
+// ----------------------------------------------------------------------------
+struct PairArgs {
+  const double* PA;   // planes of the row frames (i)
+  const double* PB;   // planes of the column frames (j)
+  const double* GA;
+  const double* GB;
+  int nKb;            // Kpad/4
+  int nRows;          // valid i frames
+  int nCols;          // valid j frames
+  int rg0;            // first row group (i tiles) of this launch
+  int nRgI;           // number of i row groups in this launch
+  int cg0;            // first column group covered by blockIdx.x == 0
+  const double* totalMass;  // device scalar
+  float* out;         // TRI: base such that out[triIndex - outBase]; FULL: out[i*ldo + j]
+  size_t outBase;
+  size_t ldo;
+};
+
+template <int VAR, bool FIT, bool TRI>
+__global__ void __launch_bounds__(PAIR_THREADS, 2) pair_kernel(PairArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + PAIR_STAGES * 2 * RG_CHUNK_BYTES);
+
+  const int it = a.rg0 + blockIdx.y;        // i row group
+  const int jt = a.cg0 + blockIdx.x;        // j row group
+  if (TRI && jt < it) return;               // below the diagonal: nothing to do
+  if (jt * ROWG >= a.nCols) return;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wi = warp >> 1, wj = warp & 1;
+  const int nChunks = a.nKb / KB_PER_CHUNK;
+  const double* gA = a.PA + (size_t)it * a.nKb * BLK_DBL;
+  const double* gB = a.PB + (size_t)jt * a.nKb * BLK_DBL;
+
+  if (tid == 0) {
+    for (int s = 0; s < PAIR_STAGES; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int c) {
+    const int s = c % PAIR_STAGES;
+    const uint32_t bar = smem_u32(&bars[s]);
+    mbar_expect_tx(bar, 2 * RG_CHUNK_BYTES);
+    bulk_g2s(smem_u32(smem + (size_t)s * 2 * RG_CHUNK_DBL), gA + (size_t)c * RG_CHUNK_DBL, RG_CHUNK_BYTES, bar);
+    bulk_g2s(smem_u32(smem + (size_t)s * 2 * RG_CHUNK_DBL + RG_CHUNK_DBL), gB + (size_t)c * RG_CHUNK_DBL,
+             RG_CHUNK_BYTES, bar);
+  };
+  if (tid == 0) {
+    for (int c = 0; c < PAIR_STAGES - 1 && c < nChunks; ++c) issue(c);
+  }
+
+  constexpr int NP = FIT ? 9 : 3;
+  double acc[NP][2][4];
+#pragma unroll
+  for (int x = 0; x < NP; ++x)
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[x][n][e] = 0.0;
+
+  // number of k-blocks consumed per MMA step
+  constexpr int KB_STEP = (VAR <= 1) ? 1 : (VAR == 2 ? 2 : 4);
+
+  for (int c = 0; c < nChunks; ++c) {
+    if (tid == 0 && c + PAIR_STAGES - 1 < nChunks) issue(c + PAIR_STAGES - 1);
+    const int s = c % PAIR_STAGES;
+    mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / PAIR_STAGES) & 1));
+    const double* sA = smem + (size_t)s * 2 * RG_CHUNK_DBL + (wi * 2) * 32 + lane;
+    const double* sB = smem + (size_t)s * 2 * RG_CHUNK_DBL + RG_CHUNK_DBL + (wj * 2) * 32 + lane;
+#pragma unroll
+    for (int kb = 0; kb < KB_PER_CHUNK; kb += KB_STEP) {
+      // fragments: fa[p][v1][v0], fb[q][nj][v1]
+      double fa[3][KB_STEP][2], fb[3][2][KB_STEP];
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int v1 = 0; v1 < KB_STEP; ++v1) {
+          fa[p][v1][0] = sA[((kb + v1) * 3 + p) * 128];
+          fa[p][v1][1] = sA[((kb + v1) * 3 + p) * 128 + 32];
+          fb[p][0][v1] = sB[((kb + v1) * 3 + p) * 128];
+          fb[p][1][v1] = sB[((kb + v1) * 3 + p) * 128 + 32];
+        }
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if (!FIT && p != q) continue;
+          const int x = FIT ? (p * 3 + q) : p;
+#pragma unroll
+          for (int nj = 0; nj < 2; ++nj) {
+            if constexpr (VAR == 0) {
+              mma_884(acc[x][nj][0], acc[x][nj][1], fa[p][0][0], fb[q][nj][0]);
+              mma_884(acc[x][nj][2], acc[x][nj][3], fa[p][0][1], fb[q][nj][0]);
+            } else if constexpr (VAR == 1) {
+              mma_1684(acc[x][nj], fa[p][0][0], fa[p][0][1], fb[q][nj][0]);
+            } else if constexpr (VAR == 2) {
+              mma_1688(acc[x][nj], &fa[p][0][0], &fb[q][nj][0]);
+            } else {
+              mma_16816(acc[x][nj], &fa[p][0][0], &fb[q][nj][0]);
+            }
+          }
+        }
+    }
+    __syncthreads();  // everyone is done with stage s before it is refilled
+  }
+
+  // ---- epilogue: per-pair solve, straight into cpptraj's matrix layout ----
+  const double invM = 1.0 / a.totalMass[0];
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nj = 0; nj < 2; ++nj)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = it * ROWG + wi * 16 + h * 8 + g;
+        const int j = jt * ROWG + wj * 16 + nj * 8 + 2 * t + e;
+        if (i >= a.nRows || j >= a.nCols) continue;
+        if (TRI && j <= i) continue;
+        const double ga = a.GA[i], gb = a.GB[j];
+        double r;
+        if (FIT) {
+          double S[9];
+#pragma unroll
+          for (int x = 0; x < 9; ++x) S[x] = acc[FIT ? x : 0][nj][e + 2 * h];
+          r = rmsd_fit_from_cov(S, 0.5 * (ga + gb), invM);
+        } else {
+          r = rmsd_nofit_from_trace(acc[0][nj][e + 2 * h] + acc[1][nj][e + 2 * h] + acc[2][nj][e + 2 * h], ga,
+                                    gb, invM);
+        }
+        size_t idx;
+        if (TRI)
+          idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
+        else
+          idx = (size_t)i * a.ldo + (size_t)j;
+        a.out[idx] = (float)r;
+      }
+}
+
+// ----------------------------------------------------------------------------
+// onevn_kernel: FB frames per CTA share each reference load.
+//   S = sum m (x - c) r^T = sum m x r^T - c (sum m r)^T,   G_t = sum m |x|^2 - M |c|^2
+// computed relative to the frame's first selected atom so the subtraction loses
+// no digits.  T = float (COORDS) or double (cpptraj Frame).
+// ----------------------------------------------------------------------------
+constexpr int ONEVN_FB = 4;
+constexpr int ONEVN_THREADS = 256;
+
+struct OneVNArgs {
+  const void* crd;
+  size_t stride;            // elements per frame
+  int nFrames;
+  const int* atomIdx;       // nullable
+  int nAtoms;
+  const double* refw;       // 4 doubles per atom: rx, ry, rz, m   (ref as given)
+  const double* refsum;     // [0..2] = sum m r, [3] = M, [4] = sum m |r|^2
+  int fit;
+  double* rmsd;
+  double* rot;              // nullable, 9 per frame
+  double* trans;            // nullable, 3 per frame
+};
+
+/// Rotation U (row-major, x' = U x as applied by Frame::Trans_Rot_Trans, src/Frame.h:572-581)
+/// from the covariance S[a][b] = sum m xt_a xr_b and its largest quartic root lam:
+/// eigenvector of the key matrix via the adjugate of (K - lam I), most stable column.
+__device__ inline void rotation_from_cov(const double* S, double lam, double* U) {
+  const double Sxx = S[0], Sxy = S[1], Sxz = S[2], Syx = S[3], Syy = S[4], Syz = S[5], Szx = S[6],
+               Szy = S[7], Szz = S[8];
+  // Key matrix for rotating the TARGET onto the REFERENCE.
+  double K[4][4];
+  K[0][0] = Sxx + Syy + Szz - lam;
+  K[0][1] = K[1][0] = Syz - Szy;
+  K[0][2] = K[2][0] = Szx - Sxz;
+  K[0][3] = K[3][0] = Sxy - Syx;
+  K[1][1] = Sxx - Syy - Szz - lam;
+  K[1][2] = K[2][1] = Sxy + Syx;
+  K[1][3] = K[3][1] = Szx + Sxz;
+  K[2][2] = -Sxx + Syy - Szz - lam;
+  K[2][3] = K[3][2] = Syz + Szy;
+  K[3][3] = -Sxx - Syy + Szz - lam;
+  // adjugate columns (cofactors); pick the column with the largest norm
+  double best[4] = {1.0, 0.0, 0.0, 0.0}, bestn = -1.0;
+  for (int col = 0; col < 4; ++col) {
+    double v[4];
+    for (int row = 0; row < 4; ++row) {
+      // cofactor C[col][row] = (-1)^(row+col) * minor(col,row); adj = C^T, K symmetric
+      int rI[3], cI[3], n = 0, m = 0;
+      for (int x = 0; x < 4; ++x) if (x != col) rI[n++] = x;
+      for (int x = 0; x < 4; ++x) if (x != row) cI[m++] = x;
+      const double d = K[rI[0]][cI[0]] * (K[rI[1]][cI[1]] * K[rI[2]][cI[2]] - K[rI[1]][cI[2]] * K[rI[2]][cI[1]]) -
+                       K[rI[0]][cI[1]] * (K[rI[1]][cI[0]] * K[rI[2]][cI[2]] - K[rI[1]][cI[2]] * K[rI[2]][cI[0]]) +
+                       K[rI[0]][cI[2]] * (K[rI[1]][cI[0]] * K[rI[2]][cI[1]] - K[rI[1]][cI[1]] * K[rI[2]][cI[0]]);
+      v[row] = ((row + col) & 1) ? -d : d;
+    }
+    const double nn = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+    if (nn > bestn) { bestn = nn; best[0] = v[0]; best[1] = v[1]; best[2] = v[2]; best[3] = v[3]; }
+  }
+  double q0 = best[0], q1 = best[1], q2 = best[2], q3 = best[3];
+  const double nrm = sqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+  if (nrm > 0.0) { q0 /= nrm; q1 /= nrm; q2 /= nrm; q3 /= nrm; } else { q0 = 1.0; q1 = q2 = q3 = 0.0; }
+  const double a2 = q0 * q0, x2 = q1 * q1, y2 = q2 * q2, z2 = q3 * q3;
+  const double xy = q1 * q2, az = q0 * q3, zx = q3 * q1, ay = q0 * q2, yz = q2 * q3, ax = q0 * q1;
+  U[0] = a2 + x2 - y2 - z2; U[1] = 2 * (xy - az);      U[2] = 2 * (zx + ay);
+  U[3] = 2 * (xy + az);     U[4] = a2 - x2 + y2 - z2;  U[5] = 2 * (yz - ax);
+  U[6] = 2 * (zx - ay);     U[7] = 2 * (yz + ax);      U[8] = a2 - x2 - y2 + z2;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
+  __shared__ double red[ONEVN_THREADS / 32][ONEVN_FB][14];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fbase = blockIdx.x * ONEVN_FB;
+  const T* crd = reinterpret_cast<const T*>(a.crd);
+  const T* src[ONEVN_FB];
+  double o[ONEVN_FB][3];
+  const int at0 = a.atomIdx ? a.atomIdx[0] : 0;
+#pragma unroll
+  for (int f = 0; f < ONEVN_FB; ++f) {
+    const int fr = min(fbase + f, a.nFrames - 1);
+    src[f] = crd + (size_t)fr * a.stride;
+    o[f][0] = (double)src[f][3 * (size_t)at0];
+    o[f][1] = (double)src[f][3 * (size_t)at0 + 1];
+    o[f][2] = (double)src[f][3 * (size_t)at0 + 2];
+  }
+  // acc[f][0..8] = sum m x_a r_b (fit) ; [9..11] = sum m x ; [12] = sum m |x|^2
+  // nofit: [0] = sum m |r - x|^2 (direct, as the reference does)
+  double acc[ONEVN_FB][13];
+#pragma unroll
+  for (int f = 0; f < ONEVN_FB; ++f)
+#pragma unroll
+    for (int x = 0; x < 13; ++x) acc[f][x] = 0.0;
+
+  for (int k = tid; k < a.nAtoms; k += ONEVN_THREADS) {
+    const int at = a.atomIdx ? a.atomIdx[k] : k;
+    const double4 rw = reinterpret_cast<const double4*>(a.refw)[k];
+#pragma unroll
+    for (int f = 0; f < ONEVN_FB; ++f) {
+      const T* p = src[f] + 3 * (size_t)at;
+      if (a.fit) {
+        const double x = (double)p[0] - o[f][0], y = (double)p[1] - o[f][1], z = (double)p[2] - o[f][2];
+        const double mx = rw.w * x, my = rw.w * y, mz = rw.w * z;
+        acc[f][0] += mx * rw.x; acc[f][1] += mx * rw.y; acc[f][2] += mx * rw.z;
+        acc[f][3] += my * rw.x; acc[f][4] += my * rw.y; acc[f][5] += my * rw.z;
+        acc[f][6] += mz * rw.x; acc[f][7] += mz * rw.y; acc[f][8] += mz * rw.z;
+        acc[f][9] += mx; acc[f][10] += my; acc[f][11] += mz;
+        acc[f][12] += mx * x + my * y + mz * z;
+      } else {
+        const double dx = rw.x - (double)p[0], dy = rw.y - (double)p[1], dz = rw.z - (double)p[2];
+        acc[f][0] += rw.w * (dx * dx + dy * dy + dz * dz);
+      }
+    }
+  }
+  const int nred = a.fit ? 13 : 1;
+#pragma unroll
+  for (int f = 0; f < ONEVN_FB; ++f)
+    for (int x = 0; x < nred; ++x) {
+      const double v = warp_sum(acc[f][x]);
+      if (lane == 0) red[warp][f][x] = v;
+    }
+  __syncthreads();
+  if (tid < ONEVN_FB) {
+    const int f = tid, fr = fbase + f;
+    if (fr < a.nFrames) {
+      double v[13];
+      for (int x = 0; x < nred; ++x) {
+        double s = 0.0;
+        for (int w = 0; w < ONEVN_THREADS / 32; ++w) s += red[w][f][x];
+        v[x] = s;
+      }
+      const double M = a.refsum[3];
+      if (!a.fit) {
+        a.rmsd[fr] = (v[0] < 0.0) ? 0.0 : sqrt(v[0] / M);
+      } else {
+        // centre relative to the frame origin o
+        const double cx = v[9] / M, cy = v[10] / M, cz = v[11] / M;
+        double S[9];
+        S[0] = v[0] - cx * a.refsum[0]; S[1] = v[1] - cx * a.refsum[1]; S[2] = v[2] - cx * a.refsum[2];
+        S[3] = v[3] - cy * a.refsum[0]; S[4] = v[4] - cy * a.refsum[1]; S[5] = v[5] - cy * a.refsum[2];
+        S[6] = v[6] - cz * a.refsum[0]; S[7] = v[7] - cz * a.refsum[1]; S[8] = v[8] - cz * a.refsum[2];
+        const double gt = v[12] - M * (cx * cx + cy * cy + cz * cz);
+        const double e0 = 0.5 * (gt + a.refsum[4]);
+        const Quartic q = quartic_of(S);
+        const double lam = largest_root(q, e0);
+        const double e = e0 - lam;
+        a.rmsd[fr] = (e < 0.0) ? 0.0 : sqrt(2.0 * e / M);
+        if (a.rot) rotation_from_cov(S, lam, a.rot + 9 * (size_t)fr);
+        if (a.trans) {
+          // Trans = -(centre of the target) in absolute coordinates (src/Frame.cpp:1164-1170)
+          a.trans[3 * (size_t)fr] = -(cx + o[f][0]);
+          a.trans[3 * (size_t)fr + 1] = -(cy + o[f][1]);
+          a.trans[3 * (size_t)fr + 2] = -(cz + o[f][2]);
+        }
+      }
+    }
+  }
+}
+
+/// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One warp.
+__global__ void onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum) {
+  double s0 = 0, s1 = 0, s2 = 0, sm = 0, sg = 0;
+  for (int k = threadIdx.x; k < n; k += 32) {
+    const double m = mass ? mass[k] : 1.0;
+    const double x = ref[3 * k], y = ref[3 * k + 1], z = ref[3 * k + 2];
+    refw[4 * k] = x; refw[4 * k + 1] = y; refw[4 * k + 2] = z; refw[4 * k + 3] = m;
+    s0 += m * x; s1 += m * y; s2 += m * z; sm += m; sg += m * (x * x + y * y + z * z);
+  }
+  s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sm = warp_sum(sm); sg = warp_sum(sg);
+  if (threadIdx.x == 0) { refsum[0] = s0; refsum[1] = s1; refsum[2] = s2; refsum[3] = sm; refsum[4] = sg; }
+}
+
+// ----------------------------------------------------------------------------
+// FP64 MMA issue-peak probe (register-only): roofline denominator for pair_kernel.
+// ----------------------------------------------------------------------------
+template <int VAR>
+__global__ void __launch_bounds__(128) fp64_mma_peak_kernel(double* sink, int iters) {
+  double c[12][4];
+#pragma unroll
+  for (int x = 0; x < 12; ++x)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) c[x][e] = 0.0;
+  double a[8], b[4];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a[e] = 1.0 + threadIdx.x * 1e-9 + e;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) b[e] = 0.5 + e;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int x = 0; x < 12; ++x) {
+      if constexpr (VAR == 0) { mma_884(c[x][0], c[x][1], a[0], b[0]); mma_884(c[x][2], c[x][3], a[1], b[0]); }
+      else if constexpr (VAR == 1) mma_1684(c[x], a[0], a[1], b[0]);
+      else if constexpr (VAR == 2) mma_1688(c[x], a, b);
+      else if constexpr (VAR == 3) mma_16816(c[x], a, b);
+      else {  // VAR 4: plain DFMA, 12 x 4 independent chains
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[x][e] = fma(a[e], b[e], c[x][e]);
+      }
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int x = 0; x < 12; ++x)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s += c[x][e];
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace b200

@@ -1,0 +1,171 @@
+/* b200_rmsd.h -- C ABI of the B200-native best-fit RMSD path for cpptraj.
+ *
+ * This is the drop-in boundary: plain pointers and
+ * sizes, no C++/torch types, no exceptions.  cpptraj keeps parsing commands,
+ * masks and owning DataSets; inside its three RMSD plugins the new host code
+ * (src/cuda_b200/) calls these entry points instead of the
+ * OpenMP pair loops.  File:line citations are relative to the cpptraj tree.
+ *
+ * Conventions
+ *   - all `crd` pointers are cpptraj COORDS storage: float32, one frame per
+ *     `frameStrideFloats` floats, position component first, xyz interleaved
+ *     (CompactFrameArray, src/CompactFrameArray.cpp:110-147,244-262);
+ *   - `atomIdx` is AtomMask::Selected() (src/AtomMask.h:32): atom numbers,
+ *     the library reads crd[frame*stride + 3*atomIdx[k] + {0,1,2}];
+ *   - `mass` is one double per SELECTED atom (Frame::SetupFrameFromMask,
+ *     src/Frame.cpp:502-512) or NULL for unit weights ("mass" keyword absent);
+ *   - `fit` != 0: best-fit RMSD (Frame::RMSD_CenteredRef, src/Frame.cpp:1137),
+ *     `fit` == 0: no-fit RMSD (Frame::RMSD_NoFit, src/Frame.cpp:1279);
+ *   - every function returns B200_OK (0) or a B200_ERR_* code; the message is
+ *     available from b200_last_error().  The caller maps non-zero to
+ *     mprinterr + Analysis::ERR / Action::ERR (src/Analysis.h:81, src/Action.h:32);
+ *   - the caller owns every host buffer; the library owns device memory,
+ *     streams and pinned staging.  Calls are blocking and must come from
+ *     outside any OpenMP region.  There is NO CPU fallback: without a usable
+ *     sm_100 device every compute entry point fails with B200_ERR_NO_DEVICE.
+ */
+#ifndef B200_RMSD_H
+#define B200_RMSD_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_NO_DEVICE 1 /* no CUDA device / not initialised            */
+#define B200_ERR_CUDA 2      /* a CUDA runtime call failed                   */
+#define B200_ERR_ARG 3       /* invalid argument                             */
+#define B200_ERR_NOMEM 4     /* host or device allocation failed             */
+#define B200_ERR_STATE 5     /* call sequence error on a streaming handle    */
+
+/* ---- lifetime -------------------------------------------------------------
+ * Device probe at first use, like src/Cpptraj.cpp:120-135,168-179 does for the
+ * existing CUDA build.  ngpu_requested <= 0 means "all visible devices".
+ * b200_init may be called again to change the device count. */
+int b200_init(int ngpu_requested, int* ngpu_used);
+/* Same, with explicit CUDA device ordinals (one process per GPU: pass LOCAL_RANK). */
+int b200_init_devices(const int* deviceIds, int n);
+void b200_shutdown(void);
+const char* b200_last_error(void);
+int b200_version(void);
+int b200_num_devices(void);
+
+/* ---- rms2d / pairwise cache: triangle -------------------------------------
+ * Replaces the pair loops of Analysis_Rms2d::Calculate_2D when
+ * !calculateFullMatrix (src/Analysis_Rms2d.cpp:247-287) and of
+ * MetricArray::calcFrameDistances (src/Cluster/MetricArray.cpp:777-795;
+ * frameIdx = framesToCache.Ptr(), src/Cluster/Cframes.h:31).
+ * frameIdx NULL means frames 0..nFrames-1.  outTri is Matrix<float>::Ptr() of
+ * a TRIANGLE matrix of nFrames columns: element (i<j) at
+ * nFrames*i - i*(i+1)/2 + j - i - 1 (src/Matrix.h:110-122).
+ * Work is split over all initialised devices. */
+int b200_rms2d_tri(const float* crd, size_t frameStrideFloats, int nFramesTotal,
+                   const int* frameIdx, int nFrames,
+                   const int* atomIdx, int nAtoms,
+                   const double* mass, int fit, float* outTri);
+
+/* Same, but computes only shard `shardRank` of `shardCount` on the CURRENT
+ * process's device 0 (one process per GPU, e.g. under torchrun / MPI).  The
+ * shard is a contiguous band of matrix rows, hence a contiguous range
+ * [*firstElt, *firstElt + *nElts) of outTri; elements outside are untouched.
+ * outTri may be NULL to query the range only. */
+int b200_rms2d_tri_shard(const float* crd, size_t frameStrideFloats, int nFramesTotal,
+                         const int* frameIdx, int nFrames,
+                         const int* atomIdx, int nAtoms,
+                         const double* mass, int fit,
+                         int shardRank, int shardCount,
+                         float* outTri, size_t* firstElt, size_t* nElts);
+
+/* ---- rms2d: full matrix ------------------------------------------------------
+ * Calculate_2D when calculateFullMatrix (reftraj and/or tgt mask != ref mask,
+ * src/Analysis_Rms2d.cpp:204-209).  outFull[itgt*nRef + iref]
+ * (Allocate2D(totalref,totaltgt), src/Matrix.h:94-96).  massTgt weights the
+ * covariance and total mass (target frame's Mass_, src/Frame.cpp:1184-1208);
+ * massRefCentering is used only to centre each reference frame
+ * (SelectedRef.CenterOnOrigin, src/Analysis_Rms2d.cpp:265-266).  Both NULL
+ * when the "mass" keyword is absent. */
+int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* atomIdxTgt,
+                    const float* crdRef, size_t strideRef, int nRef, const int* atomIdxRef,
+                    int nAtoms, const double* massTgt, const double* massRefCentering,
+                    int fit, float* outFull);
+
+/* ---- rmsd action: one-vs-many, streaming ------------------------------------
+ * Action_Rmsd::{Setup,DoAction,Print} (src/Action_Rmsd.cpp:321-417).
+ * refSelected: the selected reference atoms (3*nAtoms doubles) exactly as
+ * ReferenceAction holds them in SelectedRef(): already centred on the origin
+ * when fitting (src/ReferenceAction.cpp:155-169), raw when fit == 0.
+ * Frames are pushed in chunks, either as cpptraj Frame coordinates (double,
+ * all atoms, xyz interleaved: Frame::xAddress()) or as COORDS storage (float).
+ * Results come back in push order (DataSet_double::Add is append-only,
+ * src/DataSet_double.cpp:14-20): rmsdOut[n]; rotOut[9n] = the rotation U of
+ * RMSD_CenteredRef row-major (NULL if not wanted); transOut[3n] = the
+ * target->origin translation "Trans" (NULL if not wanted). */
+typedef struct b200_1vN b200_1vN;
+int b200_rmsd_1vN_begin(const double* refSelected, const int* atomIdx, int nAtoms,
+                        const double* mass, int fit, int wantRot, b200_1vN** handle);
+int b200_rmsd_1vN_push_f64(b200_1vN* h, const double* xyz, size_t frameStrideDoubles, int nFrames);
+int b200_rmsd_1vN_push_f32(b200_1vN* h, const float* crd, size_t frameStrideFloats, int nFrames);
+/* Number of frames pushed and not yet flushed. */
+long b200_rmsd_1vN_pending(const b200_1vN* h);
+/* Blocks until all pushed frames are done; argminFrame (nullable) receives the
+ * index (over ALL frames pushed since begin) of the smallest RMSD so far,
+ * first one wins on ties. */
+int b200_rmsd_1vN_flush(b200_1vN* h, double* rmsdOut, double* rotOut, double* transOut,
+                        long* argminFrame);
+int b200_rmsd_1vN_end(b200_1vN* h);
+
+/* ---- device-resident variants (benchmarks, pipelines that keep COORDS in HBM)
+ * All pointers are DEVICE pointers on the current device; `stream` is a
+ * cudaStream_t (NULL = default stream); asynchronous w.r.t. the host.
+ * d_outTri holds the whole triangle (nFrames*(nFrames-1)/2 floats). */
+int b200_dev_rms2d_tri(const float* d_crd, size_t frameStrideFloats,
+                       const int* d_frameIdx, int nFrames,
+                       const int* d_atomIdx, int nAtoms,
+                       const double* d_mass, int fit,
+                       int shardRank, int shardCount,
+                       float* d_outTri, void* stream);
+int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
+                      const int* d_atomIdx, int nAtoms,
+                      const double* d_refSelected, const double* d_mass, int fit,
+                      double* d_rmsdOut, double* d_rotOut, double* d_transOut, void* stream);
+
+/* ---- shard geometry (host only, no device needed) -----------------------------
+ * Rows [*row0,*row1) of the nFrames x nFrames triangle owned by a shard:
+ * contiguous, 32-row aligned, balanced by pair count. */
+int b200_shard_rows(int nFrames, int shardRank, int shardCount, int* row0, int* row1);
+
+/* ---- instrumentation -------------------------------------------------------------
+ * When profiling is enabled the library brackets its kernels with CUDA events
+ * on the streams it launches on and accumulates per-kernel device time. */
+typedef struct b200_stats {
+  double pack_ms;        /* centring/packing kernel                           */
+  double pair_ms;        /* pair-tile kernel (sum over launches)              */
+  double onevn_ms;       /* one-vs-many kernel                                */
+  long   pack_launches;
+  long   pair_launches;
+  long   onevn_launches;
+  double pairs;          /* pair RMSDs produced                               */
+  double frames_1vN;     /* frames processed by the one-vs-many kernel        */
+  double h2d_bytes;
+  double d2h_bytes;
+  long   kernel_launches; /* every kernel this library launched (all kinds)     */
+} b200_stats;
+void b200_set_profiling(int on);
+void b200_reset_stats(void);
+void b200_get_stats(b200_stats* out);
+
+/* Tuning knob: PTX shape used for the FP64 MMAs of the pair kernel
+ * (0 m8n8k4, 1 m16n8k4, 2 m16n8k8, 3 m16n8k16; all lower to DMMA.8x8x4 SASS). */
+int b200_set_mma_variant(int variant);
+
+/* Measures this device's FP64 tensor (DMMA) issue peak with a register-only
+ * mma.sync loop; returns TFLOP/s (<=0 on error).  Used as the roofline
+ * denominator for the pair-tile kernel because MEASURED_PEAKS.json holds no
+ * FP64 figure. */
+double b200_measure_fp64_mma_peak(int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

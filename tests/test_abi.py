@@ -1,0 +1,82 @@
+"""CPU-only: the C-ABI library loads without a GPU and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "b200_rmsd.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200_[a-z0-9_A-Z]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built):
+    import cpptraj_b200 as b
+    L = ctypes.CDLL(b.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "missing export %s" % s
+
+
+def test_no_torch_types_in_header():
+    src = open(os.path.join(ROOT, "include", "b200_rmsd.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)     # declarations only, comments stripped
+    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "&" not in code
+
+
+def test_library_does_not_link_oracle(built):
+    """The product must not route through the CPU checker."""
+    import subprocess
+    import cpptraj_b200 as b
+    out = subprocess.run(["ldd", b.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    assert "oracle" not in out and "cpptraj_ref" not in out
+    blob = open(b.LIB_PATH, "rb").read()
+    assert b"orc_rms2d" not in blob and b"ref_rms2d" not in blob
+
+
+def test_shard_rows_partition_and_balance(built):
+    import cpptraj_b200 as b
+    for n in (0, 1, 2, 31, 32, 33, 1000, 10000, 100000):
+        for cnt in (1, 2, 4, 8):
+            prev = 0
+            pairs = []
+            for r in range(cnt):
+                a, e = b.shard_rows(n, r, cnt)
+                assert a == prev and e >= a and (a % 32 == 0 or a == n) and (e % 32 == 0 or e == n)
+                prev = e
+                pairs.append(((n - 1 - a) + (n - e)) * (e - a) / 2 if e > a else 0)
+            assert prev == n
+            if n >= 10000:
+                assert max(pairs) / (sum(pairs) / cnt) < 1.12, (n, cnt, pairs)
+
+
+def test_shard_query_without_device(built):
+    import cpptraj_b200 as b
+    crd = np.zeros((100, 30), np.float32)
+    sel = np.arange(10, dtype=np.int32)
+    tot = 0
+    first_expected = 0
+    for r in range(4):
+        _, first, n = b.rms2d_tri_shard(crd, sel, r, 4, query_only=True)
+        assert first == first_expected
+        first_expected += n
+        tot += n
+    assert tot == b.tri_size(100)
+
+
+def test_fails_loudly_without_gpu(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cpptraj_b200 as b
+    with pytest.raises(b.B200Error) as ei:
+        b.init(1)
+    assert ei.value.code == 1
+    with pytest.raises(b.B200Error):
+        b.rms2d_tri(np.zeros((4, 9), np.float32), np.arange(3, dtype=np.int32))
