@@ -152,26 +152,69 @@ __device__ __forceinline__ Quartic quartic_of(const double* S) {
   q.c0 = 2.0 * trM2 - p1 * p1;
   return q;
 }
-__device__ __forceinline__ double largest_root(const Quartic& q, double e0) {
-  double lam = e0;
+/// Robust path for (near-)double roots of the quartic (collinear / 2-atom selections, or
+/// s2 ~ -s3'): singular values of S by one-sided Jacobi (no squaring of the condition number),
+/// lambda_max = s1 + s2 + sign(det S) * s3.  Rarely taken; deliberately not inlined.
+__device__ __noinline__ double lambda_by_svd(const double* S) {
+  double a[3][3];  // a[c] = column c of S
+#pragma unroll
+  for (int c = 0; c < 3; ++c) { a[c][0] = S[c]; a[c][1] = S[3 + c]; a[c][2] = S[6 + c]; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = (pq == 2) ? 1 : 0, q = (pq == 0) ? 1 : 2;
+      const double al = a[p][0] * a[p][0] + a[p][1] * a[p][1] + a[p][2] * a[p][2];
+      const double be = a[q][0] * a[q][0] + a[q][1] * a[q][1] + a[q][2] * a[q][2];
+      const double ga = a[p][0] * a[q][0] + a[p][1] * a[q][1] + a[p][2] * a[q][2];
+      if (ga != 0.0 && fabs(ga) > 1e-17 * sqrt(al * be)) {
+        const double zeta = (be - al) / (2.0 * ga);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const double x = a[p][r], y = a[q][r];
+          a[p][r] = c * x - sn * y;
+          a[q][r] = sn * x + c * y;
+        }
+        rotated = true;
+      }
+    }
+    if (!rotated) break;
+  }
+  double s0 = sqrt(a[0][0] * a[0][0] + a[0][1] * a[0][1] + a[0][2] * a[0][2]);
+  double s1 = sqrt(a[1][0] * a[1][0] + a[1][1] * a[1][1] + a[1][2] * a[1][2]);
+  double s2 = sqrt(a[2][0] * a[2][0] + a[2][1] * a[2][1] + a[2][2] * a[2][2]);
+  const double smin = fmin(s0, fmin(s1, s2));
+  const double det = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) +
+                     S[2] * (S[3] * S[7] - S[4] * S[6]);
+  return (s0 + s1 + s2) - ((det < 0.0) ? 2.0 * smin : 0.0);
+}
+
+__device__ __forceinline__ double largest_root(const Quartic& q, double e0, const double* S) {
+  double lam = e0, dP = 0.0;
+  bool converged = false;
 #pragma unroll 1
   for (int it = 0; it < 50; ++it) {
     const double l2 = lam * lam;
     const double b = (l2 + q.c2) * lam;
     const double a = b + q.c1;
     const double P = a * lam + q.c0;
-    const double dP = 2.0 * l2 * lam + b + a;
+    dP = 2.0 * l2 * lam + b + a;
     if (dP == 0.0) break;
     const double d = P / dP;
     lam -= d;
-    if (fabs(d) <= 1e-14 * fabs(lam)) break;
+    if (fabs(d) <= 1e-14 * fabs(lam)) { converged = true; break; }
   }
+  // Conditioning of the root: rounding noise of P (~ 64 eps lam^4) over P' must stay below
+  // ~1e-12 lam for the 1e-4 A contract; otherwise (double root) take the SVD path.
+  if (!converged || fabs(dP) < 7e-3 * fabs(lam * lam * lam)) lam = lambda_by_svd(S);
   return lam;
 }
 /// Best-fit RMSD from the 3x3 covariance S, E0 = (Ga+Gb)/2 and total mass M.
 __device__ __forceinline__ double rmsd_fit_from_cov(const double* S, double e0, double invM) {
   const Quartic q = quartic_of(S);
-  const double lam = largest_root(q, e0);
+  const double lam = largest_root(q, e0, S);
   const double e = e0 - lam;
   return (e < 0.0) ? 0.0 : sqrt(2.0 * e * invM);  // clamp: src/Frame.cpp:1264-1268
 }
@@ -568,7 +611,7 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
         const double gt = v[12] - M * (cx * cx + cy * cy + cz * cz);
         const double e0 = 0.5 * (gt + a.refsum[4]);
         const Quartic q = quartic_of(S);
-        const double lam = largest_root(q, e0);
+        const double lam = largest_root(q, e0, S);
         const double e = e0 - lam;
         a.rmsd[fr] = (e < 0.0) ? 0.0 : sqrt(2.0 * e / M);
         if (a.rot) rotation_from_cov(S, lam, a.rot + 9 * (size_t)fr);
