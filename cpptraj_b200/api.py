@@ -51,6 +51,9 @@ def lib():
     L.b200_rmsd_1vN_end.argtypes = [vp]
     L.b200_dev_rms2d_tri.argtypes = [vp, sz, vp, i, vp, i, vp, i, i, i, vp, vp]
     L.b200_dev_rmsd_1vN.argtypes = [vp, sz, i, vp, i, vp, vp, i, vp, vp, vp, vp]
+    L.b200_set_pair_engine.argtypes = [i]
+    L.b200_last_pair_engine.argtypes = [C.POINTER(i)]
+    L.b200_debug_i8.argtypes = [vp, sz, i, vp, i, vp, vp, sz, C.POINTER(sz), vp, vp, vp, C.POINTER(i)]
     L.b200_get_stats.argtypes = [C.POINTER(Stats)]
     L.b200_set_profiling.argtypes = [i]
     L.b200_measure_fp64_mma_peak.argtypes = [i]
@@ -58,7 +61,8 @@ def lib():
     for name in ("b200_init", "b200_init_devices", "b200_shard_rows", "b200_rms2d_tri", "b200_rms2d_tri_shard",
                  "b200_rms2d_full", "b200_rmsd_1vN_begin", "b200_rmsd_1vN_push_f64", "b200_rmsd_1vN_push_f32",
                  "b200_rmsd_1vN_flush", "b200_rmsd_1vN_end", "b200_dev_rms2d_tri", "b200_dev_rmsd_1vN",
-                 "b200_version", "b200_num_devices"):
+                 "b200_version", "b200_num_devices", "b200_set_pair_engine", "b200_last_pair_engine", "b200_debug_i8",
+                 "b200_set_mma_variant"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -232,8 +236,42 @@ def get_stats():
     return {k: getattr(s, k) for k, _ in Stats._fields_}
 
 
+ENGINES = {"auto": 0, "fp64": 1, "i8": 2}
+
+
+def set_pair_engine(engine):
+    """'auto' | 'fp64' | 'i8' (or 0/1/2): which kernel computes the pair covariances."""
+    _check(lib().b200_set_pair_engine(ENGINES.get(engine, engine)))
+
+
+def last_pair_engine():
+    """(engine, fractional_bits) of the last rms2d call: engine 1 = FP64 DMMA, 2 = tcgen05 int8."""
+    q = C.c_int(0)
+    e = lib().b200_last_pair_engine(C.byref(q))
+    return e, q.value
+
+
+def debug_i8(crd, atom_idx, mass=None, want_image=True, want_S=True):
+    """Test hook: packed int8 operand image, G, raw integer covariances, triangle, fractional bits."""
+    crd = _crd2d(crd)
+    sel = _arr(atom_idx, np.int32)
+    mass = _arr(mass, np.float64)
+    nF = crd.shape[0]
+    nbytes = C.c_size_t(0)
+    qs = C.c_int(0)
+    nrg = (nF + 13) // 14
+    nrg += nrg & 1
+    cap = nrg * ((len(sel) + 63) // 64) * 8192
+    img = np.zeros(cap, np.uint8) if want_image else None
+    G = np.zeros(nF, np.float64)
+    S = np.zeros((nF, nF, 9), np.float64) if want_S else None
+    tri = np.zeros(tri_size(nF), np.float32)
+    _check(lib().b200_debug_i8(_p(crd), crd.shape[1], nF, _p(sel), len(sel), _p(mass), _p(img), cap, C.byref(nbytes),
+                               _p(G), _p(S), _p(tri), C.byref(qs)))
+    return dict(image=img, G=G, S=S, tri=tri, qs=qs.value, image_bytes=nbytes.value)
+
+
 def set_mma_variant(v):
-    lib().b200_set_mma_variant.restype = C.c_int
     _check(lib().b200_set_mma_variant(int(v)))
 
 

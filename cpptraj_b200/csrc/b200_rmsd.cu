@@ -5,6 +5,7 @@
 // host buffers it passes in.
 #include "../../include/b200_rmsd.h"
 #include "rmsd_kernels.cuh"
+#include "pair_i8.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -82,6 +83,9 @@ struct Device {
   cudaEvent_t done[NSLOT] = {nullptr, nullptr, nullptr};
   // workspaces (grow-only)
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
+  DevBuf imgA, imgB, cenA, cenB, dbgS;   // tcgen05 int8 path: operand images, frame centres
+  PinBuf hostScal;                        // pinned slot for the few scalars read back per call
+  int numSMs = 0;
   DevBuf outChunk[NSLOT];
   PinBuf outStage[NSLOT];
   bool attrSet = false;
@@ -94,8 +98,10 @@ struct Device {
       stream[s] = nullptr; done[s] = nullptr;
       outChunk[s].release(); outStage[s].release();
     }
-    DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs};
+    DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
+                     &imgA, &imgB, &cenA, &cenB, &dbgS};
     for (DevBuf* b : all) b->release();
+    hostScal.release();
     id = -1;
   }
 };
@@ -166,6 +172,7 @@ int init_device(Device& d, int id) {
   CU(cudaGetDeviceProperties(&prop, id));
   if (prop.major < 10)
     return fail(B200_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", id, prop.major, prop.minor);
+  d.numSMs = prop.multiProcessorCount;
   for (int s = 0; s < NSLOT; ++s) {
     CU(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&d.done[s], cudaEventDisableTiming));
@@ -250,6 +257,138 @@ int run_pair_band(const PackSet& A, const PackSet& B, int rg0, int nRgI, bool tr
   return launch_pair(a, grid, fit, tri, st);
 }
 
+
+// ------------------------------------------------------------------ pair engine selection
+// 0 = auto (tcgen05 int8 path when the selection's extent allows >= the required fractional bits,
+//     else FP64 DMMA), 1 = FP64 DMMA always, 2 = tcgen05 int8 or fail.  Env B200_PAIR_ENGINE.
+int g_engine = -1;
+int pair_engine() {
+  if (g_engine < 0) {
+    const char* e = getenv("B200_PAIR_ENGINE");
+    g_engine = e ? atoi(e) : 0;
+    if (g_engine < 0 || g_engine > 2) g_engine = 0;
+  }
+  return g_engine;
+}
+std::atomic<int> g_lastEngine{0}, g_lastQs{0};
+
+struct I8Set {  // one quantised frame set resident on the device
+  uint8_t* image = nullptr;
+  double* G = nullptr;
+  double* centers = nullptr;
+  int nFrames = 0, nRg = 0, nC = 0;
+};
+
+/// Worst-case RMSD change caused by rounding to a grid of spacing 2^-qs (both frames):
+/// every coordinate off by half a grid step => sqrt(3)/2 * 2^-qs * sqrt(N/M) per frame.
+inline double i8_worst_error(int qs, int nAtoms, double totalMass) {
+  return std::ldexp(1.0, -qs) * std::sqrt(3.0 * (double)nAtoms / totalMass);
+}
+constexpr double I8_MAX_WORST_ERROR = 5.3e-5;  // half the 1e-4 A contract (north_star)
+
+int i8_reserve(I8Set& S, DevBuf& img, DevBuf& G, DevBuf& cen, int nFrames, int nAtoms) {
+  S.nFrames = nFrames;
+  S.nRg = (nFrames + I8_FR_PER_RG - 1) / I8_FR_PER_RG;
+  S.nRg += S.nRg & 1;   // B tiles take row groups in pairs
+  S.nC = (nAtoms + I8_KC - 1) / I8_KC;
+  int rc;
+  if ((rc = img.reserve(i8_image_bytes(S.nRg, S.nC)))) return rc;
+  if ((rc = G.reserve((size_t)S.nRg * I8_FR_PER_RG * sizeof(double)))) return rc;
+  if ((rc = cen.reserve((size_t)S.nRg * I8_FR_PER_RG * 3 * sizeof(double)))) return rc;
+  S.image = (uint8_t*)img.p; S.G = (double*)G.p; S.centers = (double*)cen.p;
+  return B200_OK;
+}
+
+int i8_stats(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
+             const int* d_atomIdx, int nAtoms, const double* d_centerMass, const double* d_covMass,
+             unsigned int* d_maxBits, cudaStream_t st) {
+  I8StatsArgs a;
+  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = S.nFrames; a.f0 = f0;
+  a.atomIdx = d_atomIdx; a.nAtoms = nAtoms; a.centerMass = d_centerMass; a.covMass = d_covMass;
+  a.centers = S.centers; a.maxAbsBits = d_maxBits;
+  const int nb = (S.nFrames - f0 + 7) / 8;
+  if (nb <= 0) return B200_OK;
+  COUNT_LAUNCH();
+  i8_stats_kernel<<<nb, 256, 0, st>>>(a);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+int i8_quant(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
+             const int* d_atomIdx, int nAtoms, const double* d_covMass, int qs, cudaStream_t st) {
+  CU(cudaMemsetAsync(S.image, 0, i8_image_bytes(S.nRg, S.nC), st));
+  CU(cudaMemsetAsync(S.G, 0, (size_t)S.nRg * I8_FR_PER_RG * sizeof(double), st));
+  I8QuantArgs a;
+  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = S.nFrames; a.f0 = f0;
+  a.atomIdx = d_atomIdx; a.nAtoms = nAtoms; a.nC = S.nC; a.covMass = d_covMass; a.centers = S.centers;
+  a.scale = std::ldexp(1.0, qs); a.invScale2 = std::ldexp(1.0, -2 * qs);
+  a.image = S.image; a.G = S.G;
+  const int nb = (S.nFrames - f0 + 7) / 8;
+  if (nb <= 0) return B200_OK;
+  COUNT_LAUNCH();
+  i8_quant_kernel<<<nb, 256, 0, st>>>(a);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+/// Reads back (max |coordinate|, total mass) after the stats kernel and picks the number of
+/// fractional bits.  *eligible = false when the grid would be too coarse for the contract.
+int i8_choose_scale(Device& d, const unsigned int* d_maxBits, const double* d_total, int nAtoms, cudaStream_t st,
+                    int* qs, bool* eligible) {
+  int rc;
+  if ((rc = d.hostScal.reserve(64))) return rc;
+  unsigned int* hBits = (unsigned int*)d.hostScal.p;
+  double* hTotal = (double*)((char*)d.hostScal.p + 8);
+  CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(hTotal, d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  float mx;
+  std::memcpy(&mx, hBits, 4);
+  const double total = *hTotal;
+  *eligible = false; *qs = 0;
+  if (!(total > 0.0) || !std::isfinite(mx)) return B200_OK;
+  int q = 30;
+  if (mx > 0.f) q = (int)std::floor(std::log2((double)I8_QMAX / (double)mx));
+  if (q > 30) q = 30;
+  if (q < 0) return B200_OK;
+  *qs = q;
+  *eligible = i8_worst_error(q, nAtoms, total) <= I8_MAX_WORST_ERROR;
+  return B200_OK;
+}
+
+template <bool TRI>
+int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
+  static bool attr[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr[dev & 63]) {
+    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    attr[dev & 63] = true;
+  }
+  COUNT_LAUNCH();
+  pair_i8_kernel<TRI><<<grid, I8_THREADS, I8_SMEM_BYTES, st>>>(a);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
+/// Rows [rowLo,rowHi) of the pair matrix through the tcgen05 int8 kernel (persistent, one CTA per SM).
+int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo, int rowHi, bool tri, int qs,
+                     const double* d_totalMass, float* out, size_t outBase, size_t ldo, double* dbgS, cudaStream_t st) {
+  if (rowHi <= rowLo) return B200_OK;
+  PairI8Args a;
+  a.PA = A.image; a.PB = B.image; a.GA = A.G; a.GB = B.G; a.nC = A.nC;
+  a.nRows = A.nFrames; a.nCols = B.nFrames; a.rowLo = rowLo; a.rowHi = rowHi;
+  a.it0 = rowLo / I8_TILE_I; a.nIt = (rowHi + I8_TILE_I - 1) / I8_TILE_I - a.it0;
+  a.jt0 = tri ? (rowLo + 1) / I8_TILE_J : 0;
+  a.nJt = (B.nFrames + I8_TILE_J - 1) / I8_TILE_J - a.jt0;
+  a.totalMass = d_totalMass; a.invScale2 = std::ldexp(1.0, -2 * qs);
+  a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
+  if (a.nIt <= 0 || a.nJt <= 0) return B200_OK;
+  const long nTiles = (long)a.nIt * a.nJt;
+  const int grid = (int)std::min<long>(nTiles, d.numSMs > 0 ? d.numSMs : 148);
+  return tri ? launch_pair_i8_t<true>(a, grid, st) : launch_pair_i8_t<false>(a, grid, st);
+}
+
 int shard_rows(int nFrames, int rank, int count, int* row0, int* row1) {
   if (nFrames < 0 || count < 1 || rank < 0 || rank >= count) return fail(B200_ERR_ARG, "bad shard %d/%d", rank, count);
   // boundary b_s: smallest 32-aligned row with area(rows < b_s) >= s/count * total
@@ -273,39 +412,84 @@ int shard_rows(int nFrames, int rank, int count, int* row0, int* row1) {
   return B200_OK;
 }
 
-// ------------------------------------------------------------------ device-resident tri
-int dev_rms2d_tri(Device& d, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int nFrames,
-                  const int* d_atomIdx, int nAtoms, const double* d_mass, int fit, int row0, int row1,
-                  float* d_out, size_t outBase, cudaStream_t st, int bandRows, Timer* tpack, Timer* tpair,
-                  bool doPack, PackSet* psInOut) {
-  if (nFrames < 2 || row1 <= row0) return B200_OK;
-  PackSet ps;
-  ps.nFrames = nFrames; ps.Fpad = round_up(nFrames, ROWG); ps.Kpad = round_up(nAtoms, KC);
+// ------------------------------------------------------------------ triangle: plan + bands
+struct TriPlan {   // what prepare_tri() left on the device for the band launches
+  bool i8 = false;
+  int qs = 0;
+  PackSet ps;      // FP64 planes   (engine FP64)
+  I8Set q;         // int8 images   (engine tcgen05)
+  double* d_total = nullptr;
+};
+
+/// Centre + pack output frames >= row0's tile for the engine that will run the pairs.
+/// Blocks the host once (a few scalars read back) when the tcgen05 engine is a candidate.
+int prepare_tri(Device& d, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int nFrames,
+                const int* d_atomIdx, int nAtoms, const double* d_mass, int fit, int row0, cudaStream_t st,
+                Timer* tpack, TriPlan& plan) {
   int rc;
-  if ((rc = d.planesA.reserve(plane_doubles(ps.Fpad, ps.Kpad) * sizeof(double)))) return rc;
-  if ((rc = d.GA.reserve((size_t)ps.Fpad * sizeof(double)))) return rc;
   if ((rc = d.scal.reserve(64))) return rc;
-  ps.planes = (double*)d.planesA.p; ps.G = (double*)d.GA.p;
   double* d_total = (double*)d.scal.p;
   double* d_shift = d_total + 1;
-  if (doPack) {
-    if (tpack) tpack->begin(st);
-    COUNT_LAUNCH();
-    mass_sum_kernel<<<1, 32, 0, st>>>(d_mass, nAtoms, d_total);
+  unsigned int* d_maxBits = (unsigned int*)(d_total + 4);
+  plan.d_total = d_total;
+  if (tpack) tpack->begin(st);
+  COUNT_LAUNCH();
+  mass_sum_kernel<<<1, 32, 0, st>>>(d_mass, nAtoms, d_total);
+  const int engine = pair_engine();
+  if (fit && engine != 1) {
+    if ((rc = i8_reserve(plan.q, d.imgA, d.GA, d.cenA, nFrames, nAtoms))) return rc;
+    const int f0 = (row0 / I8_FR_PER_RG) * I8_FR_PER_RG;
+    CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st));
+    if ((rc = i8_stats(plan.q, d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
+    bool ok = false;
+    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &plan.qs, &ok))) return rc;
+    if (ok) {
+      if ((rc = i8_quant(plan.q, d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, nAtoms, d_mass, plan.qs, st))) return rc;
+      plan.i8 = true;
+    } else if (engine == 2) {
+      return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but the selection's extent leaves only %d fractional bits", plan.qs);
+    }
+  } else if (engine == 2) {
+    return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but nofit RMSD runs on the FP64 engine only");
+  }
+  if (!plan.i8) {
+    PackSet& ps = plan.ps;
+    ps.nFrames = nFrames; ps.Fpad = round_up(nFrames, ROWG); ps.Kpad = round_up(nAtoms, KC);
+    if ((rc = d.planesA.reserve(plane_doubles(ps.Fpad, ps.Kpad) * sizeof(double)))) return rc;
+    if ((rc = d.GA.reserve((size_t)ps.Fpad * sizeof(double)))) return rc;
+    ps.planes = (double*)d.planesA.p; ps.G = (double*)d.GA.p;
     // rows >= row0 only pair with columns > row0: frames below row0's row group are never read
     const int f0 = (row0 / ROWG) * ROWG;
     if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st>>>(d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, d_shift); }
     if ((rc = run_pack(d_crd, stride, d_frameIdx, srcBase, nFrames, f0, d_atomIdx, nAtoms, d_mass, d_mass, d_shift,
                        fit, ps, st))) return rc;
-    if (tpack) tpack->end(st);
   }
-  if (psInOut) *psInOut = ps;
+  if (tpack) tpack->end(st);
+  g_lastEngine.store(plan.i8 ? 2 : 1); g_lastQs.store(plan.i8 ? plan.qs : 0);
+  return B200_OK;
+}
+
+/// Rows [i0,i1) of the triangle; `out` indexed as out[triIndex - outBase].
+int run_tri_band(Device& d, const TriPlan& plan, int i0, int i1, bool fit, float* out, size_t outBase, cudaStream_t st) {
+  if (plan.i8) return run_pair_i8_band(d, plan.q, plan.q, i0, i1, true, plan.qs, plan.d_total, out, outBase, 0, nullptr, st);
+  // the FP64 kernel works on whole 32-row groups: neighbouring bands must be 32-aligned
+  return run_pair_band(plan.ps, plan.ps, i0 / ROWG, (i1 + ROWG - 1) / ROWG - i0 / ROWG, true, fit, plan.d_total, out,
+                       outBase, 0, st);
+}
+
+int dev_rms2d_tri(Device& d, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int nFrames,
+                  const int* d_atomIdx, int nAtoms, const double* d_mass, int fit, int row0, int row1,
+                  float* d_out, size_t outBase, cudaStream_t st, int bandRows, Timer* tpack, Timer* tpair) {
+  if (nFrames < 2 || row1 <= row0) return B200_OK;
+  TriPlan plan;
+  int rc;
+  if ((rc = prepare_tri(d, d_crd, stride, d_frameIdx, srcBase, nFrames, d_atomIdx, nAtoms, d_mass, fit, row0, st, tpack, plan)))
+    return rc;
   if (bandRows <= 0) bandRows = 512;
   for (int i0 = row0; i0 < row1; i0 += bandRows) {
     const int i1 = std::min(row1, i0 + bandRows);
-    const int rg0 = i0 / ROWG, rg1 = (i1 + ROWG - 1) / ROWG;
     if (tpair) tpair->begin(st);
-    if ((rc = run_pair_band(ps, ps, rg0, rg1 - rg0, true, fit != 0, d_total, d_out, outBase, 0, st))) return rc;
+    if ((rc = run_tri_band(d, plan, i0, i1, fit != 0, d_out, outBase, st))) return rc;
     if (tpair) tpair->end(st);
   }
   return B200_OK;
@@ -357,8 +541,8 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   if (row1 <= row0 || nFrames < 2) return B200_OK;
   int maxAtom = 0, rc;
   if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
-  // source frame range needed by output frames [f0, nFrames)
-  const int f0 = (row0 / ROWG) * ROWG;
+  // source frame range needed by output frames [f0, nFrames) (f0: first frame either engine packs)
+  const int f0 = std::min((row0 / ROWG) * ROWG, (row0 / I8_FR_PER_RG) * I8_FR_PER_RG);
   int sLo = f0, sHi = nFrames;
   if (frameIdx) {
     sLo = nFramesTotal; sHi = 0;
@@ -379,24 +563,12 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   h2d += (double)nAtoms * 4 + (mass ? (double)nAtoms * 8 : 0) + (frameIdx ? (double)nFrames * 4 : 0);
 
   Timer tpack, tpair;
-  PackSet ps;
-  // pack on stream 0 (no pair launches: row1 == row0 trick), then bands round-robin over the slots
-  ps.nFrames = nFrames; ps.Fpad = round_up(nFrames, ROWG); ps.Kpad = round_up(nAtoms, KC);
-  if ((rc = d.planesA.reserve(plane_doubles(ps.Fpad, ps.Kpad) * sizeof(double)))) return rc;
-  if ((rc = d.GA.reserve((size_t)ps.Fpad * sizeof(double)))) return rc;
-  if ((rc = d.scal.reserve(64))) return rc;
-  ps.planes = (double*)d.planesA.p; ps.G = (double*)d.GA.p;
-  double* d_total = (double*)d.scal.p;
-  double* d_shift = d_total + 1;
+  TriPlan plan;
   const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
   const int* d_fidx = frameIdx ? (const int*)d.frameIdx.p : nullptr;
-  tpack.begin(st0);
-  COUNT_LAUNCH();
-  mass_sum_kernel<<<1, 32, 0, st0>>>(d_mass, nAtoms, d_total);
-  if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st0>>>((const float*)d.crd.p, width, d_fidx, (long)sLo, f0, (const int*)d.idxA.p, d_shift); }
-  if ((rc = run_pack((const float*)d.crd.p, width, d_fidx, (long)sLo, nFrames, f0, (const int*)d.idxA.p, nAtoms, d_mass,
-                     d_mass, d_shift, fit, ps, st0))) return rc;
-  tpack.end(st0);
+  // pack on stream 0, then bands round-robin over the slots
+  if ((rc = prepare_tri(d, (const float*)d.crd.p, width, d_fidx, (long)sLo, nFrames, (const int*)d.idxA.p, nAtoms, d_mass,
+                        fit, row0, st0, &tpack, plan))) return rc;
   CU(cudaEventRecord(d.done[0], st0));
   for (int s = 1; s < NSLOT; ++s) CU(cudaStreamWaitEvent(d.stream[s], d.done[0], 0));
 
@@ -430,8 +602,7 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
     const size_t base = tri_row_start(F, i0), n = tri_row_start(F, i1) - base;
     cudaStream_t st = d.stream[s];
     tpair.begin(st);
-    if ((rc = run_pair_band(ps, ps, i0 / ROWG, (i1 + ROWG - 1) / ROWG - i0 / ROWG, true, fit != 0, d_total,
-                            (float*)d.outChunk[s].p, base, 0, st))) return rc;
+    if ((rc = run_tri_band(d, plan, i0, i1, fit != 0, (float*)d.outChunk[s].p, base, st))) return rc;
     tpair.end(st);
     ++nLaunch;
     if (n) {
@@ -601,30 +772,54 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
   if (massTgt && (rc = upload_vec(d.massA, massTgt, (size_t)nAtoms, st0))) return rc;
   const double* mRef = massRefCentering ? massRefCentering : massTgt;
   if (mRef && (rc = upload_vec(d.massB, mRef, (size_t)nAtoms, st0))) return rc;
-  PackSet A, B;
-  A.nFrames = nTgt; A.Fpad = round_up(nTgt, ROWG); A.Kpad = round_up(nAtoms, KC);
-  B.nFrames = nRef; B.Fpad = round_up(nRef, ROWG); B.Kpad = A.Kpad;
-  if ((rc = d.planesA.reserve(plane_doubles(A.Fpad, A.Kpad) * sizeof(double)))) return rc;
-  if ((rc = d.planesB.reserve(plane_doubles(B.Fpad, B.Kpad) * sizeof(double)))) return rc;
-  if ((rc = d.GA.reserve((size_t)A.Fpad * sizeof(double)))) return rc;
-  if ((rc = d.GB.reserve((size_t)B.Fpad * sizeof(double)))) return rc;
   if ((rc = d.scal.reserve(64))) return rc;
-  A.planes = (double*)d.planesA.p; A.G = (double*)d.GA.p;
-  B.planes = (double*)d.planesB.p; B.G = (double*)d.GB.p;
   double* d_total = (double*)d.scal.p;
   double* d_shift = d_total + 1;
+  unsigned int* d_maxBits = (unsigned int*)(d_total + 4);
   const double* dmT = massTgt ? (const double*)d.massA.p : nullptr;
   const double* dmR = mRef ? (const double*)d.massB.p : nullptr;
   Timer tpack, tpair;
   tpack.begin(st0);
   COUNT_LAUNCH();
   mass_sum_kernel<<<1, 32, 0, st0>>>(dmT, nAtoms, d_total);
-  if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st0>>>((const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, d_shift); }
   // target: centred and weighted with its own masses; reference: centred with the reference
   // mask's masses but weighted with the TARGET masses (src/Frame.cpp:1184-1208, Analysis_Rms2d.cpp:265-266)
-  if ((rc = run_pack((const float*)d.crd.p, wT, nullptr, 0, nTgt, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_shift, fit, A, st0))) return rc;
-  if ((rc = run_pack((const float*)d.crdB.p, wR, nullptr, 0, nRef, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_shift, fit, B, st0))) return rc;
+  PackSet A, B;
+  I8Set qA, qB;
+  bool useI8 = false;
+  int qs = 0;
+  const int engine = pair_engine();
+  if (fit && engine != 1) {
+    if ((rc = i8_reserve(qA, d.imgA, d.GA, d.cenA, nTgt, nAtoms))) return rc;
+    if ((rc = i8_reserve(qB, d.imgB, d.GB, d.cenB, nRef, nAtoms))) return rc;
+    CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st0));
+    if ((rc = i8_stats(qA, (const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_maxBits, st0))) return rc;
+    if ((rc = i8_stats(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_maxBits, st0))) return rc;
+    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st0, &qs, &useI8))) return rc;
+    if (useI8) {
+      if ((rc = i8_quant(qA, (const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, dmT, qs, st0))) return rc;
+      if ((rc = i8_quant(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmT, qs, st0))) return rc;
+    } else if (engine == 2) {
+      return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but the selection's extent leaves only %d fractional bits", qs);
+    }
+  } else if (engine == 2) {
+    return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but nofit RMSD runs on the FP64 engine only");
+  }
+  if (!useI8) {
+    A.nFrames = nTgt; A.Fpad = round_up(nTgt, ROWG); A.Kpad = round_up(nAtoms, KC);
+    B.nFrames = nRef; B.Fpad = round_up(nRef, ROWG); B.Kpad = A.Kpad;
+    if ((rc = d.planesA.reserve(plane_doubles(A.Fpad, A.Kpad) * sizeof(double)))) return rc;
+    if ((rc = d.planesB.reserve(plane_doubles(B.Fpad, B.Kpad) * sizeof(double)))) return rc;
+    if ((rc = d.GA.reserve((size_t)A.Fpad * sizeof(double)))) return rc;
+    if ((rc = d.GB.reserve((size_t)B.Fpad * sizeof(double)))) return rc;
+    A.planes = (double*)d.planesA.p; A.G = (double*)d.GA.p;
+    B.planes = (double*)d.planesB.p; B.G = (double*)d.GB.p;
+    if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st0>>>((const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, d_shift); }
+    if ((rc = run_pack((const float*)d.crd.p, wT, nullptr, 0, nTgt, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_shift, fit, A, st0))) return rc;
+    if ((rc = run_pack((const float*)d.crdB.p, wR, nullptr, 0, nRef, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_shift, fit, B, st0))) return rc;
+  }
   tpack.end(st0);
+  g_lastEngine.store(useI8 ? 2 : 1); g_lastQs.store(useI8 ? qs : 0);
   // rows (targets) in bands; each band is a contiguous slab of outFull
   const size_t ld = (size_t)nRef;
   int bandRows = (int)std::min<size_t>(1024, std::max<size_t>(ROWG, ((size_t)32 << 20) / (4 * ld) / ROWG * ROWG));
@@ -653,8 +848,12 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
     const size_t base = (size_t)i0 * ld, n = (size_t)(i1 - i0) * ld;
     tpair.begin(st);
     // kernel indexes out[i*ld + j]; shift the pointer so row i0 lands at the chunk start
-    if ((rc = run_pair_band(A, B, i0 / ROWG, (i1 + ROWG - 1) / ROWG - i0 / ROWG, false, fit != 0, d_total,
-                            (float*)d.outChunk[s].p - base, 0, ld, st))) return rc;
+    if (useI8)
+      rc = run_pair_i8_band(d, qA, qB, i0, i1, false, qs, d_total, (float*)d.outChunk[s].p - base, 0, ld, nullptr, st);
+    else
+      rc = run_pair_band(A, B, i0 / ROWG, (i1 + ROWG - 1) / ROWG - i0 / ROWG, false, fit != 0, d_total,
+                         (float*)d.outChunk[s].p - base, 0, ld, st);
+    if (rc) return rc;
     tpair.end(st);
     ++nLaunch;
     float* dst = pinnedOut ? outFull + base : (float*)d.outStage[s].p;
@@ -686,7 +885,7 @@ int b200_dev_rms2d_tri(const float* d_crd, size_t frameStrideFloats, const int* 
   Timer tpack, tpair;
   cudaStream_t st = (cudaStream_t)stream;
   rc = dev_rms2d_tri(*d, d_crd, frameStrideFloats, d_frameIdx, 0, nFrames, d_atomIdx, nAtoms, d_mass, fit, r0, r1, d_outTri,
-                     0, st, 4096, g_profiling ? &tpack : nullptr, g_profiling ? &tpair : nullptr, true, nullptr);
+                     0, st, 4096, g_profiling ? &tpack : nullptr, g_profiling ? &tpair : nullptr);
   if (rc) return rc;
   if (g_profiling) {
     CU(cudaStreamSynchronize(st));
@@ -930,6 +1129,71 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
     std::lock_guard<std::mutex> sl(g_statMu);
     g_stats.onevn_ms += ms; g_stats.onevn_launches += 1; g_stats.frames_1vN += (double)nFrames;
   }
+  return B200_OK;
+}
+
+
+int b200_set_pair_engine(int engine) {
+  if (engine < 0 || engine > 2) return fail(B200_ERR_ARG, "engine must be 0 (auto), 1 (fp64) or 2 (tcgen05 int8)");
+  g_engine = engine;
+  return B200_OK;
+}
+int b200_last_pair_engine(int* fractionalBits) {
+  if (fractionalBits) *fractionalBits = g_lastQs.load();
+  return g_lastEngine.load();
+}
+
+int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms, const double* mass,
+                  unsigned char* imageOut, size_t imageCap, size_t* imageBytes, double* GOut, double* SOut, float* outTri,
+                  int* qsOut) {
+  if (!crd || nFrames < 2) return fail(B200_ERR_ARG, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc, maxAtom = 0;
+  if ((rc = ensure_init_locked())) return rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  if ((rc = upload_crd(d.crd, crd, frameStrideFloats, 0, nFrames, width, st, &h2d))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
+  const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
+  if ((rc = d.scal.reserve(64))) return rc;
+  double* d_total = (double*)d.scal.p;
+  unsigned int* d_maxBits = (unsigned int*)(d_total + 4);
+  COUNT_LAUNCH();
+  mass_sum_kernel<<<1, 32, 0, st>>>(d_mass, nAtoms, d_total);
+  I8Set q;
+  if ((rc = i8_reserve(q, d.imgA, d.GA, d.cenA, nFrames, nAtoms))) return rc;
+  CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st));
+  if ((rc = i8_stats(q, (const float*)d.crd.p, width, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
+  int qs = 0; bool ok = false;
+  if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &qs, &ok))) return rc;
+  if (qsOut) *qsOut = qs;
+  if ((rc = i8_quant(q, (const float*)d.crd.p, width, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, d_mass, qs, st))) return rc;
+  const size_t ib = i8_image_bytes(q.nRg, q.nC);
+  if (imageBytes) *imageBytes = ib;
+  if (imageOut) {
+    if (imageCap < ib) return fail(B200_ERR_ARG, "image buffer too small: %zu < %zu", imageCap, ib);
+    CU(cudaMemcpyAsync(imageOut, q.image, ib, cudaMemcpyDeviceToHost, st));
+  }
+  if (GOut) CU(cudaMemcpyAsync(GOut, q.G, (size_t)nFrames * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (outTri) {
+    const size_t nTri = (size_t)nFrames * (nFrames - 1) / 2;
+    double* d_S = nullptr;
+    if (SOut) {
+      if ((rc = d.dbgS.reserve((size_t)nFrames * nFrames * 9 * sizeof(double)))) return rc;
+      d_S = (double*)d.dbgS.p;
+      CU(cudaMemsetAsync(d_S, 0, (size_t)nFrames * nFrames * 9 * sizeof(double), st));
+    }
+    if ((rc = d.outChunk[0].reserve(nTri * sizeof(float)))) return rc;
+    if ((rc = run_pair_i8_band(d, q, q, 0, nFrames, true, qs, d_total, (float*)d.outChunk[0].p, 0, 0, d_S, st))) return rc;
+    CU(cudaMemcpyAsync(outTri, d.outChunk[0].p, nTri * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (SOut) CU(cudaMemcpyAsync(SOut, d_S, (size_t)nFrames * nFrames * 9 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
   return B200_OK;
 }
 

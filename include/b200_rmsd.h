@@ -155,6 +155,28 @@ void b200_set_profiling(int on);
 void b200_reset_stats(void);
 void b200_get_stats(b200_stats* out);
 
+/* ---- pair engine ---------------------------------------------------------------
+ * Two kernels compute the pair covariances:
+ *   1 = FP64 tensor cores (mma.sync DMMA), any input, fit and nofit;
+ *   2 = tcgen05 int8 tensor cores on coordinates rounded once per frame to a 24-bit
+ *       fixed-point grid (exact integer covariance in TMEM), fit only, used when the
+ *       selection's extent leaves enough fractional bits for a worst-case RMSD change
+ *       < 5.3e-5 A;
+ *   0 = automatic (2 when eligible, else 1) -- the default; env B200_PAIR_ENGINE.
+ * Forcing 2 on an ineligible call fails with B200_ERR_ARG. */
+int b200_set_pair_engine(int engine);
+/* Engine the last rms2d call used (1 or 2; 0 = none yet) and, for 2, the number of
+ * fractional bits of its fixed-point grid. */
+int b200_last_pair_engine(int* fractionalBits);
+
+/* Test hook for the tcgen05 path (small inputs, device 0): returns the packed int8
+ * operand image, the per-frame G, the raw integer covariances (9 doubles per (i,j),
+ * i<j, at (i*nFrames+j)*9) and the triangle.  Any output pointer may be NULL. */
+int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames,
+                  const int* atomIdx, int nAtoms, const double* mass,
+                  unsigned char* imageOut, size_t imageCap, size_t* imageBytes,
+                  double* GOut, double* SOut, float* outTri, int* qsOut);
+
 /* Tuning knob: PTX shape used for the FP64 MMAs of the pair kernel
  * (0 m8n8k4, 1 m16n8k4, 2 m16n8k8, 3 m16n8k16; all lower to DMMA.8x8x4 SASS). */
 int b200_set_mma_variant(int variant);
