@@ -254,50 +254,91 @@ def main():
     def dev_step():
         b.dev_rms2d_tri(d_crd, stride, nF, d_sel, nA, d_out_base, fit=True, rank=rank, count=world, stream=stream)
 
-    b.set_profiling(False)
-    for _ in range(args.warmup):
-        dev_step()
-    barrier()
-    b.set_profiling(True)
-    b.reset_stats()
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(args.steps):
-        dev_step()
-    ev1.record()
-    barrier()
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.result()
-    st = b.get_stats()
-    b.set_profiling(False)
-    value = total_pairs * args.steps / (dev_ms * 1e-3)
-    # checksum so that the timed work is demonstrably the real work
-    chk = float(d_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
-
-    # roofline of the dominant (pair-tile) kernel on this rank
-    launches = max(1, st["pair_launches"])
-    pair_ms_per_launch = st["pair_ms"] / launches
-    flop_per_launch = 18.0 * nA * (st["pairs"] / launches)
-    achieved = flop_per_launch / (pair_ms_per_launch * 1e-3) / 1e12 if pair_ms_per_launch > 0 else 0.0
-    peak = max(b.measure_fp64_mma_peak(0), b.measure_fp64_mma_peak(3))
     peaks_file = {}
     try:
         peaks_file = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    roofline = {
-        "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-        "frac": achieved / peak if peak > 0 else None, "traffic": None,
-        "kernel": "pair_kernel<fit,tri> (FP64 DMMA.8x8x4, 32x32 frame tiles)",
-        "peak_source": "FP64 tensor (DMMA) issue peak measured live by b200_measure_fp64_mma_peak; "
-                       "MEASURED_PEAKS.json holds no FP64 figure",
-        "launches": int(st["pair_launches"]), "avg_launch_ms": pair_ms_per_launch,
-        "kernel_share_of_step": st["pair_ms"] / (ev0.elapsed_time(ev1)) if dev_ms > 0 else None,
-        "frac_of_bf16_measured": (achieved / peaks_file["bf16_tflops_sustained"]) if peaks_file.get("bf16_tflops_sustained") else None,
-    }
+
+    def timed_device_run(steps, warmup):
+        """warmup + `steps` timed passes; returns (ms max over ranks, this rank's ms, stats, clocks)."""
+        b.set_profiling(False)
+        for _ in range(warmup):
+            dev_step()
+        barrier()
+        b.set_profiling(True)
+        b.reset_stats()
+        sampler = ClockSampler(local)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            dev_step()
+        e1.record()
+        barrier()
+        own = e0.elapsed_time(e1)
+        ms = max_over_ranks(own)
+        clk = sampler.result()
+        stt = b.get_stats()
+        b.set_profiling(False)
+        return ms, own, stt, clk
+
+    def roofline_of(stt, own_ms, engine):
+        """Roofline of the dominant (pair-tile) kernel on this rank, from CUDA events on its stream."""
+        launches = max(1, stt["pair_launches"])
+        ms_per_launch = stt["pair_ms"] / launches
+        flop_per_launch = 18.0 * nA * (stt["pairs"] / launches)       # algorithmic: SURVEY 8(d), 18*N per fitted pair
+        achieved = flop_per_launch / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch > 0 else 0.0
+        r = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": None,
+             "launches": int(stt["pair_launches"]), "avg_launch_ms": ms_per_launch,
+             "kernel_share_of_step": stt["pair_ms"] / own_ms if own_ms > 0 else None}
+        bf16 = peaks_file.get("bf16_tflops_sustained")
+        if engine == 2:
+            # 3 x 3 int8 digit products per covariance entry: the tensor pipe executes 9x the algorithmic flop
+            kpad = (nA + 63) // 64 * 64
+            executed = achieved * 9.0 * kpad / nA * (128.0 * 256.0) / (126.0 * 252.0)
+            peak = b.measure_i8_mma_peak()
+            r.update({"peak": peak, "frac": achieved / peak if peak > 0 else None,
+                      "executed": executed, "frac_executed": executed / peak if peak > 0 else None,
+                      "kernel": "pair_i8_kernel<tri> (tcgen05.mma kind::i8 M128 N256 K32, int32 accumulators in TMEM, "
+                                "14x28 frame-pair tiles, fused FP64 solve)",
+                      "peak_source": "tcgen05 kind::i8 issue peak (int8 TOP/s) measured live by b200_measure_i8_mma_peak "
+                                     "(operands resident in smem); MEASURED_PEAKS.json holds bf16 only (int8 nominal = 2x bf16). "
+                                     "achieved/frac are ALGORITHMIC (18N flop per pair); executed/frac_executed count the 81 "
+                                     "int8 dot products per pair incl. tile padding, i.e. tensor-pipe utilisation",
+                      "frac_executed_of_2x_bf16_measured": executed / (2 * bf16) if bf16 else None})
+        else:
+            peak = max(b.measure_fp64_mma_peak(0), b.measure_fp64_mma_peak(3))
+            r.update({"peak": peak, "frac": achieved / peak if peak > 0 else None,
+                      "kernel": "pair_kernel<fit,tri> (FP64 DMMA.8x8x4, 32x32 frame tiles)",
+                      "peak_source": "FP64 tensor (DMMA) issue peak measured live by b200_measure_fp64_mma_peak; "
+                                     "MEASURED_PEAKS.json holds no FP64 figure",
+                      "frac_of_bf16_measured": achieved / bf16 if bf16 else None})
+        return r
+
+    dev_ms, own_ms, st, clocks = timed_device_run(args.steps, args.warmup)
+    engine, qbits = b.last_pair_engine()
+    value = total_pairs * args.steps / (dev_ms * 1e-3)
+    # checksum so that the timed work is demonstrably the real work
+    chk = float(d_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
+    roofline = roofline_of(st, own_ms, engine)
+    roofline["engine"] = {1: "fp64-dmma", 2: "tcgen05-int8"}.get(engine, "?")
+    if engine == 2:
+        roofline["fixed_point_fraction_bits"] = qbits
+        # the always-available FP64 engine on the same inputs, for context (and as a parity cross-check)
+        b.set_pair_engine("fp64")
+        k2 = max(1, min(args.steps, 2))
+        ms2, own2, st2_, _ = timed_device_run(k2, 1)
+        chk_fp64 = float(d_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
+        r2 = roofline_of(st2_, own2, 1)
+        roofline["fp64_engine"] = {"value": total_pairs * k2 / (ms2 * 1e-3), "unit": UNIT, "achieved": r2["achieved"],
+                                   "peak": r2["peak"], "frac": r2["frac"], "checksum": chk_fp64}
+        b.set_pair_engine("auto")
+        if abs(chk - chk_fp64) > 1e-3 * max(1.0, abs(chk)):
+            raise RuntimeError("tcgen05 and FP64 engines disagree: %r vs %r" % (chk, chk_fp64))
+        dev_step()   # leave d_out as the primary engine wrote it
+        torch.cuda.synchronize()
     gpu_launches = int(st["kernel_launches"])
     del d_out
     torch.cuda.empty_cache()
@@ -359,11 +400,16 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64" if engine != 2 else "s8 x s8 -> s32 exact covariance (24-bit fixed point) + f64 solve",
+            "data": "synthetic",
             "config": {"workload": "%s: rms2d fit, %d frames x %d atoms, %d pairs" % (name, nF, nA, total_pairs),
                        "sharding": "upper-triangle row bands, %d rank(s), no collective" % world,
-                       "l2": "inputs larger than L2 (packed planes %.0f MB, output %.0f MB per rank)" % (
-                           nF * round((nA + 15) // 16 * 16) * 24 / 1e6, nelt * 4 / 1e6),
+                       "engine": roofline["engine"],
+                       "l2": "no explicit flush: every step streams %.0f MB raw COORDS + %.0f MB packed operands + a %.0f MB "
+                             "result triangle per rank through the 126 MB L2" % (
+                           nF * stride * 4 / 1e6,
+                           (nF * ((nA + 63) // 64 * 64) * 9 if engine == 2 else nF * ((nA + 15) // 16 * 16) * 24) / 1e6,
+                           nelt * 4 / 1e6),
                        "seed": seed, "gen_seconds": round(t_gen, 2)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": 1e3 * e2e_s / args.steps, "api": "b200_rms2d_tri_shard, pinned host COORDS in, pinned host triangle out"},

@@ -1197,6 +1197,35 @@ int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames, const
   return B200_OK;
 }
 
+
+double b200_measure_i8_mma_peak(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (ensure_init_locked()) return -1.0;
+  cudaDeviceProp prop;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1.0;
+  const int blocks = prop.multiProcessorCount, iters = 20000;
+  const int smem = 3 * I8_BLK_BYTES;
+  if (cudaFuncSetAttribute(i8_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1.0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  i8_mma_peak_kernel<<<blocks, 128, smem>>>(256, nullptr);
+  cudaDeviceSynchronize();
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    i8_mma_peak_kernel<<<blocks, 128, smem>>>(iters, nullptr);
+    cudaEventRecord(b);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    best = std::min(best, ms);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  if (cudaGetLastError() != cudaSuccess) return -1.0;
+  return 2.0 * 128 * 256 * 32 * (double)iters * blocks / (best * 1e-3) / 1e12;   // TOP/s
+}
+
 double b200_measure_fp64_mma_peak(int variant) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (ensure_init_locked()) return -1.0;

@@ -422,4 +422,46 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   if (warp == I8_EPI_WARPS + 1) tmem_dealloc(tmemBase, 512);
 }
 
+
+// ----------------------------------------------------------------------------
+// tcgen05 kind::i8 issue-peak probe: one CTA per SM, operands fixed in shared memory (no loads),
+// one thread issues M128 x N256 x K32 MMAs back to back.  Roofline denominator of pair_i8_kernel.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sink) {
+  extern __shared__ __align__(1024) unsigned char smem_pk[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmemSlot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (3 * I8_BLK_BYTES) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_pk)[i] = 0x01010101u * (uint32_t)(i & 3);
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc(smem_u32(&tmemSlot), 512);
+  // make the generic-proxy smem writes visible to the async (tensor core) proxy
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = tmemSlot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+    const uint32_t sA = smem_u32(smem_pk), sB = sA + I8_BLK_BYTES;
+    for (int it = 0; it < iters; ++it) {
+      umma_i8(tmemBase + (uint32_t)((it & 1) * 256), umma_desc(sA + (it & 1) * 256, 128, 512),
+              umma_desc(sB + (it & 1) * 256, 128, 512), idesc, (uint32_t)(it > 1));
+    }
+    umma_commit(smem_u32(&bar));
+    mbar_wait(smem_u32(&bar), 0);
+    tc_fence_after();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int v[4];
+    tmem_ld4(tmemBase, v);
+    tmem_ld_wait();
+    if (sink && v[0] == 0x7fffffff) sink[blockIdx.x] = v[1];
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmemBase, 512);
+}
+
 }  // namespace b200

@@ -186,6 +186,9 @@ int b200_set_mma_variant(int variant);
  * denominator for the pair-tile kernel because MEASURED_PEAKS.json holds no
  * FP64 figure. */
 double b200_measure_fp64_mma_peak(int variant);
+/* Same for the tcgen05 kind::i8 pipe (M128 x N256 x K32 MMAs on operands resident in shared
+ * memory, one CTA per SM); returns int8 TOP/s.  Roofline denominator of the tcgen05 pair engine. */
+double b200_measure_i8_mma_peak(void);
 
 #ifdef __cplusplus
 }
