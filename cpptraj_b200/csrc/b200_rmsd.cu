@@ -271,6 +271,7 @@ int pair_engine() {
   return g_engine;
 }
 std::atomic<int> g_lastEngine{0}, g_lastQs{0};
+long long* g_dbgClk = nullptr;   // device buffer for the kernel's cycle counters (timing experiments)
 
 struct I8Set {  // one quantised frame set resident on the device
   uint8_t* image = nullptr;
@@ -383,6 +384,8 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   a.nJt = (B.nFrames + I8_TILE_J - 1) / I8_TILE_J - a.jt0;
   a.totalMass = d_totalMass; a.invScale2 = std::ldexp(1.0, -2 * qs);
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
+  { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
+  a.dbgClk = g_dbgClk;
   if (a.nIt <= 0 || a.nJt <= 0) return B200_OK;
   const long nTiles = (long)a.nIt * a.nJt;
   const int grid = (int)std::min<long>(nTiles, d.numSMs > 0 ? d.numSMs : 148);
@@ -1132,6 +1135,23 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   return B200_OK;
 }
 
+
+int b200_debug_i8_clocks(long long* out, int ctas) {
+  // Arms (out == NULL) or reads back (out != NULL) the per-CTA cycle counters of pair_i8_kernel: 16 per CTA.
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (ensure_init_locked()) return B200_ERR_NO_DEVICE;
+  if (!out) {
+    if (!g_dbgClk) CU(cudaMalloc(&g_dbgClk, 16 * 1024 * sizeof(long long)));
+    CU(cudaMemset(g_dbgClk, 0, 16 * 1024 * sizeof(long long)));
+    return B200_OK;
+  }
+  if (!g_dbgClk) return fail(B200_ERR_STATE, "clock counters not armed");
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(out, g_dbgClk, (size_t)16 * std::min(ctas, 1024) * sizeof(long long), cudaMemcpyDeviceToHost));
+  CU(cudaFree(g_dbgClk));
+  g_dbgClk = nullptr;
+  return B200_OK;
+}
 
 int b200_set_pair_engine(int engine) {
   if (engine < 0 || engine > 2) return fail(B200_ERR_ARG, "engine must be 0 (auto), 1 (fp64) or 2 (tcgen05 int8)");

@@ -36,13 +36,13 @@ constexpr int I8_STAGES = 5;
 constexpr int I8_STAGE_BYTES = 3 * I8_BLK_BYTES;  // A (1 block) + B (2 blocks) = 24 KB
 constexpr int I8_TILE_I = I8_FR_PER_RG;      // 14
 constexpr int I8_TILE_J = 2 * I8_FR_PER_RG;  // 28
-constexpr int I8_EPI_WARPS = 8;
+constexpr int I8_EPI_WARPS = 16;            // 4 per TMEM sub-partition: 7 j frames (63 accumulator columns) each
 constexpr int I8_EPI_THREADS = I8_EPI_WARPS * 32;
 constexpr int I8_THREADS = I8_EPI_THREADS + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int I8_XROW_BYTES = 24;            // 3 doubles per (operand row, j frame)
 constexpr int I8_XJ_STRIDE = 128 * I8_XROW_BYTES + 88;  // 3160 B: (stride/4) % 32 == 22 -> conflict-free LDS.64
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_STRIDE; // 88480
-constexpr int I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + I8_XBUF_BYTES + 256;
+constexpr int I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + I8_XBUF_BYTES + 256 + 512;   // + barriers + per-tile G
 constexpr long long I8_QMAX = 8355711;       // 127*(1+256+65536): largest |q| with balanced digits
 
 __host__ __device__ inline size_t i8_image_bytes(int nRowGroups, int nC) {
@@ -245,6 +245,8 @@ struct PairI8Args {
   size_t outBase;
   size_t ldo;
   double* dbgS;        // nullable: 9 doubles per (i,j) at (i*nCols + j)*9, integer units
+  long long* dbgClk;   // nullable: per-CTA cycle counters [16] (timing experiments)
+  int dbgMode;         // 0 normal; timing experiments: 1 no per-pair solve, 2 epilogue only frees TMEM, 3 = 2 + no operand loads
 };
 
 template <bool TRI>
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   uint64_t* accFull = bars + 2 * I8_STAGES;    // [2]
   uint64_t* accEmpty = bars + 2 * I8_STAGES + 2;  // [2]
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 4);
+  double* gbuf = reinterpret_cast<double*>(xbuf + I8_XBUF_BYTES + 256);   // [14 GA | 28 GB] of the current tile, integer units
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nTiles = a.nIt * a.nJt;
@@ -285,107 +288,147 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
 
   if (warp == I8_EPI_WARPS) {
     // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
-        int it, jt;
-        if (!i8_tile<TRI>(a, t, it, jt)) continue;
-        const uint8_t* gA = a.PA + (size_t)it * a.nC * I8_BLK_BYTES;
-        const uint8_t* gB0 = a.PB + (size_t)(2 * jt) * a.nC * I8_BLK_BYTES;
-        const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;
-        for (int c = 0; c < a.nC; ++c) {
-          mbar_wait(smem_u32(&emptyBar[stage]), phase ^ 1u);
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t stage0 = smem_u32(stages);
+    long long cwEmpty = 0;
+    if (lane == 0)
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
+      int it, jt;
+      if (!i8_tile<TRI>(a, t, it, jt)) continue;
+      const uint8_t* gA = a.PA + (size_t)it * a.nC * I8_BLK_BYTES;
+      const uint8_t* gB0 = a.PB + (size_t)(2 * jt) * a.nC * I8_BLK_BYTES;
+      const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;
+      for (int c = 0; c < a.nC; ++c) {
+        const long long c0 = a.dbgClk ? clock64() : 0;
+        mbar_wait(smem_u32(&emptyBar[stage]), phase ^ 1u);
+        if (a.dbgClk) cwEmpty += clock64() - c0;
+        {
           const uint32_t bar = smem_u32(&fullBar[stage]);
-          const uint32_t dst = smem_u32(stages + (size_t)stage * I8_STAGE_BYTES);
-          mbar_expect_tx(bar, I8_STAGE_BYTES);
-          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          bulk_g2s(dst + I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          bulk_g2s(dst + 2 * I8_BLK_BYTES, gB1 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
+          const uint32_t dst = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
+          if (a.dbgMode == 3) {
+            mbar_arrive(bar);
+          } else {
+            mbar_expect_tx(bar, I8_STAGE_BYTES);
+            bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+            bulk_g2s(dst + I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+            bulk_g2s(dst + 2 * I8_BLK_BYTES, gB1 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+          }
         }
+        if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
+    if (a.dbgClk && lane == 0) a.dbgClk[16 * blockIdx.x + 0] += cwEmpty;
   } else if (warp == I8_EPI_WARPS + 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_i8(128, 256);
-      int stage = 0; uint32_t phase = 0; int n = 0;
-      for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
-        int it, jt;
-        if (!i8_tile<TRI>(a, t, it, jt)) continue;
-        const int b = n & 1;
-        mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
-        for (int c = 0; c < a.nC; ++c) {
-          mbar_wait(smem_u32(&fullBar[stage]), phase);
-          tc_fence_after();
-          const uint32_t sA = smem_u32(stages + (size_t)stage * I8_STAGE_BYTES);
-          const uint32_t sB = sA + I8_BLK_BYTES;
-#pragma unroll
-          for (int k = 0; k < I8_KC / 32; ++k) {
-            umma_i8(dTmem, umma_desc(sA + k * 256, 128, 512), umma_desc(sB + k * 256, 128, 512), idesc,
-                    (uint32_t)((c | k) != 0));
-          }
-          umma_commit(smem_u32(&emptyBar[stage]));
-          if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(smem_u32(&accFull[b]));
-        ++n;
-      }
-    }
-  } else {
-    // ===================== epilogue warps =====================
-    const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
-    const int half = warp >> 2;       // columns 128*half .. : j frames 14*half .. 14*half+13
-    const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit
-    const double wdig = (r % 3 == 0) ? 1.0 : ((r % 3 == 1) ? 256.0 : 65536.0);
-    const double invM = 1.0 / a.totalMass[0];
-    int n = 0;
+    constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+    // descriptor = constant high part (LBO 128 B, SBO 512 B, version 1) | (smem address >> 4)
+    constexpr uint64_t descHi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
+    const uint32_t stage0 = smem_u32(stages);
+    int stage = 0; uint32_t phase = 0; int n = 0;
+    long long cwAcc = 0, cwFull = 0, cTot = 0;
+    const long long cStart = a.dbgClk ? clock64() : 0;
+    if (lane == 0)
     for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
       int it, jt;
       if (!i8_tile<TRI>(a, t, it, jt)) continue;
       const int b = n & 1;
-      mbar_wait(smem_u32(&accFull[b]), (uint32_t)((n >> 1) & 1));
+      long long c0 = a.dbgClk ? clock64() : 0;
+      mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
+      if (a.dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
-      const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + half * 128) + ((uint32_t)(32 * sp) << 16);
+      const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
+      for (int c = 0; c < a.nC; ++c) {
+        c0 = a.dbgClk ? clock64() : 0;
+        mbar_wait(smem_u32(&fullBar[stage]), phase);
+        if (a.dbgClk) cwFull += clock64() - c0;
+        tc_fence_after();
+        const uint32_t sA = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
+        const uint64_t dA = descHi | (uint64_t)((sA >> 4) & 0x3fff);
+        const uint64_t dB = descHi | (uint64_t)(((sA + I8_BLK_BYTES) >> 4) & 0x3fff);
+#pragma unroll
+        for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
+          if (a.dbgMode != 5) umma_i8(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | k) != 0));
+        umma_commit(smem_u32(&emptyBar[stage]));
+        if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(smem_u32(&accFull[b]));
+      ++n;
+    }
+    if (a.dbgClk && lane == 0) {
+      cTot = clock64() - cStart;
+      a.dbgClk[16 * blockIdx.x + 1] += cwAcc; a.dbgClk[16 * blockIdx.x + 2] += cwFull;
+      a.dbgClk[16 * blockIdx.x + 3] += cTot; a.dbgClk[16 * blockIdx.x + 4] += n;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    // Latency-bound work (TMEM loads, int64 -> FP64 conversions, Newton iterations): 16 warps keep
+    // four independent instruction streams per scheduler in flight.
+    const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
+    const int cg = warp >> 2;         // column group: j frames 7*cg .. 7*cg+6 of the tile
+    const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit
+    const double wdig = (r % 3 == 0) ? 1.0 : ((r % 3 == 1) ? 256.0 : 65536.0);
+    const double wmagic = -6755399441055744.0 * wdig;   // -(1.5 * 2^52) * weight
+    const double outScale = 2.0 * a.invScale2 / a.totalMass[0];   // rmsd^2 = (E0 - lambda) * outScale (integer units)
+    const double toInt = 1.0 / a.invScale2;                        // G (A^2) -> integer units (exact power of two)
+    // first accumulator column of frame 7*cg: frames 0..13 start at 9*jl, frames 14..27 at 128 + 9*(jl-14)
+    const int col0 = (cg >> 1) * 128 + (cg & 1) * 63;
+    int n = 0;
+    long long cwFullAcc = 0, cRow = 0, cBar1 = 0, cPair = 0, cBar2 = 0;
+    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
+      int it, jt;
+      if (!i8_tile<TRI>(a, t, it, jt)) continue;
+      const int b = n & 1;
+      long long c0 = a.dbgClk ? clock64() : 0, c1;
+      mbar_wait(smem_u32(&accFull[b]), (uint32_t)((n >> 1) & 1));
+      if (a.dbgClk) { c1 = clock64(); cwFullAcc += c1 - c0; c0 = c1; }
+      tc_fence_after();
+      if (a.dbgMode >= 2 && a.dbgMode <= 3) {   // timing experiment: MMA + operand pipeline only
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+        ++n;
+        continue;
+      }
       // ---- row phase: digits of B folded in-thread, result to the exchange buffer ----
-      auto fold = [&](const int* v, int jl0, int nj) {
+      {
+        double gval = 0.0;
+        if (tid < I8_TILE_I) {
+          const int i = I8_TILE_I * it + tid;
+          if (i < a.nRows) gval = a.GA[i] * toInt;
+        } else if (tid < I8_TILE_I + I8_TILE_J) {
+          const int j = I8_TILE_J * jt + tid - I8_TILE_I;
+          if (j < a.nCols) gval = a.GB[j] * toInt;
+        }
+        int v[64];
+        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + col0) + ((uint32_t)(32 * sp) << 16);
+        tmem_ld32(tcol, v);
+        tmem_ld32(tcol + 32, v + 32);
+        tmem_ld_wait();
+        // this warp is done reading accumulator buffer b
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+        double* dst = reinterpret_cast<double*>(xbuf + (size_t)(7 * cg) * I8_XJ_STRIDE + (size_t)r * I8_XROW_BYTES);
+        if (a.dbgMode != 7)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          if (jj < nj) {
-            double* dst = reinterpret_cast<double*>(xbuf + (size_t)(jl0 + jj) * I8_XJ_STRIDE + (size_t)r * I8_XROW_BYTES);
+        for (int jj = 0; jj < 7; ++jj) {
 #pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const long long s = (long long)v[9 * jj + 3 * q] + (long long)v[9 * jj + 3 * q + 1] * 256 +
-                                  (long long)v[9 * jj + 3 * q + 2] * 65536;
-              dst[q] = (double)s * wdig;
-            }
+          for (int q = 0; q < 3; ++q) {
+            // exact int64 -> FP64 without the (slow, XU-pipe) I2F.F64.S64: for |V| < 2^51 the bit pattern
+            // 0x4338000000000000 + V is the double 1.5*2^52 + V; one FMA removes the offset and applies the
+            // digit weight of this operand row (both exact).
+            const long long sv = 0x4338000000000000LL + (long long)v[9 * jj + 3 * q] +
+                                 (long long)v[9 * jj + 3 * q + 1] * 256 + (long long)v[9 * jj + 3 * q + 2] * 65536;
+            dst[(size_t)jj * (I8_XJ_STRIDE / 8) + q] = fma(__longlong_as_double(sv), wdig, wmagic);
           }
         }
-      };
-#pragma unroll 1
-      for (int grp = 0; grp < 3; ++grp) {   // 4 j frames = 36 accumulator columns per step
-        int v[36];
-        tmem_ld32(tcol + grp * 36, v);
-        tmem_ld4(tcol + grp * 36 + 32, v + 32);
-        tmem_ld_wait();
-        fold(v, 14 * half + 4 * grp, 4);
+        if (tid < I8_TILE_I + I8_TILE_J) gbuf[tid] = gval;
       }
-      {                                      // last 2 j frames: columns 108..125 (+2 zero columns)
-        int v[20];
-        tmem_ld16(tcol + 108, v);
-        tmem_ld4(tcol + 124, v + 16);
-        tmem_ld_wait();
-        fold(v, 14 * half + 12, 2);
-      }
-      // this warp is done reading accumulator buffer b
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+      if (a.dbgClk) { c1 = clock64(); cRow += c1 - c0; c0 = c1; }
       epi_bar_sync();   // exchange buffer complete
+      if (a.dbgClk) { c1 = clock64(); cBar1 += c1 - c0; c0 = c1; }
       // ---- pair phase: one thread per frame pair ----
-      for (int e = tid; e < I8_TILE_I * I8_TILE_J; e += I8_EPI_THREADS) {
+      for (int e = tid; e < I8_TILE_I * I8_TILE_J && a.dbgMode != 6; e += I8_EPI_THREADS) {
         const int il = e / I8_TILE_J, jl = e % I8_TILE_J;
         const int i = I8_TILE_I * it + il, j = I8_TILE_J * jt + jl;
         if (i >= a.nRows || j >= a.nCols || i < a.rowLo || i >= a.rowHi) continue;
@@ -401,18 +444,34 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
 #pragma unroll
           for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
         }
-#pragma unroll
-        for (int x = 0; x < 9; ++x) S[x] *= a.invScale2;
-        const double rms = rmsd_fit_from_cov(S, 0.5 * (a.GA[i] + a.GB[j]), invM);
+        // everything stays in integer units (exact); one scale at the very end
+        const double e0 = 0.5 * (gbuf[il] + gbuf[I8_TILE_I + jl]);
+        float rms;
+        if (a.dbgMode == 1) {
+          rms = (float)(S[0] + S[4] + S[8]);
+        } else {
+          double gap;   // (E0 - lambda_max) / E0
+          if (!relative_gap_fast(S, e0, gap)) gap = (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
+          // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
+          // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
+          const double r2 = gap * e0 * outScale;
+          rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
+        }
         size_t idx;
         if (TRI)
           idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
         else
           idx = (size_t)i * a.ldo + (size_t)j;
-        a.out[idx] = (float)rms;
+        a.out[idx] = rms;
       }
+      if (a.dbgClk) { c1 = clock64(); cPair += c1 - c0; c0 = c1; }
       epi_bar_sync();   // exchange buffer free again
+      if (a.dbgClk) { c1 = clock64(); cBar2 += c1 - c0; c0 = c1; }
       ++n;
+    }
+    if (a.dbgClk && (tid == 0 || tid == 64)) {
+      long long* o = a.dbgClk + 16 * blockIdx.x + (tid == 0 ? 5 : 10);
+      o[0] += cwFullAcc; o[1] += cRow; o[2] += cBar1; o[3] += cPair; o[4] += cBar2;
     }
   }
   // ---- teardown ----

@@ -177,6 +177,10 @@ int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames,
                   unsigned char* imageOut, size_t imageCap, size_t* imageBytes,
                   double* GOut, double* SOut, float* outTri, int* qsOut);
 
+/* Timing experiments: out == NULL arms per-CTA cycle counters (16 per CTA) that the next
+ * tcgen05 pair launches fill in; a later call with out != NULL copies them back and disarms. */
+int b200_debug_i8_clocks(long long* out, int ctas);
+
 /* Tuning knob: PTX shape used for the FP64 MMAs of the pair kernel
  * (0 m8n8k4, 1 m16n8k4, 2 m16n8k8, 3 m16n8k16; all lower to DMMA.8x8x4 SASS). */
 int b200_set_mma_variant(int variant);
