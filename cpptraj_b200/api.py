@@ -59,6 +59,8 @@ def lib():
     L.b200_measure_fp64_mma_peak.argtypes = [i]
     L.b200_measure_fp64_mma_peak.restype = dbl
     L.b200_measure_i8_mma_peak.restype = dbl
+    L.b200_measure_i8_mma_peak_variant.argtypes = [i]
+    L.b200_measure_i8_mma_peak_variant.restype = dbl
     for name in ("b200_init", "b200_init_devices", "b200_shard_rows", "b200_rms2d_tri", "b200_rms2d_tri_shard",
                  "b200_rms2d_full", "b200_rmsd_1vN_begin", "b200_rmsd_1vN_push_f64", "b200_rmsd_1vN_push_f32",
                  "b200_rmsd_1vN_flush", "b200_rmsd_1vN_end", "b200_dev_rms2d_tri", "b200_dev_rmsd_1vN",
@@ -276,8 +278,8 @@ def set_mma_variant(v):
     _check(lib().b200_set_mma_variant(int(v)))
 
 
-def measure_i8_mma_peak():
-    return lib().b200_measure_i8_mma_peak()
+def measure_i8_mma_peak(variant=0):
+    return lib().b200_measure_i8_mma_peak_variant(int(variant))
 
 
 def measure_fp64_mma_peak(variant=0):

@@ -379,15 +379,17 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   PairI8Args a;
   a.PA = A.image; a.PB = B.image; a.GA = A.G; a.GB = B.G; a.nC = A.nC;
   a.nRows = A.nFrames; a.nCols = B.nFrames; a.rowLo = rowLo; a.rowHi = rowHi;
-  a.it0 = rowLo / I8_TILE_I; a.nIt = (rowHi + I8_TILE_I - 1) / I8_TILE_I - a.it0;
+  a.it0 = rowLo / I8_TILE_I; a.it1 = (rowHi + I8_TILE_I - 1) / I8_TILE_I;
   a.jt0 = tri ? (rowLo + 1) / I8_TILE_J : 0;
-  a.nJt = (B.nFrames + I8_TILE_J - 1) / I8_TILE_J - a.jt0;
+  a.jt1 = (B.nFrames + I8_TILE_J - 1) / I8_TILE_J;
   a.totalMass = d_totalMass; a.invScale2 = std::ldexp(1.0, -2 * qs);
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
   { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
   a.dbgClk = g_dbgClk;
-  if (a.nIt <= 0 || a.nJt <= 0) return B200_OK;
-  const long nTiles = (long)a.nIt * a.nJt;
+  if (a.it1 <= a.it0 || a.jt1 <= a.jt0) return B200_OK;
+  const long nTiles = tri ? i8_count_tiles<true>(a.it0, a.it1, a.jt0, a.jt1) : i8_count_tiles<false>(a.it0, a.it1, a.jt0, a.jt1);
+  if (nTiles <= 0) return B200_OK;
+  if (nTiles > 0x7fffffffL - 1024) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
   const int grid = (int)std::min<long>(nTiles, d.numSMs > 0 ? d.numSMs : 148);
   return tri ? launch_pair_i8_t<true>(a, grid, st) : launch_pair_i8_t<false>(a, grid, st);
 }
@@ -1218,7 +1220,9 @@ int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames, const
 }
 
 
-double b200_measure_i8_mma_peak(void) {
+double b200_measure_i8_mma_peak(void) { return b200_measure_i8_mma_peak_variant(0); }
+
+double b200_measure_i8_mma_peak_variant(int variant) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (ensure_init_locked()) return -1.0;
   cudaDeviceProp prop;
@@ -1229,12 +1233,12 @@ double b200_measure_i8_mma_peak(void) {
   if (cudaFuncSetAttribute(i8_mma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1.0;
   cudaEvent_t a, b;
   cudaEventCreate(&a); cudaEventCreate(&b);
-  i8_mma_peak_kernel<<<blocks, 128, smem>>>(256, nullptr);
+  i8_mma_peak_kernel<<<blocks, 128, smem>>>(256, nullptr, variant);
   cudaDeviceSynchronize();
   float best = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
     cudaEventRecord(a);
-    i8_mma_peak_kernel<<<blocks, 128, smem>>>(iters, nullptr);
+    i8_mma_peak_kernel<<<blocks, 128, smem>>>(iters, nullptr, variant);
     cudaEventRecord(b);
     cudaEventSynchronize(b);
     float ms = 0.f;

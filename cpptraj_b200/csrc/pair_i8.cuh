@@ -36,13 +36,6 @@ constexpr int I8_STAGES = 5;
 constexpr int I8_STAGE_BYTES = 3 * I8_BLK_BYTES;  // A (1 block) + B (2 blocks) = 24 KB
 constexpr int I8_TILE_I = I8_FR_PER_RG;      // 14
 constexpr int I8_TILE_J = 2 * I8_FR_PER_RG;  // 28
-constexpr int I8_EPI_WARPS = 16;            // 4 per TMEM sub-partition: 7 j frames (63 accumulator columns) each
-constexpr int I8_EPI_THREADS = I8_EPI_WARPS * 32;
-constexpr int I8_THREADS = I8_EPI_THREADS + 64;   // + TMA producer warp + MMA issuer warp
-constexpr int I8_XROW_BYTES = 24;            // 3 doubles per (operand row, j frame)
-constexpr int I8_XJ_STRIDE = 128 * I8_XROW_BYTES + 88;  // 3160 B: (stride/4) % 32 == 22 -> conflict-free LDS.64
-constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_STRIDE; // 88480
-constexpr int I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + I8_XBUF_BYTES + 256 + 512;   // + barriers + per-tile G
 constexpr long long I8_QMAX = 8355711;       // 127*(1+256+65536): largest |q| with balanced digits
 
 __host__ __device__ inline size_t i8_image_bytes(int nRowGroups, int nC) {
@@ -224,11 +217,39 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, int* v) {
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(I8_EPI_THREADS) : "memory"); }
 
 // ----------------------------------------------------------------------------
 // pair_i8_kernel
+//
+// Persistent, warp-specialised, one CTA per SM.  Roles (20 warps):
+//   warp 18       TMA producer: operand stages (A block + 2 B blocks per 64 atoms) through a
+//                 5-deep full/empty mbarrier ring
+//   warp 19       MMA issuer: tcgen05.mma kind::i8 M128 N256 K32 into one of two TMEM accumulators
+//   warps 0..3    drain: one per TMEM sub-partition; tcgen05.ld 64 accumulator columns (7 column
+//                 frames x 9), fold the three B digits in-thread, apply the A digit weight of
+//                 the own operand row, hand 21 doubles per thread to the exchange buffer
+//   warps 4..17   solve: one thread per frame pair (2 row frames x 14 column frames per warp):
+//                 gather the 27 partial sums of the pair, fold the A digits, per-pair solve,
+//                 store the float straight into cpptraj's Matrix<float> layout
+// The exchange buffer is a ring of four column groups (7 column frames each) with its own
+// full/empty mbarriers, so the drain of tile n+1 runs under the solve of tile n, both under the
+// MMAs of tile n+2: no CTA-wide barrier anywhere in the steady state.
+// Tiles are enumerated column tile by column tile (valid row tiles only), tile t of that list
+// going to CTA t % gridDim.x: every CTA gets the same number of tiles (+-1) and CTAs running
+// at the same time share their B operand in L2.
 // ----------------------------------------------------------------------------
+constexpr int I8_DRAIN_WARPS = 4;
+constexpr int I8_SOLVE_WARPS = 14;
+constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 18
+constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 19
+constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
+constexpr int I8_XROW_BYTES = 24;            // 3 doubles per (operand row, column frame)
+constexpr int I8_XJ_STRIDE = 128 * I8_XROW_BYTES + 88;  // 3160 B: (stride/4) % 32 == 22 -> conflict-free LDS.64 / STS.64
+constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_STRIDE;  // 88480
+constexpr int I8_NBARS = 2 * I8_STAGES + 4 + 8;
+constexpr int I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + I8_XBUF_BYTES + 256;   // + barriers
+static_assert(I8_NBARS * 8 + 8 <= 256, "barrier block");
+
 struct PairI8Args {
   const uint8_t* PA;   // operand images of the row frames (i)
   const uint8_t* PB;   // operand images of the column frames (j); even number of row groups allocated
@@ -237,8 +258,8 @@ struct PairI8Args {
   int nC;              // 64-atom chunks
   int nRows, nCols;    // valid i / j frames
   int rowLo, rowHi;    // rows written by this launch: [rowLo, rowHi)
-  int it0, nIt;        // i tiles (14 frames) of this launch
-  int jt0, nJt;        // j tiles (28 frames) of this launch
+  int it0, it1;        // i tiles (14 frames) of this launch: [it0, it1)
+  int jt0, jt1;        // j tiles (28 frames) of this launch: [jt0, jt1)
   const double* totalMass;
   double invScale2;    // 2^-2qs: integer covariance -> A^2
   float* out;          // TRI: out[triIndex - outBase]; FULL: out[i*ldo + j]
@@ -246,17 +267,93 @@ struct PairI8Args {
   size_t ldo;
   double* dbgS;        // nullable: 9 doubles per (i,j) at (i*nCols + j)*9, integer units
   long long* dbgClk;   // nullable: per-CTA cycle counters [16] (timing experiments)
-  int dbgMode;         // 0 normal; timing experiments: 1 no per-pair solve, 2 epilogue only frees TMEM, 3 = 2 + no operand loads
+  int dbgMode;         // 0 normal; timing experiments: 1 no per-pair solve, 2 drain only frees TMEM,
+                       // 3 = 2 + no operand loads, 6 = solve warps only recycle the exchange buffer
 };
 
+/// Row tiles [it0, hi) of column tile jt hold at least one wanted pair.
 template <bool TRI>
-__device__ __forceinline__ bool i8_tile(const PairI8Args& a, int t, int& it, int& jt) {
-  it = a.it0 + t % a.nIt;
-  jt = a.jt0 + t / a.nIt;
-  if (I8_TILE_I * it >= a.nRows || I8_TILE_J * jt >= a.nCols) return false;
-  if (I8_TILE_I * it >= a.rowHi || I8_TILE_I * it + I8_TILE_I <= a.rowLo) return false;
-  if (TRI && I8_TILE_J * jt + I8_TILE_J - 1 <= I8_TILE_I * it) return false;  // every j <= every i
-  return true;
+__host__ __device__ __forceinline__ int i8_col_tiles(int it0, int it1, int jt) {
+  // TRI: a tile is wanted iff its largest j exceeds its smallest i: 28 jt + 27 > 14 it  <=>  it <= 2 jt + 1
+  const int hi = TRI ? (it1 < 2 * jt + 2 ? it1 : 2 * jt + 2) : it1;
+  return hi > it0 ? hi - it0 : 0;
+}
+template <bool TRI>
+__host__ __device__ inline long i8_count_tiles(int it0, int it1, int jt0, int jt1) {
+  long n = 0;
+  for (int jt = jt0; jt < jt1; ++jt) n += i8_col_tiles<TRI>(it0, it1, jt);
+  return n;
+}
+/// Walks this CTA's share of the tile list; every role keeps its own copy (two registers).
+template <bool TRI>
+struct I8TileIter {
+  int jt, base, t;
+  __device__ __forceinline__ void init(const PairI8Args& a) { jt = a.jt0; base = 0; t = (int)blockIdx.x; }
+  __device__ __forceinline__ bool next(const PairI8Args& a, int& it, int& jtOut) {
+    while (jt < a.jt1) {
+      const int c = i8_col_tiles<TRI>(a.it0, a.it1, jt);
+      if (t < base + c) { it = a.it0 + (t - base); jtOut = jt; t += (int)gridDim.x; return true; }
+      base += c; ++jt;
+    }
+    return false;
+  }
+};
+
+/// (E0 - lambda_max)/E0 for the tcgen05 epilogue.  FP64 dependent-issue latency is long on this part, so
+/// the FP64 chain is kept as short as the cancellation allows.  With everything divided by E0 the key-matrix
+/// quartic is P(x) = x^4 + c2 x^2 + c1 x + c0 with the wanted root x = lambda/E0 in (0,1]; x = 1 - y gives
+///     Q(y) = y^4 - 4 y^3 + (6 + c2) y^2 - (4 + 2 c2 + c1) y + (1 + c2 + c1 + c0),
+/// whose smallest non-negative root y is the quantity the RMSD needs.  The coefficients (q0 is a
+/// cancellation down to ~y) and ONE final Newton correction are FP64; the monotone approach from y = 0 runs
+/// in FP32, which resolves y to ~1e-7 RELATIVE whatever its magnitude.  Returns false when the root is
+/// ill-conditioned or the correction is not small: the caller then takes the guarded FP64 path.
+__device__ __forceinline__ bool i8_relative_gap(const double* S, double sInv, double& gap) {
+  double T[9];
+#pragma unroll
+  for (int x = 0; x < 9; ++x) T[x] = S[x] * sInv;
+  const double m00 = fma(T[6], T[6], fma(T[3], T[3], T[0] * T[0]));
+  const double m11 = fma(T[7], T[7], fma(T[4], T[4], T[1] * T[1]));
+  const double m22 = fma(T[8], T[8], fma(T[5], T[5], T[2] * T[2]));
+  const double m01 = fma(T[6], T[7], fma(T[3], T[4], T[0] * T[1]));
+  const double m02 = fma(T[6], T[8], fma(T[3], T[5], T[0] * T[2]));
+  const double m12 = fma(T[7], T[8], fma(T[4], T[5], T[1] * T[2]));
+  const double p1 = (m00 + m11) + m22;
+  const double off = fma(m01, m01, fma(m02, m02, m12 * m12));
+  const double trM2 = fma(2.0, off, fma(m00, m00, fma(m11, m11, m22 * m22)));
+  const double det = fma(T[0], fma(T[4], T[8], -T[5] * T[7]), fma(-T[1], fma(T[3], T[8], -T[5] * T[6]),
+                                                                  T[2] * fma(T[3], T[7], -T[4] * T[6])));
+  const double c2 = -2.0 * p1, c1 = -8.0 * det, c0 = fma(2.0, trM2, -p1 * p1);
+  const double q0 = ((1.0 + c2) + c1) + c0;
+  const double q1 = -((4.0 + 2.0 * c2) + c1);
+  const double q2 = 6.0 + c2;
+  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2;
+  float y = 0.f, dq = f1, step;
+#pragma unroll
+  for (int it = 0; it < 3; ++it) {
+    const float qy = fmaf(fmaf(fmaf(y - 4.f, y, f2), y, f1), y, f0);
+    dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+    y -= __fdividef(qy, dq);
+  }
+#pragma unroll 1
+  for (int it = 0; it < 24; ++it) {   // until the whole warp has converged (gaps up to y ~ 0.5: RMSD ~ radius of gyration)
+    const float qy = fmaf(fmaf(fmaf(y - 4.f, y, f2), y, f1), y, f0);
+    dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+    step = __fdividef(qy, dq);
+    y -= step;
+    if (!__any_sync(0xffffffffu, fabsf(step) > 4e-7f * fabsf(y))) break;
+  }
+  double yd = (double)y;
+  const double Q = fma(fma(fma(yd - 4.0, yd, q2), yd, q1), yd, q0);
+  dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+  const double d = Q * (double)__frcp_rn(dq);
+  yd -= d;
+  gap = yd;
+  // conditioning (|P'| relative to lambda^3 = 1 here) and size of the correction (FP32 left ~1e-7 relative)
+  return (fabsf(dq) >= 7e-3f) && (fabs(d) <= 1e-5 * fabs(yd) + 1e-14) && (yd < 1.5);
+}
+/// Guarded FP64 path (Newton on the unscaled quartic, SVD for double roots); rarely taken.
+__device__ __noinline__ double i8_relative_gap_slow(const double* S, double e0) {
+  return (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
 }
 
 template <bool TRI>
@@ -265,36 +362,38 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   unsigned char* stages = smem_i8;
   unsigned char* xbuf = smem_i8 + I8_STAGES * I8_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + I8_XBUF_BYTES);
-  uint64_t* fullBar = bars;                    // [I8_STAGES]
-  uint64_t* emptyBar = bars + I8_STAGES;       // [I8_STAGES]
-  uint64_t* accFull = bars + 2 * I8_STAGES;    // [2]
-  uint64_t* accEmpty = bars + 2 * I8_STAGES + 2;  // [2]
-  uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + 2 * I8_STAGES + 4);
-  double* gbuf = reinterpret_cast<double*>(xbuf + I8_XBUF_BYTES + 256);   // [14 GA | 28 GB] of the current tile, integer units
+  uint64_t* fullBar = bars;                        // [I8_STAGES]  operands landed
+  uint64_t* emptyBar = bars + I8_STAGES;           // [I8_STAGES]  MMAs reading the stage done
+  uint64_t* accFull = bars + 2 * I8_STAGES;        // [2]  accumulator complete
+  uint64_t* accEmpty = bars + 2 * I8_STAGES + 2;   // [2]  accumulator drained
+  uint64_t* xFull = bars + 2 * I8_STAGES + 4;      // [4]  exchange group written
+  uint64_t* xEmpty = bars + 2 * I8_STAGES + 8;     // [4]  exchange group read
+  uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nTiles = a.nIt * a.nJt;
 
   if (tid == 0) {
     for (int s = 0; s < I8_STAGES; ++s) { mbar_init(smem_u32(&fullBar[s]), 1); mbar_init(smem_u32(&emptyBar[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_EPI_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS); }
+    for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), I8_DRAIN_WARPS); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
     mbar_fence_init();
   }
-  if (warp == I8_EPI_WARPS + 1) tmem_alloc(smem_u32(tmemBaseSlot), 512);
+  if (warp == I8_WARP_MMA) tmem_alloc(smem_u32(tmemBaseSlot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmemBase = *tmemBaseSlot;
+  I8TileIter<TRI> tiles;
+  tiles.init(a);
+  int it, jt;
 
-  if (warp == I8_EPI_WARPS) {
+  if (warp == I8_WARP_PRODUCER) {
     // ===================== TMA producer (one thread) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage0 = smem_u32(stages);
     long long cwEmpty = 0;
     if (lane == 0)
-    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
-      int it, jt;
-      if (!i8_tile<TRI>(a, t, it, jt)) continue;
+    while (tiles.next(a, it, jt)) {
       const uint8_t* gA = a.PA + (size_t)it * a.nC * I8_BLK_BYTES;
       const uint8_t* gB0 = a.PB + (size_t)(2 * jt) * a.nC * I8_BLK_BYTES;
       const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;
@@ -302,35 +401,31 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         const long long c0 = a.dbgClk ? clock64() : 0;
         mbar_wait(smem_u32(&emptyBar[stage]), phase ^ 1u);
         if (a.dbgClk) cwEmpty += clock64() - c0;
-        {
-          const uint32_t bar = smem_u32(&fullBar[stage]);
-          const uint32_t dst = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
-          if (a.dbgMode == 3) {
-            mbar_arrive(bar);
-          } else {
-            mbar_expect_tx(bar, I8_STAGE_BYTES);
-            bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-            bulk_g2s(dst + I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-            bulk_g2s(dst + 2 * I8_BLK_BYTES, gB1 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          }
+        const uint32_t bar = smem_u32(&fullBar[stage]);
+        const uint32_t dst = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
+        if (a.dbgMode == 3) {
+          mbar_arrive(bar);
+        } else {
+          mbar_expect_tx(bar, I8_STAGE_BYTES);
+          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+          bulk_g2s(dst + I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+          bulk_g2s(dst + 2 * I8_BLK_BYTES, gB1 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
         }
         if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
     if (a.dbgClk && lane == 0) a.dbgClk[16 * blockIdx.x + 0] += cwEmpty;
-  } else if (warp == I8_EPI_WARPS + 1) {
+  } else if (warp == I8_WARP_MMA) {
     // ===================== MMA issuer (one thread) =====================
     constexpr uint32_t idesc = umma_idesc_i8(128, 256);
     // descriptor = constant high part (LBO 128 B, SBO 512 B, version 1) | (smem address >> 4)
     constexpr uint64_t descHi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     const uint32_t stage0 = smem_u32(stages);
     int stage = 0; uint32_t phase = 0; int n = 0;
-    long long cwAcc = 0, cwFull = 0, cTot = 0;
+    long long cwAcc = 0, cwFull = 0;
     const long long cStart = a.dbgClk ? clock64() : 0;
     if (lane == 0)
-    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
-      int it, jt;
-      if (!i8_tile<TRI>(a, t, it, jt)) continue;
+    while (tiles.next(a, it, jt)) {
       const int b = n & 1;
       long long c0 = a.dbgClk ? clock64() : 0;
       mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
@@ -347,7 +442,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         const uint64_t dB = descHi | (uint64_t)(((sA + I8_BLK_BYTES) >> 4) & 0x3fff);
 #pragma unroll
         for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
-          if (a.dbgMode != 5) umma_i8(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | k) != 0));
+          umma_i8(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | k) != 0));
         umma_commit(smem_u32(&emptyBar[stage]));
         if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -355,61 +450,49 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       ++n;
     }
     if (a.dbgClk && lane == 0) {
-      cTot = clock64() - cStart;
       a.dbgClk[16 * blockIdx.x + 1] += cwAcc; a.dbgClk[16 * blockIdx.x + 2] += cwFull;
-      a.dbgClk[16 * blockIdx.x + 3] += cTot; a.dbgClk[16 * blockIdx.x + 4] += n;
+      a.dbgClk[16 * blockIdx.x + 3] += clock64() - cStart; a.dbgClk[16 * blockIdx.x + 4] += n;
     }
-  } else {
-    // ===================== epilogue warps =====================
-    // Latency-bound work (TMEM loads, int64 -> FP64 conversions, Newton iterations): 16 warps keep
-    // four independent instruction streams per scheduler in flight.
-    const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
-    const int cg = warp >> 2;         // column group: j frames 7*cg .. 7*cg+6 of the tile
+  } else if (warp < I8_DRAIN_WARPS) {
+    // ===================== drain warps =====================
+    const int sp = warp;              // TMEM sub-partition: lanes 32*sp .. 32*sp+31
     const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit
     const double wdig = (r % 3 == 0) ? 1.0 : ((r % 3 == 1) ? 256.0 : 65536.0);
     const double wmagic = -6755399441055744.0 * wdig;   // -(1.5 * 2^52) * weight
-    const double outScale = 2.0 * a.invScale2 / a.totalMass[0];   // rmsd^2 = (E0 - lambda) * outScale (integer units)
-    const double toInt = 1.0 / a.invScale2;                        // G (A^2) -> integer units (exact power of two)
-    // first accumulator column of frame 7*cg: frames 0..13 start at 9*jl, frames 14..27 at 128 + 9*(jl-14)
-    const int col0 = (cg >> 1) * 128 + (cg & 1) * 63;
+    unsigned char* xrow = xbuf + (size_t)r * I8_XROW_BYTES;
     int n = 0;
-    long long cwFullAcc = 0, cRow = 0, cBar1 = 0, cPair = 0, cBar2 = 0;
-    for (int t = blockIdx.x; t < nTiles; t += gridDim.x) {
-      int it, jt;
-      if (!i8_tile<TRI>(a, t, it, jt)) continue;
+    long long cwAcc = 0, cwX = 0;
+    const long long cStart = a.dbgClk ? clock64() : 0;
+    while (tiles.next(a, it, jt)) {
       const int b = n & 1;
-      long long c0 = a.dbgClk ? clock64() : 0, c1;
+      long long c0 = a.dbgClk ? clock64() : 0;
       mbar_wait(smem_u32(&accFull[b]), (uint32_t)((n >> 1) & 1));
-      if (a.dbgClk) { c1 = clock64(); cwFullAcc += c1 - c0; c0 = c1; }
+      if (a.dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
-      if (a.dbgMode >= 2 && a.dbgMode <= 3) {   // timing experiment: MMA + operand pipeline only
+      if (a.dbgMode == 2 || a.dbgMode == 3) {   // timing experiment: MMA + operand pipeline only
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
         ++n;
         continue;
       }
-      // ---- row phase: digits of B folded in-thread, result to the exchange buffer ----
-      {
-        double gval = 0.0;
-        if (tid < I8_TILE_I) {
-          const int i = I8_TILE_I * it + tid;
-          if (i < a.nRows) gval = a.GA[i] * toInt;
-        } else if (tid < I8_TILE_I + I8_TILE_J) {
-          const int j = I8_TILE_J * jt + tid - I8_TILE_I;
-          if (j < a.nCols) gval = a.GB[j] * toInt;
-        }
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        // column frames 7g .. 7g+6: accumulator columns 9*jl (frames 0..13) or 128 + 9*(jl-14) (frames 14..27)
+        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + (g >> 1) * 128 + (g & 1) * 63) + ((uint32_t)(32 * sp) << 16);
         int v[64];
-        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + col0) + ((uint32_t)(32 * sp) << 16);
         tmem_ld32(tcol, v);
         tmem_ld32(tcol + 32, v + 32);
+        c0 = a.dbgClk ? clock64() : 0;
+        mbar_wait(smem_u32(&xEmpty[g]), (uint32_t)((n & 1) ^ 1));   // the solve warps are done with this group of tile n-1
+        if (a.dbgClk) cwX += clock64() - c0;
         tmem_ld_wait();
-        // this warp is done reading accumulator buffer b
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
-        double* dst = reinterpret_cast<double*>(xbuf + (size_t)(7 * cg) * I8_XJ_STRIDE + (size_t)r * I8_XROW_BYTES);
-        if (a.dbgMode != 7)
+        if (g == 3) {   // this warp is done reading accumulator buffer b
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+        }
+        double* dst = reinterpret_cast<double*>(xrow + (size_t)(7 * g) * I8_XJ_STRIDE);
 #pragma unroll
         for (int jj = 0; jj < 7; ++jj) {
 #pragma unroll
@@ -422,41 +505,80 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
             dst[(size_t)jj * (I8_XJ_STRIDE / 8) + q] = fma(__longlong_as_double(sv), wdig, wmagic);
           }
         }
-        if (tid < I8_TILE_I + I8_TILE_J) gbuf[tid] = gval;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&xFull[g]));
       }
-      if (a.dbgClk) { c1 = clock64(); cRow += c1 - c0; c0 = c1; }
-      epi_bar_sync();   // exchange buffer complete
-      if (a.dbgClk) { c1 = clock64(); cBar1 += c1 - c0; c0 = c1; }
-      // ---- pair phase: one thread per frame pair ----
-      for (int e = tid; e < I8_TILE_I * I8_TILE_J && a.dbgMode != 6; e += I8_EPI_THREADS) {
-        const int il = e / I8_TILE_J, jl = e % I8_TILE_J;
-        const int i = I8_TILE_I * it + il, j = I8_TILE_J * jt + jl;
-        if (i >= a.nRows || j >= a.nCols || i < a.rowLo || i >= a.rowHi) continue;
-        if (TRI && j <= i) continue;
-        const double* src = reinterpret_cast<const double*>(xbuf + (size_t)jl * I8_XJ_STRIDE +
-                                                            (size_t)(9 * il) * I8_XROW_BYTES);
-        double S[9];
+      ++n;
+    }
+    if (a.dbgClk && lane == 0 && warp == 0) {
+      a.dbgClk[16 * blockIdx.x + 5] += cwAcc; a.dbgClk[16 * blockIdx.x + 6] += cwX;
+      a.dbgClk[16 * blockIdx.x + 7] += clock64() - cStart;
+    }
+  } else {
+    // ===================== solve warps: one thread per frame pair =====================
+    const int u = warp - I8_DRAIN_WARPS;          // 0..13
+    const int h = u & 1;                          // column half of the tile: frames 14h .. 14h+13 = exchange groups 2h, 2h+1
+    const int il = 2 * (u >> 1) + (lane >> 4);    // row frame of the tile
+    const int jlRaw = lane & 15;
+    const bool laneOn = jlRaw < I8_TILE_I;
+    const int jl = I8_TILE_I * h + (laneOn ? jlRaw : I8_TILE_I - 1);
+    const double outScale = 2.0 * a.invScale2 / a.totalMass[0];   // rmsd^2 = (E0 - lambda) * outScale (integer units)
+    const double toInt = 1.0 / a.invScale2;                        // G (A^2) -> integer units (exact power of two)
+    const double* src = reinterpret_cast<const double*>(xbuf + (size_t)jl * I8_XJ_STRIDE + (size_t)(9 * il) * I8_XROW_BYTES);
+    const bool solveOff = (a.dbgMode == 2 || a.dbgMode == 3);
+    int n = 0;
+    long long cwX = 0;
+    const long long cStart = a.dbgClk ? clock64() : 0;
+    while (tiles.next(a, it, jt)) {
+      if (solveOff) continue;
+      const int i = I8_TILE_I * it + il, j = I8_TILE_J * jt + jl;
+      const bool valid = laneOn && i < a.nRows && j < a.nCols && i >= a.rowLo && i < a.rowHi && (!TRI || j > i);
+      // everything stays in integer units (exact); one scale at the very end
+      double e0 = 1.0;
+      if (valid) e0 = 0.5 * (__ldg(a.GA + i) + __ldg(a.GB + j)) * toInt;
+      const double sInv = 1.0 / e0;
+      long long c0 = a.dbgClk ? clock64() : 0;
+      mbar_wait(smem_u32(&xFull[2 * h]), (uint32_t)(n & 1));
+      mbar_wait(smem_u32(&xFull[2 * h + 1]), (uint32_t)(n & 1));
+      if (a.dbgClk) cwX += clock64() - c0;
+      double S[9];
+      if (a.dbgMode != 6) {
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) S[3 * p + q] = src[(3 * p) * 3 + q] + src[(3 * p + 1) * 3 + q] + src[(3 * p + 2) * 3 + q];
-        if (a.dbgS) {
+          for (int q = 0; q < 3; ++q) S[3 * p + q] = (src[(3 * p) * 3 + q] + src[(3 * p + 1) * 3 + q]) + src[(3 * p + 2) * 3 + q];
+      } else {
 #pragma unroll
-          for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
-        }
-        // everything stays in integer units (exact); one scale at the very end
-        const double e0 = 0.5 * (gbuf[il] + gbuf[I8_TILE_I + jl]);
-        float rms;
-        if (a.dbgMode == 1) {
-          rms = (float)(S[0] + S[4] + S[8]);
-        } else {
-          double gap;   // (E0 - lambda_max) / E0
-          if (!relative_gap_fast(S, e0, gap)) gap = (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
-          // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
-          // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
-          const double r2 = gap * e0 * outScale;
-          rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
-        }
+        for (int x = 0; x < 9; ++x) S[x] = 0.0;
+      }
+      // the loads above have completed (their values are consumed): hand the groups back to the drain warps
+      {
+        double keep = S[0];
+#pragma unroll
+        for (int x = 1; x < 9; ++x) keep += S[x];
+        asm volatile("" ::"d"(keep) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(smem_u32(&xEmpty[2 * h])); mbar_arrive(smem_u32(&xEmpty[2 * h + 1])); }
+      ++n;
+      if (a.dbgMode == 6) continue;
+      if (a.dbgS && valid) {
+#pragma unroll
+        for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
+      }
+      float rms;
+      if (a.dbgMode == 1) {
+        rms = (float)(S[0] + S[4] + S[8]);
+      } else {
+        double gap;   // (E0 - lambda_max) / E0
+        const bool ok = i8_relative_gap(S, sInv, gap);
+        if (valid && !ok) gap = i8_relative_gap_slow(S, e0);
+        // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
+        // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
+        const double r2 = gap * (e0 * outScale);
+        rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
+      }
+      if (valid) {
         size_t idx;
         if (TRI)
           idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
@@ -464,21 +586,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
           idx = (size_t)i * a.ldo + (size_t)j;
         a.out[idx] = rms;
       }
-      if (a.dbgClk) { c1 = clock64(); cPair += c1 - c0; c0 = c1; }
-      epi_bar_sync();   // exchange buffer free again
-      if (a.dbgClk) { c1 = clock64(); cBar2 += c1 - c0; c0 = c1; }
-      ++n;
     }
-    if (a.dbgClk && (tid == 0 || tid == 64)) {
-      long long* o = a.dbgClk + 16 * blockIdx.x + (tid == 0 ? 5 : 10);
-      o[0] += cwFullAcc; o[1] += cRow; o[2] += cBar1; o[3] += cPair; o[4] += cBar2;
+    if (a.dbgClk && lane == 0 && u == 0) {
+      a.dbgClk[16 * blockIdx.x + 8] += cwX; a.dbgClk[16 * blockIdx.x + 9] += clock64() - cStart;
     }
   }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == I8_EPI_WARPS + 1) tmem_dealloc(tmemBase, 512);
+  if (warp == I8_WARP_MMA) tmem_dealloc(tmemBase, 512);
 }
 
 
@@ -486,13 +603,16 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
 // tcgen05 kind::i8 issue-peak probe: one CTA per SM, operands fixed in shared memory (no loads),
 // one thread issues M128 x N256 x K32 MMAs back to back.  Roofline denominator of pair_i8_kernel.
 // ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sink) {
+__global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sink, int variant) {
+  // variant 0: consecutive MMAs alternate between the two accumulators (independent);
+  //         1: all MMAs accumulate into one accumulator (the dependent chain of a real K loop);
+  //         2: as 1, plus a tcgen05.commit to a (never waited) mbarrier after every second MMA, as the pair kernel does
   extern __shared__ __align__(1024) unsigned char smem_pk[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;
   __shared__ uint32_t tmemSlot;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (3 * I8_BLK_BYTES) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_pk)[i] = 0x01010101u * (uint32_t)(i & 3);
-  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); mbar_fence_init(); }
   if (warp == 0) tmem_alloc(smem_u32(&tmemSlot), 512);
   // make the generic-proxy smem writes visible to the async (tensor core) proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -504,8 +624,10 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sin
     constexpr uint32_t idesc = umma_idesc_i8(128, 256);
     const uint32_t sA = smem_u32(smem_pk), sB = sA + I8_BLK_BYTES;
     for (int it = 0; it < iters; ++it) {
-      umma_i8(tmemBase + (uint32_t)((it & 1) * 256), umma_desc(sA + (it & 1) * 256, 128, 512),
-              umma_desc(sB + (it & 1) * 256, 128, 512), idesc, (uint32_t)(it > 1));
+      const uint32_t buf = variant == 0 ? (uint32_t)((it & 1) * 256) : 0u;
+      umma_i8(tmemBase + buf, umma_desc(sA + (it & 1) * 256, 128, 512),
+              umma_desc(sB + (it & 1) * 256, 128, 512), idesc, (uint32_t)((variant == 0) ? (it > 1) : ((it & 31) != 0)));
+      if (variant == 2 && (it & 1)) umma_commit(smem_u32(&bar2));
     }
     umma_commit(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);

@@ -193,6 +193,8 @@ double b200_measure_fp64_mma_peak(int variant);
 /* Same for the tcgen05 kind::i8 pipe (M128 x N256 x K32 MMAs on operands resident in shared
  * memory, one CTA per SM); returns int8 TOP/s.  Roofline denominator of the tcgen05 pair engine. */
 double b200_measure_i8_mma_peak(void);
+/* variant 0 independent accumulators (issue peak), 1 one accumulator (dependent K loop), 2 = 1 + a commit every second MMA */
+double b200_measure_i8_mma_peak_variant(int variant);
 
 #ifdef __cplusplus
 }

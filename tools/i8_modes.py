@@ -33,8 +33,7 @@ if os.environ.get("B200_I8_CLOCKS"):
     buf = np.zeros((148, 16), np.int64)
     L.b200_debug_i8_clocks(buf.ctypes.data_as(C.c_void_p), 148)
     names = ["prod_wait_empty", "mma_wait_accEmpty", "mma_wait_full", "mma_total", "mma_tiles",
-             "e0_wait_accFull", "e0_row", "e0_bar1", "e0_pair", "e0_bar2", "e2_wait_accFull", "e2_row", "e2_bar1", "e2_pair", "e2_bar2"]
+             "drain_wait_accFull", "drain_wait_xEmpty", "drain_total", "solve_wait_xFull", "solve_total"]
     # counters accumulate over the 3 band launches of one step (last launch overwrites: use sums per CTA of last launch only)
-    print("per-CTA cycle counters (summed over the band launches of one step), mean / max over CTAs:")
     for k, nm in enumerate(names):
         print("  %-18s mean %12.0f  max %12.0f" % (nm, buf[:, k].mean(), buf[:, k].max()))
