@@ -52,6 +52,7 @@ def lib():
     L.b200_dev_rms2d_tri.argtypes = [vp, sz, vp, i, vp, i, vp, i, i, i, vp, vp]
     L.b200_dev_rmsd_1vN.argtypes = [vp, sz, i, vp, i, vp, vp, i, vp, vp, vp, vp]
     L.b200_set_pair_engine.argtypes = [i]
+    L.b200_set_i8_cta_group.argtypes = [i]
     L.b200_last_pair_engine.argtypes = [C.POINTER(i)]
     L.b200_debug_i8.argtypes = [vp, sz, i, vp, i, vp, vp, sz, C.POINTER(sz), vp, vp, vp, C.POINTER(i)]
     L.b200_get_stats.argtypes = [C.POINTER(Stats)]
@@ -64,7 +65,7 @@ def lib():
     for name in ("b200_init", "b200_init_devices", "b200_shard_rows", "b200_rms2d_tri", "b200_rms2d_tri_shard",
                  "b200_rms2d_full", "b200_rmsd_1vN_begin", "b200_rmsd_1vN_push_f64", "b200_rmsd_1vN_push_f32",
                  "b200_rmsd_1vN_flush", "b200_rmsd_1vN_end", "b200_dev_rms2d_tri", "b200_dev_rmsd_1vN",
-                 "b200_version", "b200_num_devices", "b200_set_pair_engine", "b200_last_pair_engine", "b200_debug_i8",
+                 "b200_version", "b200_num_devices", "b200_set_pair_engine", "b200_set_i8_cta_group", "b200_get_i8_cta_group", "b200_last_pair_engine", "b200_debug_i8",
                  "b200_set_mma_variant"):
         getattr(L, name).restype = i
     _lib = L
@@ -245,6 +246,15 @@ ENGINES = {"auto": 0, "fp64": 1, "i8": 2}
 def set_pair_engine(engine):
     """'auto' | 'fp64' | 'i8' (or 0/1/2): which kernel computes the pair covariances."""
     _check(lib().b200_set_pair_engine(ENGINES.get(engine, engine)))
+
+
+def set_i8_cta_group(cta_group):
+    """MMA CTA group of the tcgen05 int8 kernel: 2 = CTA pairs (default), 1 = single CTA."""
+    _check(lib().b200_set_i8_cta_group(int(cta_group)))
+
+
+def get_i8_cta_group():
+    return int(lib().b200_get_i8_cta_group())
 
 
 def last_pair_engine():

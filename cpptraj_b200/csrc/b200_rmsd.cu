@@ -357,19 +357,54 @@ int i8_choose_scale(Device& d, const unsigned int* d_maxBits, const double* d_to
   return B200_OK;
 }
 
-template <bool TRI>
+// MMA CTA group of the tcgen05 kernel: 2 = CTA pairs (tcgen05.mma.cta_group::2, 28 x 28 tiles), 1 = single CTA
+// (14 x 28 tiles).  Env B200_I8_CTA_GROUP or b200_set_i8_cta_group().
+int g_i8Cg = -1;
+int i8_cta_group() {
+  if (g_i8Cg < 0) {
+    const char* e = getenv("B200_I8_CTA_GROUP");
+    g_i8Cg = e ? atoi(e) : 2;
+    if (g_i8Cg != 1 && g_i8Cg != 2) g_i8Cg = 2;
+  }
+  return g_i8Cg;
+}
+
+template <bool TRI, int CG>
 int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
+  constexpr int smem = i8_smem_bytes<CG>();
   if (!attr[dev & 63]) {
-    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr[dev & 63] = true;
   }
   COUNT_LAUNCH();
-  pair_i8_kernel<TRI><<<grid, I8_THREADS, I8_SMEM_BYTES, st>>>(a);
+  if (CG == 1) {
+    pair_i8_kernel<TRI, CG><<<grid, I8_THREADS, smem, st>>>(a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, pair_i8_kernel<TRI, CG>, a));
+  }
   CU(cudaGetLastError());
   return B200_OK;
+}
+
+template <int CG>
+int run_pair_i8_band_t(const Device& d, PairI8Args& a, int rowLo, int rowHi, bool tri, cudaStream_t st) {
+  a.it0 = rowLo / (I8_TILE_I * CG); a.it1 = (rowHi + I8_TILE_I * CG - 1) / (I8_TILE_I * CG);
+  if (a.it1 <= a.it0 || a.jt1 <= a.jt0) return B200_OK;
+  const long nTiles = tri ? i8_count_tiles<true, CG>(a.it0, a.it1, a.jt0, a.jt1) : i8_count_tiles<false, CG>(a.it0, a.it1, a.jt0, a.jt1);
+  if (nTiles <= 0) return B200_OK;
+  if (nTiles > 0x7fffffffL - 1024) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
+  const int groups = (d.numSMs > 0 ? d.numSMs : 148) / CG;   // persistent: one CTA per SM, CG CTAs per tile
+  const int grid = (int)std::min<long>(nTiles, groups) * CG;
+  return tri ? launch_pair_i8_t<true, CG>(a, grid, st) : launch_pair_i8_t<false, CG>(a, grid, st);
 }
 
 /// Rows [rowLo,rowHi) of the pair matrix through the tcgen05 int8 kernel (persistent, one CTA per SM).
@@ -379,19 +414,13 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   PairI8Args a;
   a.PA = A.image; a.PB = B.image; a.GA = A.G; a.GB = B.G; a.nC = A.nC;
   a.nRows = A.nFrames; a.nCols = B.nFrames; a.rowLo = rowLo; a.rowHi = rowHi;
-  a.it0 = rowLo / I8_TILE_I; a.it1 = (rowHi + I8_TILE_I - 1) / I8_TILE_I;
   a.jt0 = tri ? (rowLo + 1) / I8_TILE_J : 0;
   a.jt1 = (B.nFrames + I8_TILE_J - 1) / I8_TILE_J;
   a.totalMass = d_totalMass; a.invScale2 = std::ldexp(1.0, -2 * qs);
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
   { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
   a.dbgClk = g_dbgClk;
-  if (a.it1 <= a.it0 || a.jt1 <= a.jt0) return B200_OK;
-  const long nTiles = tri ? i8_count_tiles<true>(a.it0, a.it1, a.jt0, a.jt1) : i8_count_tiles<false>(a.it0, a.it1, a.jt0, a.jt1);
-  if (nTiles <= 0) return B200_OK;
-  if (nTiles > 0x7fffffffL - 1024) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
-  const int grid = (int)std::min<long>(nTiles, d.numSMs > 0 ? d.numSMs : 148);
-  return tri ? launch_pair_i8_t<true>(a, grid, st) : launch_pair_i8_t<false>(a, grid, st);
+  return i8_cta_group() == 2 ? run_pair_i8_band_t<2>(d, a, rowLo, rowHi, tri, st) : run_pair_i8_band_t<1>(d, a, rowLo, rowHi, tri, st);
 }
 
 int shard_rows(int nFrames, int rank, int count, int* row0, int* row1) {
@@ -1160,6 +1189,12 @@ int b200_set_pair_engine(int engine) {
   g_engine = engine;
   return B200_OK;
 }
+int b200_set_i8_cta_group(int ctaGroup) {
+  if (ctaGroup != 1 && ctaGroup != 2) return fail(B200_ERR_ARG, "cta group must be 1 or 2");
+  g_i8Cg = ctaGroup;
+  return B200_OK;
+}
+int b200_get_i8_cta_group(void) { return i8_cta_group(); }
 int b200_last_pair_engine(int* fractionalBits) {
   if (fractionalBits) *fractionalBits = g_lastQs.load();
   return g_lastEngine.load();

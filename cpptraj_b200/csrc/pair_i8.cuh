@@ -32,8 +32,23 @@ constexpr int I8_FR_PER_RG = 14;             // frames per 128-row operand group
 constexpr int I8_ROWS_PER_FR = 9;            // 3 planes x 3 digits
 constexpr int I8_KC = 64;                    // atoms (bytes per row) per pipeline stage
 constexpr int I8_BLK_BYTES = 128 * I8_KC;    // 8192
-constexpr int I8_STAGES = 5;
-constexpr int I8_STAGE_BYTES = 3 * I8_BLK_BYTES;  // A (1 block) + B (2 blocks) = 24 KB
+/// Pipeline geometry per MMA CTA group.  CG = 1: one CTA computes a 14 x 28 tile (M128 N256), a stage
+/// holds 64 atoms of A (1 block) and B (2 blocks).  CG = 2: a CTA pair computes a 28 x 28 tile
+/// (tcgen05.mma.cta_group::2, M256 N256); each CTA stages its own A row group and ONE of the two B row
+/// groups, so shared-memory fill and operand-read traffic per SM drop by a third and a stage can hold
+/// 128 atoms (4 MMAs) in the same footprint.
+template <int CG> struct I8Geom;
+template <> struct I8Geom<1> {
+  static constexpr int BPS = 1;      // 64-atom blocks per stage
+  static constexpr int STAGES = 5;
+  static constexpr int BBLK = 2;     // B blocks per 64 atoms held by this CTA
+};
+template <> struct I8Geom<2> {
+  static constexpr int BPS = 2;
+  static constexpr int STAGES = 4;
+  static constexpr int BBLK = 1;
+};
+template <int CG> __host__ __device__ constexpr int i8_stage_bytes() { return I8Geom<CG>::BPS * (1 + I8Geom<CG>::BBLK) * I8_BLK_BYTES; }
 constexpr int I8_TILE_I = I8_FR_PER_RG;      // 14
 constexpr int I8_TILE_J = 2 * I8_FR_PER_RG;  // 28
 constexpr long long I8_QMAX = 8355711;       // 127*(1+256+65536): largest |q| with balanced digits
@@ -163,24 +178,81 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dstSmem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dstSmem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dstSmem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dstSmem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-/// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, issued by one thread.
+/// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, issued by one thread.  CG == 2: issued by the
+/// leader CTA of a pair; M = 256 (128 rows from each CTA's A), each CTA supplies half of B's N columns.
+template <int CG>
 __device__ __forceinline__ void umma_i8(uint32_t dTmem, uint64_t aDesc, uint64_t bDesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc),
-      "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(dTmem), "l"(aDesc), "l"(bDesc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
 }
-/// mbarrier arrive once all previously issued MMAs of this thread have completed.
+/// mbarrier arrive once all previously issued MMAs of this thread have completed.  CG == 2: the arrive is
+/// multicast to the barrier at the same shared-memory offset in both CTAs of the pair.
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+// ---- thread-block-cluster helpers (CTA pair)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+/// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cluster_map(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t clusterAddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAITC_LOOP:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAITC_DONE;\n"
+      "bra.uni WAITC_LOOP;\n"
+      "WAITC_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
 }
 /// K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes) {
@@ -246,9 +318,11 @@ constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
 constexpr int I8_XROW_BYTES = 24;            // 3 doubles per (operand row, column frame)
 constexpr int I8_XJ_STRIDE = 128 * I8_XROW_BYTES + 88;  // 3160 B: (stride/4) % 32 == 22 -> conflict-free LDS.64 / STS.64
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_STRIDE;  // 88480
-constexpr int I8_NBARS = 2 * I8_STAGES + 4 + 8;
-constexpr int I8_SMEM_BYTES = I8_STAGES * I8_STAGE_BYTES + I8_XBUF_BYTES + 256;   // + barriers
+constexpr int I8_MAX_STAGES = 5;
+constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8;
+template <int CG> __host__ __device__ constexpr int i8_smem_bytes() { return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 256; }   // + barriers
 static_assert(I8_NBARS * 8 + 8 <= 256, "barrier block");
+static_assert(i8_smem_bytes<1>() <= 232448 && i8_smem_bytes<2>() <= 232448, "shared memory budget");
 
 struct PairI8Args {
   const uint8_t* PA;   // operand images of the row frames (i)
@@ -258,7 +332,7 @@ struct PairI8Args {
   int nC;              // 64-atom chunks
   int nRows, nCols;    // valid i / j frames
   int rowLo, rowHi;    // rows written by this launch: [rowLo, rowHi)
-  int it0, it1;        // i tiles (14 frames) of this launch: [it0, it1)
+  int it0, it1;        // i super-tiles (CG row groups = 14*CG frames) of this launch: [it0, it1)
   int jt0, jt1;        // j tiles (28 frames) of this launch: [jt0, jt1)
   const double* totalMass;
   double invScale2;    // 2^-2qs: integer covariance -> A^2
@@ -271,28 +345,30 @@ struct PairI8Args {
                        // 3 = 2 + no operand loads, 6 = solve warps only recycle the exchange buffer
 };
 
-/// Row tiles [it0, hi) of column tile jt hold at least one wanted pair.
-template <bool TRI>
+/// Row super-tiles [it0, hi) of column tile jt hold at least one wanted pair.
+template <bool TRI, int CG>
 __host__ __device__ __forceinline__ int i8_col_tiles(int it0, int it1, int jt) {
-  // TRI: a tile is wanted iff its largest j exceeds its smallest i: 28 jt + 27 > 14 it  <=>  it <= 2 jt + 1
-  const int hi = TRI ? (it1 < 2 * jt + 2 ? it1 : 2 * jt + 2) : it1;
+  // TRI: a tile is wanted iff its largest j exceeds its smallest i: 28 jt + 27 > 14 CG it
+  //      CG = 1: it <= 2 jt + 1;  CG = 2: it <= jt
+  const int lim = CG == 1 ? 2 * jt + 2 : jt + 1;
+  const int hi = TRI ? (it1 < lim ? it1 : lim) : it1;
   return hi > it0 ? hi - it0 : 0;
 }
-template <bool TRI>
+template <bool TRI, int CG>
 __host__ __device__ inline long i8_count_tiles(int it0, int it1, int jt0, int jt1) {
   long n = 0;
-  for (int jt = jt0; jt < jt1; ++jt) n += i8_col_tiles<TRI>(it0, it1, jt);
+  for (int jt = jt0; jt < jt1; ++jt) n += i8_col_tiles<TRI, CG>(it0, it1, jt);
   return n;
 }
-/// Walks this CTA's share of the tile list; every role keeps its own copy (two registers).
-template <bool TRI>
+/// Walks this CTA group's share of the tile list; every role keeps its own copy (two registers).
+template <bool TRI, int CG>
 struct I8TileIter {
   int jt, base, t;
-  __device__ __forceinline__ void init(const PairI8Args& a) { jt = a.jt0; base = 0; t = (int)blockIdx.x; }
+  __device__ __forceinline__ void init(const PairI8Args& a) { jt = a.jt0; base = 0; t = (int)blockIdx.x / CG; }
   __device__ __forceinline__ bool next(const PairI8Args& a, int& it, int& jtOut) {
     while (jt < a.jt1) {
-      const int c = i8_col_tiles<TRI>(a.it0, a.it1, jt);
-      if (t < base + c) { it = a.it0 + (t - base); jtOut = jt; t += (int)gridDim.x; return true; }
+      const int c = i8_col_tiles<TRI, CG>(a.it0, a.it1, jt);
+      if (t < base + c) { it = a.it0 + (t - base); jtOut = jt; t += (int)gridDim.x / CG; return true; }
       base += c; ++jt;
     }
     return false;
@@ -356,68 +432,88 @@ __device__ __noinline__ double i8_relative_gap_slow(const double* S, double e0) 
   return (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
 }
 
-template <bool TRI>
+template <bool TRI, int CG>
 __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
+  using GEO = I8Geom<CG>;
+  constexpr int STAGES = GEO::STAGES, BPS = GEO::BPS, BBLK = GEO::BBLK;
+  constexpr int STAGE_BYTES = i8_stage_bytes<CG>();
   extern __shared__ __align__(1024) unsigned char smem_i8[];
   unsigned char* stages = smem_i8;
-  unsigned char* xbuf = smem_i8 + I8_STAGES * I8_STAGE_BYTES;
+  unsigned char* xbuf = smem_i8 + STAGES * STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + I8_XBUF_BYTES);
-  uint64_t* fullBar = bars;                        // [I8_STAGES]  operands landed
-  uint64_t* emptyBar = bars + I8_STAGES;           // [I8_STAGES]  MMAs reading the stage done
-  uint64_t* accFull = bars + 2 * I8_STAGES;        // [2]  accumulator complete
-  uint64_t* accEmpty = bars + 2 * I8_STAGES + 2;   // [2]  accumulator drained
-  uint64_t* xFull = bars + 2 * I8_STAGES + 4;      // [4]  exchange group written
-  uint64_t* xEmpty = bars + 2 * I8_STAGES + 8;     // [4]  exchange group read
+  uint64_t* fullBar = bars;                            // [STAGES]  operands landed (CG 2: in both CTAs, seen by the leader)
+  uint64_t* emptyBar = bars + I8_MAX_STAGES;           // [STAGES]  MMAs reading the stage done
+  uint64_t* accFull = bars + 2 * I8_MAX_STAGES;        // [2]  accumulator complete
+  uint64_t* accEmpty = bars + 2 * I8_MAX_STAGES + 2;   // [2]  accumulator drained (CG 2: by both CTAs; leader's copy is used)
+  uint64_t* xFull = bars + 2 * I8_MAX_STAGES + 4;      // [4]  exchange group written
+  uint64_t* xEmpty = bars + 2 * I8_MAX_STAGES + 8;     // [4]  exchange group read
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();   // 0 = leader (issues the MMAs)
 
   if (tid == 0) {
-    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(smem_u32(&fullBar[s]), 1); mbar_init(smem_u32(&emptyBar[s]), 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS); }
+    for (int s = 0; s < STAGES; ++s) {
+      // CG 2, leader: its own producer's expect_tx arrive + the peer's relayed "my half has landed"
+      mbar_init(smem_u32(&fullBar[s]), (CG == 2 && rank == 0) ? 2 : 1);
+      mbar_init(smem_u32(&emptyBar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS * CG); }
     for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), I8_DRAIN_WARPS); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
     mbar_fence_init();
   }
-  if (warp == I8_WARP_MMA) tmem_alloc(smem_u32(tmemBaseSlot), 512);
+  if (warp == I8_WARP_MMA) tmem_alloc<CG>(smem_u32(tmemBaseSlot), 512);
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the peer's barriers are initialised before anything remote touches them
   tc_fence_after();
   const uint32_t tmemBase = *tmemBaseSlot;
-  I8TileIter<TRI> tiles;
+  I8TileIter<TRI, CG> tiles;
   tiles.init(a);
   int it, jt;
 
   if (warp == I8_WARP_PRODUCER) {
-    // ===================== TMA producer (one thread) =====================
+    // ===================== TMA producer (one thread per CTA) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage0 = smem_u32(stages);
     long long cwEmpty = 0;
     if (lane == 0)
     while (tiles.next(a, it, jt)) {
-      const uint8_t* gA = a.PA + (size_t)it * a.nC * I8_BLK_BYTES;
-      const uint8_t* gB0 = a.PB + (size_t)(2 * jt) * a.nC * I8_BLK_BYTES;
-      const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;
-      for (int c = 0; c < a.nC; ++c) {
+      // this CTA's A row group, and the B row group(s) it stages: both (CG 1) or the rank-th (CG 2)
+      const uint8_t* gA = a.PA + (size_t)(CG * it + (int)rank) * a.nC * I8_BLK_BYTES;
+      const uint8_t* gB0 = a.PB + (size_t)(2 * jt + (CG == 2 ? (int)rank : 0)) * a.nC * I8_BLK_BYTES;
+      const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;   // CG 1 only
+      for (int c = 0; c < a.nC; c += BPS) {
+        const int nb = (a.nC - c < BPS) ? a.nC - c : BPS;
         const long long c0 = a.dbgClk ? clock64() : 0;
         mbar_wait(smem_u32(&emptyBar[stage]), phase ^ 1u);
         if (a.dbgClk) cwEmpty += clock64() - c0;
         const uint32_t bar = smem_u32(&fullBar[stage]);
-        const uint32_t dst = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
+        const uint32_t dst = stage0 + (uint32_t)stage * STAGE_BYTES;
         if (a.dbgMode == 3) {
           mbar_arrive(bar);
         } else {
-          mbar_expect_tx(bar, I8_STAGE_BYTES);
-          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          bulk_g2s(dst + I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
-          bulk_g2s(dst + 2 * I8_BLK_BYTES, gB1 + (size_t)c * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+          mbar_expect_tx(bar, (uint32_t)(nb * (1 + BBLK) * I8_BLK_BYTES));
+          // consecutive 64-atom blocks of one row group are contiguous in the image: one bulk copy per operand
+          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
+          if constexpr (CG == 2) {
+            bulk_g2s(dst + BPS * I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
+          } else {
+#pragma unroll
+            for (int cc = 0; cc < BPS; ++cc)
+              if (cc < nb) {
+                bulk_g2s(dst + (BPS + 2 * cc) * I8_BLK_BYTES, gB0 + (size_t)(c + cc) * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+                bulk_g2s(dst + (BPS + 2 * cc + 1) * I8_BLK_BYTES, gB1 + (size_t)(c + cc) * I8_BLK_BYTES, I8_BLK_BYTES, bar);
+              }
+          }
         }
-        if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
     if (a.dbgClk && lane == 0) a.dbgClk[16 * blockIdx.x + 0] += cwEmpty;
-  } else if (warp == I8_WARP_MMA) {
-    // ===================== MMA issuer (one thread) =====================
-    constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+  } else if (warp == I8_WARP_MMA && rank == 0) {
+    // ===================== MMA issuer (one thread; CG 2: of the leader CTA) =====================
+    constexpr uint32_t idesc = umma_idesc_i8(128 * CG, 256);
     // descriptor = constant high part (LBO 128 B, SBO 512 B, version 1) | (smem address >> 4)
     constexpr uint64_t descHi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     const uint32_t stage0 = smem_u32(stages);
@@ -428,30 +524,52 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     while (tiles.next(a, it, jt)) {
       const int b = n & 1;
       long long c0 = a.dbgClk ? clock64() : 0;
-      mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
+      if constexpr (CG == 2) mbar_wait_cluster(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
+      else mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       if (a.dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
       const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
-      for (int c = 0; c < a.nC; ++c) {
+      for (int c = 0; c < a.nC; c += BPS) {
+        const int nb = (a.nC - c < BPS) ? a.nC - c : BPS;
         c0 = a.dbgClk ? clock64() : 0;
-        mbar_wait(smem_u32(&fullBar[stage]), phase);
+        if constexpr (CG == 2) mbar_wait_cluster(smem_u32(&fullBar[stage]), phase);
+        else mbar_wait(smem_u32(&fullBar[stage]), phase);
         if (a.dbgClk) cwFull += clock64() - c0;
         tc_fence_after();
-        const uint32_t sA = stage0 + (uint32_t)stage * I8_STAGE_BYTES;
-        const uint64_t dA = descHi | (uint64_t)((sA >> 4) & 0x3fff);
-        const uint64_t dB = descHi | (uint64_t)(((sA + I8_BLK_BYTES) >> 4) & 0x3fff);
+        const uint32_t sA = stage0 + (uint32_t)stage * STAGE_BYTES;
+        const uint32_t sB = sA + BPS * I8_BLK_BYTES;
 #pragma unroll
-        for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
-          umma_i8(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | k) != 0));
-        umma_commit(smem_u32(&emptyBar[stage]));
-        if (++stage == I8_STAGES) { stage = 0; phase ^= 1u; }
+        for (int cc = 0; cc < BPS; ++cc) {
+          if (cc < nb) {
+            const uint64_t dA = descHi | (uint64_t)(((sA + cc * I8_BLK_BYTES) >> 4) & 0x3fff);
+            const uint64_t dB = descHi | (uint64_t)(((sB + cc * BBLK * I8_BLK_BYTES) >> 4) & 0x3fff);
+#pragma unroll
+            for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
+              umma_i8<CG>(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | cc | k) != 0));
+          }
+        }
+        umma_commit<CG>(smem_u32(&emptyBar[stage]));
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(smem_u32(&accFull[b]));
+      umma_commit<CG>(smem_u32(&accFull[b]));
       ++n;
     }
     if (a.dbgClk && lane == 0) {
       a.dbgClk[16 * blockIdx.x + 1] += cwAcc; a.dbgClk[16 * blockIdx.x + 2] += cwFull;
       a.dbgClk[16 * blockIdx.x + 3] += clock64() - cStart; a.dbgClk[16 * blockIdx.x + 4] += n;
+    }
+  } else if (warp == I8_WARP_MMA) {
+    // ===================== CG 2, peer CTA: relay "my operand half has landed" to the leader =====================
+    if constexpr (CG == 2) {
+      int stage = 0; uint32_t phase = 0;
+      if (lane == 0)
+      while (tiles.next(a, it, jt)) {
+        for (int c = 0; c < a.nC; c += BPS) {
+          mbar_wait(smem_u32(&fullBar[stage]), phase);
+          mbar_arrive_cluster(cluster_map(smem_u32(&fullBar[stage]), 0));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
     }
   } else if (warp < I8_DRAIN_WARPS) {
     // ===================== drain warps =====================
@@ -472,7 +590,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       if (a.dbgMode == 2 || a.dbgMode == 3) {   // timing experiment: MMA + operand pipeline only
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(cluster_map(smem_u32(&accEmpty[b]), 0));
+          else mbar_arrive(smem_u32(&accEmpty[b]));
+        }
         ++n;
         continue;
       }
@@ -490,7 +611,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         if (g == 3) {   // this warp is done reading accumulator buffer b
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&accEmpty[b]));
+          if (lane == 0) {
+            if constexpr (CG == 2) mbar_arrive_cluster(cluster_map(smem_u32(&accEmpty[b]), 0));
+            else mbar_arrive(smem_u32(&accEmpty[b]));
+          }
         }
         double* dst = reinterpret_cast<double*>(xrow + (size_t)(7 * g) * I8_XJ_STRIDE);
 #pragma unroll
@@ -531,7 +655,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     const long long cStart = a.dbgClk ? clock64() : 0;
     while (tiles.next(a, it, jt)) {
       if (solveOff) continue;
-      const int i = I8_TILE_I * it + il, j = I8_TILE_J * jt + jl;
+      const int i = I8_TILE_I * (CG * it + (int)rank) + il, j = I8_TILE_J * jt + jl;
       const bool valid = laneOn && i < a.nRows && j < a.nCols && i >= a.rowLo && i < a.rowHi && (!TRI || j > i);
       // everything stays in integer units (exact); one scale at the very end
       double e0 = 1.0;
@@ -592,10 +716,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     }
   }
   // ---- teardown ----
+  __syncwarp();   // single-lane roles: reconverge before the (warp-aligned) block and cluster barriers
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();   // the pair's MMAs, multicast commits and remote arrives are all done
   tc_fence_after();
-  if (warp == I8_WARP_MMA) tmem_dealloc(tmemBase, 512);
+  if (warp == I8_WARP_MMA) tmem_dealloc<CG>(tmemBase, 512);
 }
 
 
@@ -613,7 +739,7 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sin
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (3 * I8_BLK_BYTES) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_pk)[i] = 0x01010101u * (uint32_t)(i & 3);
   if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_init(smem_u32(&bar2), 1); mbar_fence_init(); }
-  if (warp == 0) tmem_alloc(smem_u32(&tmemSlot), 512);
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tmemSlot), 512);
   // make the generic-proxy smem writes visible to the async (tensor core) proxy
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc_fence_before();
@@ -625,11 +751,11 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sin
     const uint32_t sA = smem_u32(smem_pk), sB = sA + I8_BLK_BYTES;
     for (int it = 0; it < iters; ++it) {
       const uint32_t buf = variant == 0 ? (uint32_t)((it & 1) * 256) : 0u;
-      umma_i8(tmemBase + buf, umma_desc(sA + (it & 1) * 256, 128, 512),
+      umma_i8<1>(tmemBase + buf, umma_desc(sA + (it & 1) * 256, 128, 512),
               umma_desc(sB + (it & 1) * 256, 128, 512), idesc, (uint32_t)((variant == 0) ? (it > 1) : ((it & 31) != 0)));
-      if (variant == 2 && (it & 1)) umma_commit(smem_u32(&bar2));
+      if (variant == 2 && (it & 1)) umma_commit<1>(smem_u32(&bar2));
     }
-    umma_commit(smem_u32(&bar));
+    umma_commit<1>(smem_u32(&bar));
     mbar_wait(smem_u32(&bar), 0);
     tc_fence_after();
   }
@@ -642,7 +768,7 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sin
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmemBase, 512);
+  if (warp == 0) tmem_dealloc<1>(tmemBase, 512);
 }
 
 }  // namespace b200

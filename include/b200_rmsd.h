@@ -165,6 +165,10 @@ void b200_get_stats(b200_stats* out);
  *   0 = automatic (2 when eligible, else 1) -- the default; env B200_PAIR_ENGINE.
  * Forcing 2 on an ineligible call fails with B200_ERR_ARG. */
 int b200_set_pair_engine(int engine);
+/* MMA CTA group of the tcgen05 int8 kernel: 2 (default) = CTA pairs, tcgen05.mma.cta_group::2,
+ * 28 x 28 frame-pair tiles; 1 = single-CTA MMAs, 14 x 28 tiles.  Same results; a tuning/test knob. */
+int b200_set_i8_cta_group(int ctaGroup);
+int b200_get_i8_cta_group(void);
 /* Engine the last rms2d call used (1 or 2; 0 = none yet) and, for 2, the number of
  * fractional bits of its fixed-point grid. */
 int b200_last_pair_engine(int* fractionalBits);

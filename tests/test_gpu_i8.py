@@ -47,10 +47,13 @@ def numpy_quant(crd, sel, mass, qs):
     return v, np.rint(v * 2.0 ** qs).astype(np.int64)
 
 
-@pytest.fixture()
-def i8(b200):
+@pytest.fixture(params=[2, 1], ids=["cta_pair", "single_cta"])
+def i8(b200, request):
+    """tcgen05 engine forced, in both MMA CTA-group modes (tcgen05.mma.cta_group::2 pairs / ::1)."""
     b200.set_pair_engine("i8")
+    b200.set_i8_cta_group(request.param)
     yield b200
+    b200.set_i8_cta_group(2)
     b200.set_pair_engine("auto")
 
 
@@ -79,10 +82,15 @@ def test_packed_image_and_G(b200, nf, na, use_mass):
     assert not r["image"][: r["image_bytes"]][~used].any()
 
 
-@pytest.mark.parametrize("nf,na", [(20, 64), (30, 70), (61, 200)])
-def test_integer_covariance_is_exact(b200, nf, na):
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("nf,na", [(20, 64), (30, 70), (61, 200), (90, 130)])
+def test_integer_covariance_is_exact(b200, nf, na, cg):
     c, m, sel = synth_case(11 + nf, nf, na)
-    r = b200.debug_i8(c, sel, mass=m[sel])
+    b200.set_i8_cta_group(cg)
+    try:
+        r = b200.debug_i8(c, sel, mass=m[sel])
+    finally:
+        b200.set_i8_cta_group(2)
     q = decode_image(r["image"][: r["image_bytes"]], nf, na)
     S = np.einsum("iap,jaq->ijpq", q, q).reshape(nf, nf, 9)    # int64, exact (|q| < 2^23, na small)
     iu = np.triu_indices(nf, 1)

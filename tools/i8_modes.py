@@ -35,5 +35,7 @@ if os.environ.get("B200_I8_CLOCKS"):
     names = ["prod_wait_empty", "mma_wait_accEmpty", "mma_wait_full", "mma_total", "mma_tiles",
              "drain_wait_accFull", "drain_wait_xEmpty", "drain_total", "solve_wait_xFull", "solve_total"]
     # counters accumulate over the 3 band launches of one step (last launch overwrites: use sums per CTA of last launch only)
+    # with CTA pairs the MMA counters exist on the leader CTAs only: average over the CTAs that counted
     for k, nm in enumerate(names):
-        print("  %-18s mean %12.0f  max %12.0f" % (nm, buf[:, k].mean(), buf[:, k].max()))
+        col = buf[:, k]; nz = col[col != 0]
+        print("  %-18s mean %12.0f  max %12.0f  (%d CTAs)" % (nm, nz.mean() if len(nz) else 0, col.max(), len(nz)))
