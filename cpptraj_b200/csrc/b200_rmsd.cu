@@ -369,19 +369,30 @@ int i8_cta_group() {
   return g_i8Cg;
 }
 
-template <bool TRI, int CG>
+// B-resident mode of the CTA-pair kernel (column operand kept in shared memory down a column of tiles):
+// default on; env B200_I8_RESIDENT=0 or b200_set_i8_resident(0) streams both operands instead.
+int g_i8Res = -1;
+int i8_resident() {
+  if (g_i8Res < 0) {
+    const char* e = getenv("B200_I8_RESIDENT");
+    g_i8Res = e ? (atoi(e) != 0) : 1;
+  }
+  return g_i8Res;
+}
+
+template <bool TRI, int CG, bool RES, bool DBG>
 int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  constexpr int smem = i8_smem_bytes<CG>();
+  constexpr int smem = i8_smem_bytes<CG, RES>();
   if (!attr[dev & 63]) {
-    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG, RES, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr[dev & 63] = true;
   }
   COUNT_LAUNCH();
   if (CG == 1) {
-    pair_i8_kernel<TRI, CG><<<grid, I8_THREADS, smem, st>>>(a);
+    pair_i8_kernel<TRI, CG, RES, DBG><<<grid, I8_THREADS, smem, st>>>(a);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -389,22 +400,34 @@ int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, pair_i8_kernel<TRI, CG>, a));
+    CU(cudaLaunchKernelEx(&cfg, pair_i8_kernel<TRI, CG, RES, DBG>, a));
   }
   CU(cudaGetLastError());
   return B200_OK;
 }
 
-template <int CG>
+template <int CG, bool RES>
 int run_pair_i8_band_t(const Device& d, PairI8Args& a, int rowLo, int rowHi, bool tri, cudaStream_t st) {
   a.it0 = rowLo / (I8_TILE_I * CG); a.it1 = (rowHi + I8_TILE_I * CG - 1) / (I8_TILE_I * CG);
   if (a.it1 <= a.it0 || a.jt1 <= a.jt0) return B200_OK;
   const long nTiles = tri ? i8_count_tiles<true, CG>(a.it0, a.it1, a.jt0, a.jt1) : i8_count_tiles<false, CG>(a.it0, a.it1, a.jt0, a.jt1);
   if (nTiles <= 0) return B200_OK;
-  if (nTiles > 0x7fffffffL - 1024) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
+  if (nTiles > (1L << 30)) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
   const int groups = (d.numSMs > 0 ? d.numSMs : 148) / CG;   // persistent: one CTA per SM, CG CTAs per tile
-  const int grid = (int)std::min<long>(nTiles, groups) * CG;
-  return tri ? launch_pair_i8_t<true, CG>(a, grid, st) : launch_pair_i8_t<false, CG>(a, grid, st);
+  // chunks of consecutive tiles (same column => same resident operand): every group gets k chunks of equal length
+  long L = 1;
+  if (RES) {
+    const char* e = getenv("B200_I8_CHUNK");
+    const long target = e ? std::max(1, atoi(e)) : 32;
+    const long k = std::max<long>(1, (nTiles + groups * target / 2) / (groups * target));
+    L = (nTiles + groups * k - 1) / (groups * k);
+  }
+  a.chunkLen = (int)L;
+  const long nChunks = (nTiles + L - 1) / L;
+  const int grid = (int)std::min<long>(nChunks, groups) * CG;
+  const bool dbg = a.dbgMode != 0 || a.dbgClk != nullptr || a.dbgS != nullptr;
+  if (dbg) return tri ? launch_pair_i8_t<true, CG, RES, true>(a, grid, st) : launch_pair_i8_t<false, CG, RES, true>(a, grid, st);
+  return tri ? launch_pair_i8_t<true, CG, RES, false>(a, grid, st) : launch_pair_i8_t<false, CG, RES, false>(a, grid, st);
 }
 
 /// Rows [rowLo,rowHi) of the pair matrix through the tcgen05 int8 kernel (persistent, one CTA per SM).
@@ -420,7 +443,9 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
   { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
   a.dbgClk = g_dbgClk;
-  return i8_cta_group() == 2 ? run_pair_i8_band_t<2>(d, a, rowLo, rowHi, tri, st) : run_pair_i8_band_t<1>(d, a, rowLo, rowHi, tri, st);
+  if (i8_cta_group() != 2) return run_pair_i8_band_t<1, false>(d, a, rowLo, rowHi, tri, st);
+  if (i8_resident() && a.nC <= I8_RES_MAX_C) return run_pair_i8_band_t<2, true>(d, a, rowLo, rowHi, tri, st);
+  return run_pair_i8_band_t<2, false>(d, a, rowLo, rowHi, tri, st);
 }
 
 int shard_rows(int nFrames, int rank, int count, int* row0, int* row1) {
@@ -1195,6 +1220,8 @@ int b200_set_i8_cta_group(int ctaGroup) {
   return B200_OK;
 }
 int b200_get_i8_cta_group(void) { return i8_cta_group(); }
+int b200_set_i8_resident(int on) { g_i8Res = on ? 1 : 0; return B200_OK; }
+int b200_get_i8_resident(void) { return i8_resident(); }
 int b200_last_pair_engine(int* fractionalBits) {
   if (fractionalBits) *fractionalBits = g_lastQs.load();
   return g_lastEngine.load();
@@ -1283,6 +1310,26 @@ double b200_measure_i8_mma_peak_variant(int variant) {
   cudaEventDestroy(a); cudaEventDestroy(b);
   if (cudaGetLastError() != cudaSuccess) return -1.0;
   return 2.0 * 128 * 256 * 32 * (double)iters * blocks / (best * 1e-3) / 1e12;   // TOP/s
+}
+
+double b200_debug_i8_mma_latency(int nMma, int ctas) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (ensure_init_locked()) return -1.0;
+  if (nMma < 0 || ctas < 1 || ctas > 148) return -1.0;
+  const int smem = 3 * I8_BLK_BYTES;
+  if (cudaFuncSetAttribute(i8_mma_latency_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1.0;
+  long long* d_out = nullptr;
+  if (cudaMalloc(&d_out, 148 * sizeof(long long)) != cudaSuccess) return -1.0;
+  i8_mma_latency_kernel<<<ctas, 128, smem>>>(nMma, 200, d_out);
+  long long h[148];
+  double avg = -1.0;
+  if (cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(h, d_out, ctas * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess) {
+    avg = 0.0;
+    for (int i = 0; i < ctas; ++i) avg += (double)h[i];
+    avg /= ctas;
+  }
+  cudaFree(d_out);
+  return avg;
 }
 
 double b200_measure_fp64_mma_peak(int variant) {

@@ -35,20 +35,29 @@ constexpr int I8_BLK_BYTES = 128 * I8_KC;    // 8192
 /// Pipeline geometry per MMA CTA group.  CG = 1: one CTA computes a 14 x 28 tile (M128 N256), a stage
 /// holds 64 atoms of A (1 block) and B (2 blocks).  CG = 2: a CTA pair computes a 28 x 28 tile
 /// (tcgen05.mma.cta_group::2, M256 N256); each CTA stages its own A row group and ONE of the two B row
-/// groups, so shared-memory fill and operand-read traffic per SM drop by a third and a stage can hold
-/// 128 atoms (4 MMAs) in the same footprint.
-template <int CG> struct I8Geom;
-template <> struct I8Geom<1> {
+/// groups.  RES (CG 2 only, <= 1024 atoms): the CTA's B row group stays RESIDENT in shared memory while the
+/// pair walks down a column of tiles, so only A is streamed through the ring: 128 KB instead of 256 KB of
+/// L2 -> SM traffic per tile and CTA (the measured limiter of this kernel, see profiles/).
+template <int CG, bool RES> struct I8Geom;
+template <> struct I8Geom<1, false> {
   static constexpr int BPS = 1;      // 64-atom blocks per stage
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = 8;
   static constexpr int BBLK = 2;     // B blocks per 64 atoms held by this CTA
 };
-template <> struct I8Geom<2> {
+template <> struct I8Geom<2, false> {
   static constexpr int BPS = 2;
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = 6;
   static constexpr int BBLK = 1;
 };
-template <int CG> __host__ __device__ constexpr int i8_stage_bytes() { return I8Geom<CG>::BPS * (1 + I8Geom<CG>::BBLK) * I8_BLK_BYTES; }
+template <> struct I8Geom<2, true> {
+  static constexpr int BPS = 2;
+  static constexpr int STAGES = 4;
+  static constexpr int BBLK = 0;     // B is not in the ring
+};
+constexpr int I8_RES_MAX_C = 16;     // 64-atom chunks a resident B row group may have (128 KB)
+template <int CG, bool RES> __host__ __device__ constexpr int i8_stage_bytes() {
+  return I8Geom<CG, RES>::BPS * (1 + I8Geom<CG, RES>::BBLK) * I8_BLK_BYTES;
+}
 constexpr int I8_TILE_I = I8_FR_PER_RG;      // 14
 constexpr int I8_TILE_J = 2 * I8_FR_PER_RG;  // 28
 constexpr long long I8_QMAX = 8355711;       // 127*(1+256+65536): largest |q| with balanced digits
@@ -223,6 +232,13 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  "h"((unsigned short)3)
                  : "memory");
 }
+/// One lane of the (converged) warp: the single-thread roles run their loops warp-uniformly, so that addresses,
+/// descriptors and counters stay in uniform registers, and only issue under this predicate.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 // ---- thread-block-cluster helpers (CTA pair)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -238,22 +254,15 @@ __device__ __forceinline__ uint32_t cluster_map(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+/// Arrive on an mbarrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+/// ClusterBarrier::arrive does: the explicit .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR in front of
+/// every arrive (and .acquire.cluster waits to a CCTL.IVALL after every wait), which made the operand ring of the
+/// CTA-pair kernel latency-bound.  What the barriers order here is async-proxy traffic (TMA writes, tensor-core
+/// reads, TMEM) which is fenced by complete_tx / tcgen05.commit / tcgen05.fence, not by generic-proxy scopes.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t clusterAddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(clusterAddr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAITC_LOOP:\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAITC_DONE;\n"
-      "bra.uni WAITC_LOOP;\n"
-      "WAITC_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) { mbar_wait(bar, parity); }
 /// K-major, no-swizzle UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor, version 1).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smemAddr, uint32_t lboBytes, uint32_t sboBytes) {
   return (uint64_t)((smemAddr >> 4) & 0x3fff) | ((uint64_t)((lboBytes >> 4) & 0x3fff) << 16) |
@@ -293,36 +302,46 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------
 // pair_i8_kernel
 //
-// Persistent, warp-specialised, one CTA per SM.  Roles (20 warps):
-//   warp 18       TMA producer: operand stages (A block + 2 B blocks per 64 atoms) through a
-//                 5-deep full/empty mbarrier ring
-//   warp 19       MMA issuer: tcgen05.mma kind::i8 M128 N256 K32 into one of two TMEM accumulators
-//   warps 0..3    drain: one per TMEM sub-partition; tcgen05.ld 64 accumulator columns (7 column
-//                 frames x 9), fold the three B digits in-thread, apply the A digit weight of
-//                 the own operand row, hand 21 doubles per thread to the exchange buffer
-//   warps 4..17   solve: one thread per frame pair (2 row frames x 14 column frames per warp):
-//                 gather the 27 partial sums of the pair, fold the A digits, per-pair solve,
-//                 store the float straight into cpptraj's Matrix<float> layout
+// Persistent, warp-specialised, one CTA per SM.  Roles (24 warps):
+//   warp 22       TMA producer: operand stages through a full/empty mbarrier ring
+//   warp 23       MMA issuer: tcgen05.mma kind::i8 K32 into one of two TMEM accumulators
+//                 (CG 2: the leader CTA issues for the pair; the peer's warp 23 relays "landed")
+//   warps 0..7    drain: two per TMEM sub-partition (one per column half of the tile); tcgen05.ld the
+//                 accumulator columns of 7 column frames (x 9) in three pieces, fold the three B digits in-thread (exact int64), apply the A digit
+//                 weight of the own operand row, fold the three A digits across the three lanes of
+//                 a (frame, plane) triple with two shuffles, hand 3 doubles per (triple, column
+//                 frame) to the exchange buffer
+//   warps 8..21   solve: one thread per frame pair (2 row frames x 14 column frames per warp):
+//                 read the 9 covariance entries of the pair, per-pair solve, store the float
+//                 straight into cpptraj's Matrix<float> layout
+// 128 rows = 42 triples + 2 padding rows, and 32 is no multiple of 3: triples 10 (rows 30..32) and
+// 21 (rows 63..65) straddle two drain warps.  Their tail lanes write a partial sum to two extra
+// slots which the solve threads of row frames 3 and 7 add.
 // The exchange buffer is a ring of four column groups (7 column frames each) with its own
 // full/empty mbarriers, so the drain of tile n+1 runs under the solve of tile n, both under the
 // MMAs of tile n+2: no CTA-wide barrier anywhere in the steady state.
-// Tiles are enumerated column tile by column tile (valid row tiles only), tile t of that list
-// going to CTA t % gridDim.x: every CTA gets the same number of tiles (+-1) and CTAs running
-// at the same time share their B operand in L2.
+// Tiles are enumerated column tile by column tile (valid row tiles only); the list is cut into
+// chunks of `chunkLen` consecutive tiles, chunk c going to CTA group c % groups: every group gets
+// the same number of tiles (+-1), groups running at the same time work on neighbouring columns
+// (their A rows stay in L2), and consecutive tiles of a group share the column operand (RES).
 // ----------------------------------------------------------------------------
-constexpr int I8_DRAIN_WARPS = 4;
+constexpr int I8_DRAIN_WARPS = 8;            // two per TMEM sub-partition: one per column half of the tile
 constexpr int I8_SOLVE_WARPS = 14;
-constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 18
-constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 19
-constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
-constexpr int I8_XROW_BYTES = 24;            // 3 doubles per (operand row, column frame)
-constexpr int I8_XJ_STRIDE = 128 * I8_XROW_BYTES + 88;  // 3160 B: (stride/4) % 32 == 22 -> conflict-free LDS.64 / STS.64
-constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_STRIDE;  // 88480
-constexpr int I8_MAX_STAGES = 5;
-constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8;
-template <int CG> __host__ __device__ constexpr int i8_smem_bytes() { return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 256; }   // + barriers
+constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 22
+constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 23
+constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 768
+constexpr int I8_XSLOTS = 44;                // 42 (frame, plane) triples + 2 partial-sum slots
+constexpr int I8_XJ_DBL = 3 * I8_XSLOTS + 1; // 133 doubles per column frame: odd => conflict-free LDS.64 / STS.64
+constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 29792
+constexpr int I8_MAX_STAGES = 8;
+constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 1;
+template <int CG, bool RES> __host__ __device__ constexpr int i8_smem_bytes() {
+  return I8Geom<CG, RES>::STAGES * i8_stage_bytes<CG, RES>() + (RES ? I8_RES_MAX_C * I8_BLK_BYTES : 0) + I8_XBUF_BYTES + 32 + 256;
+}
 static_assert(I8_NBARS * 8 + 8 <= 256, "barrier block");
-static_assert(i8_smem_bytes<1>() <= 232448 && i8_smem_bytes<2>() <= 232448, "shared memory budget");
+static_assert(I8_XBUF_BYTES % 32 == 0, "barrier alignment");
+static_assert(i8_smem_bytes<1, false>() <= 232448 && i8_smem_bytes<2, false>() <= 232448 && i8_smem_bytes<2, true>() <= 232448,
+              "shared memory budget");
 
 struct PairI8Args {
   const uint8_t* PA;   // operand images of the row frames (i)
@@ -334,15 +353,18 @@ struct PairI8Args {
   int rowLo, rowHi;    // rows written by this launch: [rowLo, rowHi)
   int it0, it1;        // i super-tiles (CG row groups = 14*CG frames) of this launch: [it0, it1)
   int jt0, jt1;        // j tiles (28 frames) of this launch: [jt0, jt1)
+  int chunkLen;        // consecutive tiles of the list per chunk (>= 1)
   const double* totalMass;
   double invScale2;    // 2^-2qs: integer covariance -> A^2
   float* out;          // TRI: out[triIndex - outBase]; FULL: out[i*ldo + j]
   size_t outBase;
   size_t ldo;
+  // ---- DBG instantiation only
   double* dbgS;        // nullable: 9 doubles per (i,j) at (i*nCols + j)*9, integer units
   long long* dbgClk;   // nullable: per-CTA cycle counters [16] (timing experiments)
   int dbgMode;         // 0 normal; timing experiments: 1 no per-pair solve, 2 drain only frees TMEM,
-                       // 3 = 2 + no operand loads, 6 = solve warps only recycle the exchange buffer
+                       // 3 = 2 + no operand loads, 4 = 2 + every CTA streams the same A rows, 5 = 2 + no MMAs,
+                       // 6 = solve warps only recycle the exchange buffer
 };
 
 /// Row super-tiles [it0, hi) of column tile jt hold at least one wanted pair.
@@ -360,97 +382,140 @@ __host__ __device__ inline long i8_count_tiles(int it0, int it1, int jt0, int jt
   for (int jt = jt0; jt < jt1; ++jt) n += i8_col_tiles<TRI, CG>(it0, it1, jt);
   return n;
 }
-/// Walks this CTA group's share of the tile list; every role keeps its own copy (two registers).
+/// Walks this CTA group's chunks of the tile list; every role keeps its own copy.
 template <bool TRI, int CG>
 struct I8TileIter {
-  int jt, base, t;
-  __device__ __forceinline__ void init(const PairI8Args& a) { jt = a.jt0; base = 0; t = (int)blockIdx.x / CG; }
+  int jt, base;         // column being walked and the list position of its first tile
+  int pos, chunkEnd;    // next list position of this group, end of its current chunk
+  int skip;             // list positions between the end of one chunk and the start of the group's next one
+  __device__ __forceinline__ void init(const PairI8Args& a) {
+    jt = a.jt0; base = 0;
+    pos = ((int)blockIdx.x / CG) * a.chunkLen; chunkEnd = pos + a.chunkLen;
+    skip = ((int)gridDim.x / CG - 1) * a.chunkLen;
+  }
   __device__ __forceinline__ bool next(const PairI8Args& a, int& it, int& jtOut) {
+    if (pos == chunkEnd) { pos += skip; chunkEnd = pos + a.chunkLen; }
     while (jt < a.jt1) {
       const int c = i8_col_tiles<TRI, CG>(a.it0, a.it1, jt);
-      if (t < base + c) { it = a.it0 + (t - base); jtOut = jt; t += (int)gridDim.x / CG; return true; }
+      if (pos < base + c) { it = a.it0 + (pos - base); jtOut = jt; ++pos; return true; }
       base += c; ++jt;
     }
     return false;
   }
 };
 
-/// (E0 - lambda_max)/E0 for the tcgen05 epilogue.  FP64 dependent-issue latency is long on this part, so
-/// the FP64 chain is kept as short as the cancellation allows.  With everything divided by E0 the key-matrix
-/// quartic is P(x) = x^4 + c2 x^2 + c1 x + c0 with the wanted root x = lambda/E0 in (0,1]; x = 1 - y gives
-///     Q(y) = y^4 - 4 y^3 + (6 + c2) y^2 - (4 + 2 c2 + c1) y + (1 + c2 + c1 + c0),
-/// whose smallest non-negative root y is the quantity the RMSD needs.  The coefficients (q0 is a
-/// cancellation down to ~y) and ONE final Newton correction are FP64; the monotone approach from y = 0 runs
-/// in FP32, which resolves y to ~1e-7 RELATIVE whatever its magnitude.  Returns false when the root is
-/// ill-conditioned or the correction is not small: the caller then takes the guarded FP64 path.
-__device__ __forceinline__ bool i8_relative_gap(const double* S, double sInv, double& gap) {
-  double T[9];
-#pragma unroll
-  for (int x = 0; x < 9; ++x) T[x] = S[x] * sInv;
-  const double m00 = fma(T[6], T[6], fma(T[3], T[3], T[0] * T[0]));
-  const double m11 = fma(T[7], T[7], fma(T[4], T[4], T[1] * T[1]));
-  const double m22 = fma(T[8], T[8], fma(T[5], T[5], T[2] * T[2]));
-  const double m01 = fma(T[6], T[7], fma(T[3], T[4], T[0] * T[1]));
-  const double m02 = fma(T[6], T[8], fma(T[3], T[5], T[0] * T[2]));
-  const double m12 = fma(T[7], T[8], fma(T[4], T[5], T[1] * T[2]));
+// Per-pair solve of the tcgen05 epilogue.  On this part FP64 instructions share the tensor pipe with
+// tcgen05.mma and crawl (~10 % of their rate) while MMAs are in flight (tools/microbench/mma_fp64_mix.cu),
+// so the solve is cut in two: i8_coeffs() -- everything that must be FP64, 47 instructions -- runs in a short
+// window between two tiles' MMAs (the MMA warp waits for it), i8_root() -- FP32 Newton, integer exponent
+// scaling and 8 FP64 instructions for the final correction -- runs under the next tile's MMAs.
+//
+// Key-matrix quartic P(l) = l^4 + c2 l^2 + c1 l + c0 (src/qcprot.cpp:167-246 states the same identity); the
+// wanted root is lambda_max <= E0.  With l = E0 - y:
+//     Q(y) = y^4 - 4 E0 y^3 + (6 E0^2 + c2) y^2 - (4 E0^3 + 2 c2 E0 + c1) y + P(E0),
+// whose smallest non-negative root y = E0 - lambda_max is the quantity the RMSD needs.  All coefficients are
+// computed UNSCALED in FP64 (values up to ~2^240: no division, no normalisation multiplies).
+struct I8Quartic { double q0, q1, q2, e0; };
+__device__ __forceinline__ I8Quartic i8_coeffs(const double* S, double e0) {
+  const double m00 = fma(S[6], S[6], fma(S[3], S[3], S[0] * S[0]));
+  const double m11 = fma(S[7], S[7], fma(S[4], S[4], S[1] * S[1]));
+  const double m22 = fma(S[8], S[8], fma(S[5], S[5], S[2] * S[2]));
+  const double m01 = fma(S[6], S[7], fma(S[3], S[4], S[0] * S[1]));
+  const double m02 = fma(S[6], S[8], fma(S[3], S[5], S[0] * S[2]));
+  const double m12 = fma(S[7], S[8], fma(S[4], S[5], S[1] * S[2]));
   const double p1 = (m00 + m11) + m22;
   const double off = fma(m01, m01, fma(m02, m02, m12 * m12));
   const double trM2 = fma(2.0, off, fma(m00, m00, fma(m11, m11, m22 * m22)));
-  const double det = fma(T[0], fma(T[4], T[8], -T[5] * T[7]), fma(-T[1], fma(T[3], T[8], -T[5] * T[6]),
-                                                                  T[2] * fma(T[3], T[7], -T[4] * T[6])));
+  const double det = fma(S[0], fma(S[4], S[8], -S[5] * S[7]), fma(-S[1], fma(S[3], S[8], -S[5] * S[6]),
+                                                                  S[2] * fma(S[3], S[7], -S[4] * S[6])));
   const double c2 = -2.0 * p1, c1 = -8.0 * det, c0 = fma(2.0, trM2, -p1 * p1);
-  const double q0 = ((1.0 + c2) + c1) + c0;
-  const double q1 = -((4.0 + 2.0 * c2) + c1);
-  const double q2 = 6.0 + c2;
-  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2;
+  const double e2 = e0 * e0;
+  I8Quartic r;
+  r.q0 = fma(fma(e2 + c2, e0, c1), e0, c0);
+  r.q1 = -fma(fma(4.0, e2, 2.0 * c2), e0, c1);
+  r.q2 = fma(6.0, e2, c2);
+  r.e0 = e0;
+  return r;
+}
+/// v * 2^e through the exponent field (integer pipe; zero, denormal and underflowing results give 0).
+__device__ __forceinline__ double i8_scale2(double v, int e) {
+  const int hi = __double2hiint(v);
+  const int ex = ((hi >> 20) & 0x7ff);
+  const int nx = ex + e;
+  return (ex == 0 || nx <= 0) ? 0.0 : __hiloint2double((hi & 0x800fffff) | (nx << 20), __double2loint(v));
+}
+/// Smallest non-negative root of Q, returned as r2 = y * unit (unit = 2/M in integer units).  In the variable
+/// y' = y / 2^k, 2^k <= E0 < 2^(k+1), the coefficients are O(1): the monotone approach from y' = 0 runs in FP32
+/// (resolves y' to ~1e-7 RELATIVE whatever its magnitude), ONE final Newton correction is FP64.  Returns false
+/// when the root is ill-conditioned or the correction is not small: the caller then takes the guarded FP64 path.
+__device__ __forceinline__ bool i8_root(const I8Quartic& c, double unit, double& r2) {
+  const int k = ((__double2hiint(c.e0) >> 20) & 0x7ff) - 1023;
+  const double q0 = i8_scale2(c.q0, -4 * k), q1 = i8_scale2(c.q1, -3 * k), q2 = i8_scale2(c.q2, -2 * k);
+  const double q3 = -4.0 * i8_scale2(c.e0, -k);
+  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2, f3 = (float)q3;
+  const float g3 = 3.f * f3, g2 = 2.f * f2;
   float y = 0.f, dq = f1, step;
 #pragma unroll
   for (int it = 0; it < 3; ++it) {
-    const float qy = fmaf(fmaf(fmaf(y - 4.f, y, f2), y, f1), y, f0);
-    dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+    const float qy = fmaf(fmaf(fmaf(y + f3, y, f2), y, f1), y, f0);
+    dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
     y -= __fdividef(qy, dq);
   }
 #pragma unroll 1
-  for (int it = 0; it < 24; ++it) {   // until the whole warp has converged (gaps up to y ~ 0.5: RMSD ~ radius of gyration)
-    const float qy = fmaf(fmaf(fmaf(y - 4.f, y, f2), y, f1), y, f0);
-    dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+  for (int it = 0; it < 24; ++it) {   // until the whole warp has converged (gaps up to y' ~ 0.5: RMSD ~ radius of gyration)
+    const float qy = fmaf(fmaf(fmaf(y + f3, y, f2), y, f1), y, f0);
+    dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
     step = __fdividef(qy, dq);
     y -= step;
     if (!__any_sync(0xffffffffu, fabsf(step) > 4e-7f * fabsf(y))) break;
   }
   double yd = (double)y;
-  const double Q = fma(fma(fma(yd - 4.0, yd, q2), yd, q1), yd, q0);
-  dq = fmaf(fmaf(fmaf(4.f, y, -12.f), y, 2.f * f2), y, f1);
+  const double Q = fma(fma(fma(yd + q3, yd, q2), yd, q1), yd, q0);
+  dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
   const double d = Q * (double)__frcp_rn(dq);
   yd -= d;
-  gap = yd;
-  // conditioning (|P'| relative to lambda^3 = 1 here) and size of the correction (FP32 left ~1e-7 relative)
-  return (fabsf(dq) >= 7e-3f) && (fabs(d) <= 1e-5 * fabs(yd) + 1e-14) && (yd < 1.5);
+  r2 = yd * i8_scale2(unit, k);
+  // conditioning (|P'| relative to lambda^3 ~ 1 here) and size of the correction (FP32 left ~1e-7 relative)
+  const float x0 = -0.25f * f3;   // E0 / 2^k in [1, 2): lambda^3 scale of the derivative
+  return (fabsf(dq) >= 7e-3f * x0 * x0 * x0) && (fabs(d) <= 1e-5 * fabs(yd) + 1e-14) && (yd < 3.0) && (k > 0);
 }
-/// Guarded FP64 path (Newton on the unscaled quartic, SVD for double roots); rarely taken.
-__device__ __noinline__ double i8_relative_gap_slow(const double* S, double e0) {
+/// Guarded FP64 path (Newton on the unscaled quartic, SVD for double roots); rarely taken.  The covariance
+/// travels BY VALUE: a pointer parameter would force the caller's S into local memory on every pair.
+__device__ __noinline__ double i8_relative_gap_slow(double s0, double s1, double s2, double s3, double s4, double s5,
+                                                    double s6, double s7, double s8, double e0) {
+  const double S[9] = {s0, s1, s2, s3, s4, s5, s6, s7, s8};
   return (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
 }
 
-template <bool TRI, int CG>
+template <bool TRI, int CG, bool RES, bool DBG>
 __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
-  using GEO = I8Geom<CG>;
+  static_assert(!RES || CG == 2, "the resident column operand needs the CTA-pair geometry");
+  using GEO = I8Geom<CG, RES>;
   constexpr int STAGES = GEO::STAGES, BPS = GEO::BPS, BBLK = GEO::BBLK;
-  constexpr int STAGE_BYTES = i8_stage_bytes<CG>();
+  constexpr int STAGE_BYTES = i8_stage_bytes<CG, RES>();
   extern __shared__ __align__(1024) unsigned char smem_i8[];
   unsigned char* stages = smem_i8;
-  unsigned char* xbuf = smem_i8 + STAGES * STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(xbuf + I8_XBUF_BYTES);
+  unsigned char* bres = smem_i8 + STAGES * STAGE_BYTES;                     // RES: this CTA's column row group, all chunks
+  unsigned char* xbufRaw = bres + (RES ? I8_RES_MAX_C * I8_BLK_BYTES : 0);
+  long long* xbuf = reinterpret_cast<long long*>(xbufRaw);   // exchange buffer: exact int64 covariance entries
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xbufRaw + I8_XBUF_BYTES);
   uint64_t* fullBar = bars;                            // [STAGES]  operands landed (CG 2: in both CTAs, seen by the leader)
   uint64_t* emptyBar = bars + I8_MAX_STAGES;           // [STAGES]  MMAs reading the stage done
   uint64_t* accFull = bars + 2 * I8_MAX_STAGES;        // [2]  accumulator complete
   uint64_t* accEmpty = bars + 2 * I8_MAX_STAGES + 2;   // [2]  accumulator drained (CG 2: by both CTAs; leader's copy is used)
   uint64_t* xFull = bars + 2 * I8_MAX_STAGES + 4;      // [4]  exchange group written
   uint64_t* xEmpty = bars + 2 * I8_MAX_STAGES + 8;     // [4]  exchange group read
+  uint64_t* fpDone = bars + 2 * I8_MAX_STAGES + 12;    // [1]  FP64 window of a tile closed (CG 2: by both CTAs; leader's copy)
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();   // 0 = leader (issues the MMAs)
+  const int dbgMode = DBG ? a.dbgMode : 0;
+  long long* const dbgClk = DBG ? a.dbgClk : nullptr;
+  // Ring depth.  RES: a resident chunk may be overwritten (next column) only after the previous tile's MMAs on it
+  // are done; waiting for the ring slot proves that when a tile has at least `depth` stages.
+  const int stagesPerTile = (a.nC + BPS - 1) / BPS;
+  const int depth = stagesPerTile < STAGES ? stagesPerTile : STAGES;
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -459,7 +524,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       mbar_init(smem_u32(&emptyBar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS * CG); }
-    for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), I8_DRAIN_WARPS); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
+    for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), I8_DRAIN_WARPS / 2); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
+    mbar_init(smem_u32(fpDone), I8_SOLVE_WARPS * CG);
     mbar_fence_init();
   }
   if (warp == I8_WARP_MMA) tmem_alloc<CG>(smem_u32(tmemBaseSlot), 512);
@@ -476,22 +542,32 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     // ===================== TMA producer (one thread per CTA) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage0 = smem_u32(stages);
+    const uint32_t bres0 = smem_u32(bres);
     long long cwEmpty = 0;
-    if (lane == 0)
+    int lastJt = -1;
     while (tiles.next(a, it, jt)) {
       // this CTA's A row group, and the B row group(s) it stages: both (CG 1) or the rank-th (CG 2)
-      const uint8_t* gA = a.PA + (size_t)(CG * it + (int)rank) * a.nC * I8_BLK_BYTES;
+      const int itA = (DBG && dbgMode == 4) ? a.it0 : it;   // timing experiment 4: every CTA streams the same A rows
+      const uint8_t* gA = a.PA + (size_t)(CG * itA + (int)rank) * a.nC * I8_BLK_BYTES;
       const uint8_t* gB0 = a.PB + (size_t)(2 * jt + (CG == 2 ? (int)rank : 0)) * a.nC * I8_BLK_BYTES;
       const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;   // CG 1 only
+      const bool newCol = RES && (jt != lastJt);
+      lastJt = jt;
       for (int c = 0; c < a.nC; c += BPS) {
         const int nb = (a.nC - c < BPS) ? a.nC - c : BPS;
-        const long long c0 = a.dbgClk ? clock64() : 0;
+        const long long c0 = (DBG && dbgClk) ? clock64() : 0;
         mbar_wait(smem_u32(&emptyBar[stage]), phase ^ 1u);
-        if (a.dbgClk) cwEmpty += clock64() - c0;
+        if (DBG && dbgClk) cwEmpty += clock64() - c0;
         const uint32_t bar = smem_u32(&fullBar[stage]);
         const uint32_t dst = stage0 + (uint32_t)stage * STAGE_BYTES;
-        if (a.dbgMode == 3) {
+        if (!elect_one()) {
+          // the other lanes only keep the loop converged
+        } else if (DBG && dbgMode == 3) {
           mbar_arrive(bar);
+        } else if constexpr (RES) {
+          mbar_expect_tx(bar, (uint32_t)(nb * I8_BLK_BYTES * (newCol ? 2 : 1)));
+          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
+          if (newCol) bulk_g2s(bres0 + (uint32_t)c * I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
         } else {
           mbar_expect_tx(bar, (uint32_t)(nb * (1 + BBLK) * I8_BLK_BYTES));
           // consecutive 64-atom blocks of one row group are contiguous in the image: one bulk copy per operand
@@ -507,87 +583,122 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
               }
           }
         }
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        __syncwarp();
+        if (++stage == depth) { stage = 0; phase ^= 1u; }
       }
     }
-    if (a.dbgClk && lane == 0) a.dbgClk[16 * blockIdx.x + 0] += cwEmpty;
+    if (DBG && dbgClk && lane == 0) dbgClk[16 * blockIdx.x + 0] += cwEmpty;
   } else if (warp == I8_WARP_MMA && rank == 0) {
     // ===================== MMA issuer (one thread; CG 2: of the leader CTA) =====================
     constexpr uint32_t idesc = umma_idesc_i8(128 * CG, 256);
     // descriptor = constant high part (LBO 128 B, SBO 512 B, version 1) | (smem address >> 4)
     constexpr uint64_t descHi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     const uint32_t stage0 = smem_u32(stages);
+    const uint32_t bres0 = smem_u32(bres);
     int stage = 0; uint32_t phase = 0; int n = 0;
     long long cwAcc = 0, cwFull = 0;
-    const long long cStart = a.dbgClk ? clock64() : 0;
-    if (lane == 0)
+    const long long cStart = (DBG && dbgClk) ? clock64() : 0;
     while (tiles.next(a, it, jt)) {
       const int b = n & 1;
-      long long c0 = a.dbgClk ? clock64() : 0;
+      long long c0 = (DBG && dbgClk) ? clock64() : 0;
       if constexpr (CG == 2) mbar_wait_cluster(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       else mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
-      if (a.dbgClk) cwAcc += clock64() - c0;
+      // FP64 window: the solve warps finished the FP64 part of tile n-2 (they started it when tile n-1's MMAs completed)
+      if (n >= 2) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1));
+      if (DBG && dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
       const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
       for (int c = 0; c < a.nC; c += BPS) {
         const int nb = (a.nC - c < BPS) ? a.nC - c : BPS;
-        c0 = a.dbgClk ? clock64() : 0;
+        c0 = (DBG && dbgClk) ? clock64() : 0;
         if constexpr (CG == 2) mbar_wait_cluster(smem_u32(&fullBar[stage]), phase);
         else mbar_wait(smem_u32(&fullBar[stage]), phase);
-        if (a.dbgClk) cwFull += clock64() - c0;
+        if (DBG && dbgClk) cwFull += clock64() - c0;
         tc_fence_after();
         const uint32_t sA = stage0 + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t sB = sA + BPS * I8_BLK_BYTES;
+        const uint32_t sB = RES ? bres0 + (uint32_t)c * I8_BLK_BYTES : sA + BPS * I8_BLK_BYTES;
+        constexpr int BSTEP = RES ? 1 : BBLK;   // blocks between consecutive 64-atom chunks of B
+        if (elect_one()) {
+        if (!(DBG && dbgMode == 5))   // timing experiment 5: operand pipeline without the MMAs
 #pragma unroll
         for (int cc = 0; cc < BPS; ++cc) {
           if (cc < nb) {
             const uint64_t dA = descHi | (uint64_t)(((sA + cc * I8_BLK_BYTES) >> 4) & 0x3fff);
-            const uint64_t dB = descHi | (uint64_t)(((sB + cc * BBLK * I8_BLK_BYTES) >> 4) & 0x3fff);
+            const uint64_t dB = descHi | (uint64_t)(((sB + cc * BSTEP * I8_BLK_BYTES) >> 4) & 0x3fff);
 #pragma unroll
             for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
               umma_i8<CG>(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | cc | k) != 0));
           }
         }
         umma_commit<CG>(smem_u32(&emptyBar[stage]));
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (c + BPS >= a.nC) umma_commit<CG>(smem_u32(&accFull[b]));   // last stage of the tile: accumulator complete
+        }
+        __syncwarp();
+        if (++stage == depth) { stage = 0; phase ^= 1u; }
       }
-      umma_commit<CG>(smem_u32(&accFull[b]));
       ++n;
     }
-    if (a.dbgClk && lane == 0) {
-      a.dbgClk[16 * blockIdx.x + 1] += cwAcc; a.dbgClk[16 * blockIdx.x + 2] += cwFull;
-      a.dbgClk[16 * blockIdx.x + 3] += clock64() - cStart; a.dbgClk[16 * blockIdx.x + 4] += n;
+    if (DBG && dbgClk && lane == 0) {
+      dbgClk[16 * blockIdx.x + 1] += cwAcc; dbgClk[16 * blockIdx.x + 2] += cwFull;
+      dbgClk[16 * blockIdx.x + 3] += clock64() - cStart; dbgClk[16 * blockIdx.x + 4] += n;
     }
   } else if (warp == I8_WARP_MMA) {
     // ===================== CG 2, peer CTA: relay "my operand half has landed" to the leader =====================
     if constexpr (CG == 2) {
       int stage = 0; uint32_t phase = 0;
-      if (lane == 0)
       while (tiles.next(a, it, jt)) {
         for (int c = 0; c < a.nC; c += BPS) {
           mbar_wait(smem_u32(&fullBar[stage]), phase);
-          mbar_arrive_cluster(cluster_map(smem_u32(&fullBar[stage]), 0));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          if (elect_one()) mbar_arrive_cluster(cluster_map(smem_u32(&fullBar[stage]), 0));
+          __syncwarp();
+          if (++stage == depth) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp < I8_DRAIN_WARPS) {
     // ===================== drain warps =====================
-    const int sp = warp;              // TMEM sub-partition: lanes 32*sp .. 32*sp+31
-    const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit
-    const double wdig = (r % 3 == 0) ? 1.0 : ((r % 3 == 1) ? 256.0 : 65536.0);
-    const double wmagic = -6755399441055744.0 * wdig;   // -(1.5 * 2^52) * weight
-    unsigned char* xrow = xbuf + (size_t)r * I8_XROW_BYTES;
+    const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
+    const int hh = warp >> 2;         // column half of the tile: exchange groups 2*hh, 2*hh+1
+    const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit = 3*triple + digit
+    const int dg = r % 3, trip = r / 3;
+    const int wshift = 8 * dg;        // A digit weight 256^dg of this operand row
+    // rows r+1 / r+2 join this lane's sum when they belong to the same triple AND the same warp
+    const bool take1 = (lane + 1 < 32) && ((r + 1) / 3 == trip);
+    const bool take2 = (lane + 2 < 32) && ((r + 2) / 3 == trip);
+    // writers: the head row of every triple (whole, or the head part of a straddling one) and lane 0 when it is
+    // the tail part of a straddling triple (row 32: triple 10 -> slot 42; row 64: triple 21 -> slot 43)
+    const bool writer = (r < 3 * 42) && (dg == 0 || lane == 0);
+    const int slot = (dg == 0) ? trip : (sp == 1 ? 42 : 43);
+    long long* xdst = xbuf + 3 * slot;
     int n = 0;
-    long long cwAcc = 0, cwX = 0;
-    const long long cStart = a.dbgClk ? clock64() : 0;
+    long long cwAcc = 0, cwX = 0, cwLd = 0, cwFold = 0;
+    const long long cStart = (DBG && dbgClk) ? clock64() : 0;
+    // One column frame: 9 accumulators (q-major, B digit minor) -> 3 exact int64 sums over the B digits, weighted
+    // by the A digit of this row and folded over the three rows of the triple with two shuffles.  INTEGER ONLY:
+    // on this part FP64 instructions share the tensor pipe with tcgen05.mma and crawl (~10 % of their rate)
+    // while MMAs are in flight (tools/microbench/mma_fp64_mix.cu), so the drain must not touch the FP64 pipe.
+    auto fold_frame = [&](const int* v, long long* dst) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const long long x0 = ((long long)v[3 * q] + (long long)v[3 * q + 1] * 256 + (long long)v[3 * q + 2] * 65536) << wshift;
+        long long x1 = x0, x2 = x0;
+        if (!(DBG && dbgMode == 7)) {   // timing experiment 7: no shuffles
+          x1 = __shfl_down_sync(0xffffffffu, x0, 1);
+          x2 = __shfl_down_sync(0xffffffffu, x0, 2);
+        }
+        long long tot = x0;
+        if (take1) tot += x1;
+        if (take2) tot += x2;
+        if (writer) dst[q] = tot;
+      }
+    };
     while (tiles.next(a, it, jt)) {
       const int b = n & 1;
-      long long c0 = a.dbgClk ? clock64() : 0;
+      long long c0 = (DBG && dbgClk) ? clock64() : 0;
       mbar_wait(smem_u32(&accFull[b]), (uint32_t)((n >> 1) & 1));
-      if (a.dbgClk) cwAcc += clock64() - c0;
+      if (DBG && dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
-      if (a.dbgMode == 2 || a.dbgMode == 3) {   // timing experiment: MMA + operand pipeline only
+      if (DBG && dbgMode >= 2 && dbgMode <= 5) {   // timing experiment: MMA + operand pipeline only
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -598,17 +709,36 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         continue;
       }
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = 2 * hh + gg;
         // column frames 7g .. 7g+6: accumulator columns 9*jl (frames 0..13) or 128 + 9*(jl-14) (frames 14..27)
-        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + (g >> 1) * 128 + (g & 1) * 63) + ((uint32_t)(32 * sp) << 16);
-        int v[64];
-        tmem_ld32(tcol, v);
-        tmem_ld32(tcol + 32, v + 32);
-        c0 = a.dbgClk ? clock64() : 0;
+        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + hh * 128 + gg * 63) + ((uint32_t)(32 * sp) << 16);
+        long long* dst = xdst + (size_t)(7 * g) * I8_XJ_DBL;
+        int v[32];
+        long long c1 = (DBG && dbgClk) ? clock64() : 0;
+        if (DBG && dbgMode == 8) {   // timing experiment 8: no TMEM loads
+#pragma unroll
+          for (int x = 0; x < 32; ++x) v[x] = x + lane;
+        } else
+        tmem_ld32(tcol, v);                     // frames 0..2 of the group (27 columns)
+        c0 = (DBG && dbgClk) ? clock64() : 0;
         mbar_wait(smem_u32(&xEmpty[g]), (uint32_t)((n & 1) ^ 1));   // the solve warps are done with this group of tile n-1
-        if (a.dbgClk) cwX += clock64() - c0;
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwX += c2 - c0; c1 += c2 - c0; }
         tmem_ld_wait();
-        if (g == 3) {   // this warp is done reading accumulator buffer b
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + (size_t)jj * I8_XJ_DBL);
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; c1 = c2; }
+        if (!(DBG && dbgMode == 8)) tmem_ld32(tcol + 27, v);                // frames 3..5
+        tmem_ld_wait();
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
+#pragma unroll
+        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + (size_t)(3 + jj) * I8_XJ_DBL);
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; c1 = c2; }
+        if (!(DBG && dbgMode == 8)) tmem_ld16(tcol + 47, v);                // columns 47..62: frame 6 is the last 9 (stays inside the accumulator)
+        tmem_ld_wait();
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
+        if (gg == 1) {   // this warp is done reading accumulator buffer b
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -616,27 +746,17 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
             else mbar_arrive(smem_u32(&accEmpty[b]));
           }
         }
-        double* dst = reinterpret_cast<double*>(xrow + (size_t)(7 * g) * I8_XJ_STRIDE);
-#pragma unroll
-        for (int jj = 0; jj < 7; ++jj) {
-#pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            // exact int64 -> FP64 without the (slow, XU-pipe) I2F.F64.S64: for |V| < 2^51 the bit pattern
-            // 0x4338000000000000 + V is the double 1.5*2^52 + V; one FMA removes the offset and applies the
-            // digit weight of this operand row (both exact).
-            const long long sv = 0x4338000000000000LL + (long long)v[9 * jj + 3 * q] +
-                                 (long long)v[9 * jj + 3 * q + 1] * 256 + (long long)v[9 * jj + 3 * q + 2] * 65536;
-            dst[(size_t)jj * (I8_XJ_STRIDE / 8) + q] = fma(__longlong_as_double(sv), wdig, wmagic);
-          }
-        }
+        fold_frame(v + 7, dst + (size_t)6 * I8_XJ_DBL);
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&xFull[g]));
       }
       ++n;
     }
-    if (a.dbgClk && lane == 0 && warp == 0) {
-      a.dbgClk[16 * blockIdx.x + 5] += cwAcc; a.dbgClk[16 * blockIdx.x + 6] += cwX;
-      a.dbgClk[16 * blockIdx.x + 7] += clock64() - cStart;
+    if (DBG && dbgClk && lane == 0 && warp == 0) {
+      dbgClk[16 * blockIdx.x + 5] += cwAcc; dbgClk[16 * blockIdx.x + 6] += cwX;
+      dbgClk[16 * blockIdx.x + 7] += clock64() - cStart;
+      dbgClk[16 * blockIdx.x + 10] += cwLd; dbgClk[16 * blockIdx.x + 11] += cwFold;
     }
   } else {
     // ===================== solve warps: one thread per frame pair =====================
@@ -647,30 +767,49 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     const bool laneOn = jlRaw < I8_TILE_I;
     const int jl = I8_TILE_I * h + (laneOn ? jlRaw : I8_TILE_I - 1);
     const double outScale = 2.0 * a.invScale2 / a.totalMass[0];   // rmsd^2 = (E0 - lambda) * outScale (integer units)
-    const double toInt = 1.0 / a.invScale2;                        // G (A^2) -> integer units (exact power of two)
-    const double* src = reinterpret_cast<const double*>(xbuf + (size_t)jl * I8_XJ_STRIDE + (size_t)(9 * il) * I8_XROW_BYTES);
-    const bool solveOff = (a.dbgMode == 2 || a.dbgMode == 3);
+    const double halfToInt = 0.5 / a.invScale2;                    // G (A^2) -> integer units, halved (exact power of two)
+    const long long* src = xbuf + (size_t)jl * I8_XJ_DBL + 9 * il;    // [3*il + p][q], p-major: S[3p+q] directly
+    // straddling triples: 10 = (frame 3, plane 1) and 21 = (frame 7, plane 0) have a second partial sum
+    const long long* srcX = xbuf + (size_t)jl * I8_XJ_DBL + 3 * (il == 3 ? 42 : 43);
+    const int xOff = (il == 3) ? 3 : ((il == 7) ? 0 : -1);
+    const bool solveOff = DBG && dbgMode >= 2 && dbgMode <= 5;
+    const uint32_t fpDoneAddr = CG == 2 ? cluster_map(smem_u32(fpDone), 0) : smem_u32(fpDone);
     int n = 0;
-    long long cwX = 0;
-    const long long cStart = a.dbgClk ? clock64() : 0;
-    while (tiles.next(a, it, jt)) {
-      if (solveOff) continue;
+    long long cwX = 0, cwWin = 0;
+    const long long cStart = (DBG && dbgClk) ? clock64() : 0;
+    int itN, jtN;
+    bool have = tiles.next(a, it, jt);
+    while (have) {
+      const bool hasNext = tiles.next(a, itN, jtN);   // one tile of look-ahead: is there an MMA to wait for?
+      if (solveOff) {
+        __syncwarp();
+        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr); }
+        ++n; it = itN; jt = jtN; have = hasNext;
+        continue;
+      }
       const int i = I8_TILE_I * (CG * it + (int)rank) + il, j = I8_TILE_J * jt + jl;
       const bool valid = laneOn && i < a.nRows && j < a.nCols && i >= a.rowLo && i < a.rowHi && (!TRI || j > i);
-      // everything stays in integer units (exact); one scale at the very end
-      double e0 = 1.0;
-      if (valid) e0 = 0.5 * (__ldg(a.GA + i) + __ldg(a.GB + j)) * toInt;
-      const double sInv = 1.0 / e0;
-      long long c0 = a.dbgClk ? clock64() : 0;
+      double ga = 0.5, gb = 0.5;
+      if (valid) { ga = __ldg(a.GA + i); gb = __ldg(a.GB + j); }
+      // ---- 1. the exact integer covariance of the pair (under the MMAs of tile n+1)
+      long long c0 = (DBG && dbgClk) ? clock64() : 0;
       mbar_wait(smem_u32(&xFull[2 * h]), (uint32_t)(n & 1));
       mbar_wait(smem_u32(&xFull[2 * h + 1]), (uint32_t)(n & 1));
-      if (a.dbgClk) cwX += clock64() - c0;
+      if (DBG && dbgClk) cwX += clock64() - c0;
       double S[9];
-      if (a.dbgMode != 6) {
+      if (!(DBG && dbgMode == 6)) {
+        long long SI[9];
 #pragma unroll
-        for (int p = 0; p < 3; ++p)
+        for (int x = 0; x < 9; ++x) SI[x] = src[x];
+        if (xOff >= 0) {
 #pragma unroll
-          for (int q = 0; q < 3; ++q) S[3 * p + q] = (src[(3 * p) * 3 + q] + src[(3 * p + 1) * 3 + q]) + src[(3 * p + 2) * 3 + q];
+          for (int q = 0; q < 3; ++q) {
+            const long long e = srcX[q];
+            if (xOff == 3) SI[3 + q] += e; else SI[q] += e;
+          }
+        }
+#pragma unroll
+        for (int x = 0; x < 9; ++x) S[x] = __ll2double_rn(SI[x]);   // I2F.F64.S64: XU pipe, not the FP64 pipe
       } else {
 #pragma unroll
         for (int x = 0; x < 9; ++x) S[x] = 0.0;
@@ -684,35 +823,53 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       }
       __syncwarp();
       if (lane == 0) { mbar_arrive(smem_u32(&xEmpty[2 * h])); mbar_arrive(smem_u32(&xEmpty[2 * h + 1])); }
-      ++n;
-      if (a.dbgMode == 6) continue;
-      if (a.dbgS && valid) {
+      if (DBG && a.dbgS && valid) {
 #pragma unroll
         for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
       }
-      float rms;
-      if (a.dbgMode == 1) {
-        rms = (float)(S[0] + S[4] + S[8]);
+      // ---- 2. FP64 window: wait until the MMAs of tile n+1 are done (the MMA warp will not issue tile n+2 before
+      //         every solve warp of the CTA (pair) has arrived on fpDone), do all the FP64 work, let the MMAs go on
+      c0 = (DBG && dbgClk) ? clock64() : 0;
+      if (hasNext) mbar_wait(smem_u32(&accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
+      I8Quartic cq;
+      if (!(DBG && (dbgMode == 6 || dbgMode == 1 || dbgMode == 7 || dbgMode == 8))) {
+        cq = i8_coeffs(S, (ga + gb) * halfToInt);
+        asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2) : "memory");   // computed before the arrive below
       } else {
-        double gap;   // (E0 - lambda_max) / E0
-        const bool ok = i8_relative_gap(S, sInv, gap);
-        if (valid && !ok) gap = i8_relative_gap_slow(S, e0);
-        // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
-        // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
-        const double r2 = gap * (e0 * outScale);
-        rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
+        cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0;
       }
-      if (valid) {
-        size_t idx;
-        if (TRI)
-          idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
-        else
-          idx = (size_t)i * a.ldo + (size_t)j;
-        a.out[idx] = rms;
+      __syncwarp();
+      if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr); }
+      if (DBG && dbgClk) cwWin += clock64() - c0;
+      ++n;
+      // ---- 3. root and store (under the MMAs of tile n+2)
+      if (!(DBG && dbgMode == 6)) {
+        float rms;
+        if (DBG && (dbgMode == 1 || dbgMode == 7 || dbgMode == 8)) {
+          rms = (float)(S[0] + S[4] + S[8]);
+        } else {
+          double r2;
+          const bool ok = i8_root(cq, outScale, r2);
+          if (valid && !ok)
+            r2 = i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale);
+          // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
+          // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
+          rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
+        }
+        if (valid) {
+          size_t idx;
+          if (TRI)
+            idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
+          else
+            idx = (size_t)i * a.ldo + (size_t)j;
+          a.out[idx] = rms;
+        }
       }
+      it = itN; jt = jtN; have = hasNext;
     }
-    if (a.dbgClk && lane == 0 && u == 0) {
-      a.dbgClk[16 * blockIdx.x + 8] += cwX; a.dbgClk[16 * blockIdx.x + 9] += clock64() - cStart;
+    if (DBG && dbgClk && lane == 0 && u == 0) {
+      dbgClk[16 * blockIdx.x + 8] += cwX; dbgClk[16 * blockIdx.x + 9] += clock64() - cStart;
+      dbgClk[16 * blockIdx.x + 12] += cwWin;
     }
   }
   // ---- teardown ----
@@ -769,6 +926,47 @@ __global__ void __launch_bounds__(128, 1) i8_mma_peak_kernel(int iters, int* sin
   }
   __syncthreads();
   if (warp == 0) tmem_dealloc<1>(tmemBase, 512);
+}
+
+
+// ----------------------------------------------------------------------------
+// tcgen05 latency probe: one thread issues nMma MMAs (M128 N256 K32, one accumulator), commits to an
+// mbarrier and waits for it; returns the average cycles from first issue to wake-up.  nMma = 0 measures
+// the commit -> mbarrier -> try_wait round trip alone.  Sizes the operand ring of pair_i8_kernel.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) i8_mma_latency_kernel(int nMma, int reps, long long* out) {
+  extern __shared__ __align__(1024) unsigned char smem_pk[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmemSlot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (3 * I8_BLK_BYTES) / 4; i += 128) reinterpret_cast<uint32_t*>(smem_pk)[i] = 0x01010101u * (uint32_t)(i & 3);
+  if (tid == 0) { mbar_init(smem_u32(&bar), 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<1>(smem_u32(&tmemSlot), 512);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmemBase = tmemSlot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = umma_idesc_i8(128, 256);
+    const uint32_t sA = smem_u32(smem_pk), sB = sA + I8_BLK_BYTES;
+    long long tot = 0;
+    uint32_t phase = 0;
+    for (int r = 0; r < reps + 2; ++r) {
+      const long long t0 = clock64();
+      for (int k = 0; k < nMma; ++k)
+        umma_i8<1>(tmemBase, umma_desc(sA + (k & 1) * 256, 128, 512), umma_desc(sB + (k & 1) * 256, 128, 512), idesc, (uint32_t)(k != 0));
+      umma_commit<1>(smem_u32(&bar));
+      mbar_wait(smem_u32(&bar), phase);
+      phase ^= 1u;
+      tc_fence_after();
+      const long long t1 = clock64();
+      if (r >= 2) tot += t1 - t0;
+    }
+    out[blockIdx.x] = tot / reps;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_before(); tmem_dealloc<1>(tmemBase, 512); }
 }
 
 }  // namespace b200
