@@ -53,7 +53,6 @@ def lib():
     L.b200_dev_rmsd_1vN.argtypes = [vp, sz, i, vp, i, vp, vp, i, vp, vp, vp, vp]
     L.b200_set_pair_engine.argtypes = [i]
     L.b200_set_i8_cta_group.argtypes = [i]
-    L.b200_set_i8_resident.argtypes = [i]
     L.b200_last_pair_engine.argtypes = [C.POINTER(i)]
     L.b200_debug_i8.argtypes = [vp, sz, i, vp, i, vp, vp, sz, C.POINTER(sz), vp, vp, vp, C.POINTER(i)]
     L.b200_get_stats.argtypes = [C.POINTER(Stats)]
@@ -66,7 +65,7 @@ def lib():
     for name in ("b200_init", "b200_init_devices", "b200_shard_rows", "b200_rms2d_tri", "b200_rms2d_tri_shard",
                  "b200_rms2d_full", "b200_rmsd_1vN_begin", "b200_rmsd_1vN_push_f64", "b200_rmsd_1vN_push_f32",
                  "b200_rmsd_1vN_flush", "b200_rmsd_1vN_end", "b200_dev_rms2d_tri", "b200_dev_rmsd_1vN",
-                 "b200_version", "b200_num_devices", "b200_set_pair_engine", "b200_set_i8_cta_group", "b200_get_i8_cta_group", "b200_set_i8_resident", "b200_get_i8_resident", "b200_last_pair_engine", "b200_debug_i8",
+                 "b200_version", "b200_num_devices", "b200_set_pair_engine", "b200_set_i8_cta_group", "b200_get_i8_cta_group", "b200_last_pair_engine", "b200_debug_i8",
                  "b200_set_mma_variant"):
         getattr(L, name).restype = i
     _lib = L
@@ -256,15 +255,6 @@ def set_i8_cta_group(cta_group):
 
 def get_i8_cta_group():
     return int(lib().b200_get_i8_cta_group())
-
-
-def set_i8_resident(on):
-    """CTA-pair kernel: keep the column operand resident in shared memory (default) or stream both operands."""
-    _check(lib().b200_set_i8_resident(int(bool(on))))
-
-
-def get_i8_resident():
-    return int(lib().b200_get_i8_resident())
 
 
 def last_pair_engine():

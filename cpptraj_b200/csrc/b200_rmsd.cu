@@ -369,30 +369,19 @@ int i8_cta_group() {
   return g_i8Cg;
 }
 
-// B-resident mode of the CTA-pair kernel (column operand kept in shared memory down a column of tiles):
-// default on; env B200_I8_RESIDENT=0 or b200_set_i8_resident(0) streams both operands instead.
-int g_i8Res = -1;
-int i8_resident() {
-  if (g_i8Res < 0) {
-    const char* e = getenv("B200_I8_RESIDENT");
-    g_i8Res = e ? (atoi(e) != 0) : 1;
-  }
-  return g_i8Res;
-}
-
-template <bool TRI, int CG, bool RES, bool DBG>
+template <bool TRI, int CG, bool DBG>
 int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
   static bool attr[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  constexpr int smem = i8_smem_bytes<CG, RES>();
+  constexpr int smem = i8_smem_bytes<CG>();
   if (!attr[dev & 63]) {
-    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG, RES, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr[dev & 63] = true;
   }
   COUNT_LAUNCH();
   if (CG == 1) {
-    pair_i8_kernel<TRI, CG, RES, DBG><<<grid, I8_THREADS, smem, st>>>(a);
+    pair_i8_kernel<TRI, CG, DBG><<<grid, I8_THREADS, smem, st>>>(a);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(I8_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -400,13 +389,13 @@ int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CG; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, pair_i8_kernel<TRI, CG, RES, DBG>, a));
+    CU(cudaLaunchKernelEx(&cfg, pair_i8_kernel<TRI, CG, DBG>, a));
   }
   CU(cudaGetLastError());
   return B200_OK;
 }
 
-template <int CG, bool RES>
+template <int CG>
 int run_pair_i8_band_t(const Device& d, PairI8Args& a, int rowLo, int rowHi, bool tri, cudaStream_t st) {
   a.it0 = rowLo / (I8_TILE_I * CG); a.it1 = (rowHi + I8_TILE_I * CG - 1) / (I8_TILE_I * CG);
   if (a.it1 <= a.it0 || a.jt1 <= a.jt0) return B200_OK;
@@ -414,20 +403,23 @@ int run_pair_i8_band_t(const Device& d, PairI8Args& a, int rowLo, int rowHi, boo
   if (nTiles <= 0) return B200_OK;
   if (nTiles > (1L << 30)) return fail(B200_ERR_ARG, "pair matrix too large for one launch (%ld tiles)", nTiles);
   const int groups = (d.numSMs > 0 ? d.numSMs : 148) / CG;   // persistent: one CTA per SM, CG CTAs per tile
-  // chunks of consecutive tiles (same column => same resident operand): every group gets k chunks of equal length
+  // chunks of consecutive tiles of the list: every group gets k chunks of equal length (env B200_I8_CHUNK = target
+  // chunk length; 1 = tile t to group t % groups)
   long L = 1;
-  if (RES) {
+  {
     const char* e = getenv("B200_I8_CHUNK");
-    const long target = e ? std::max(1, atoi(e)) : 32;
-    const long k = std::max<long>(1, (nTiles + groups * target / 2) / (groups * target));
-    L = (nTiles + groups * k - 1) / (groups * k);
+    const long target = e ? std::max(1, atoi(e)) : 1;
+    if (target > 1) {
+      const long k = std::max<long>(1, (nTiles + groups * target / 2) / (groups * target));
+      L = (nTiles + groups * k - 1) / (groups * k);
+    }
   }
   a.chunkLen = (int)L;
   const long nChunks = (nTiles + L - 1) / L;
   const int grid = (int)std::min<long>(nChunks, groups) * CG;
   const bool dbg = a.dbgMode != 0 || a.dbgClk != nullptr || a.dbgS != nullptr;
-  if (dbg) return tri ? launch_pair_i8_t<true, CG, RES, true>(a, grid, st) : launch_pair_i8_t<false, CG, RES, true>(a, grid, st);
-  return tri ? launch_pair_i8_t<true, CG, RES, false>(a, grid, st) : launch_pair_i8_t<false, CG, RES, false>(a, grid, st);
+  if (dbg) return tri ? launch_pair_i8_t<true, CG, true>(a, grid, st) : launch_pair_i8_t<false, CG, true>(a, grid, st);
+  return tri ? launch_pair_i8_t<true, CG, false>(a, grid, st) : launch_pair_i8_t<false, CG, false>(a, grid, st);
 }
 
 /// Rows [rowLo,rowHi) of the pair matrix through the tcgen05 int8 kernel (persistent, one CTA per SM).
@@ -443,9 +435,7 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
   { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
   a.dbgClk = g_dbgClk;
-  if (i8_cta_group() != 2) return run_pair_i8_band_t<1, false>(d, a, rowLo, rowHi, tri, st);
-  if (i8_resident() && a.nC <= I8_RES_MAX_C) return run_pair_i8_band_t<2, true>(d, a, rowLo, rowHi, tri, st);
-  return run_pair_i8_band_t<2, false>(d, a, rowLo, rowHi, tri, st);
+  return i8_cta_group() == 2 ? run_pair_i8_band_t<2>(d, a, rowLo, rowHi, tri, st) : run_pair_i8_band_t<1>(d, a, rowLo, rowHi, tri, st);
 }
 
 int shard_rows(int nFrames, int rank, int count, int* row0, int* row1) {
@@ -545,8 +535,11 @@ int dev_rms2d_tri(Device& d, const float* d_crd, size_t stride, const int* d_fra
   if ((rc = prepare_tri(d, d_crd, stride, d_frameIdx, srcBase, nFrames, d_atomIdx, nAtoms, d_mass, fit, row0, st, tpack, plan)))
     return rc;
   if (bandRows <= 0) bandRows = 512;
-  for (int i0 = row0; i0 < row1; i0 += bandRows) {
-    const int i1 = std::min(row1, i0 + bandRows);
+  // (one launch per shard was measured slower than 4096-row bands for the tcgen05 kernel: the row operands of a band,
+  //  ~37 MB at 1000 atoms, stay in L2 while the columns stream)
+  for (long i0l = row0; i0l < row1; i0l += bandRows) {
+    const int i0 = (int)i0l;
+    const int i1 = (int)std::min<long>(row1, i0l + bandRows);
     if (tpair) tpair->begin(st);
     if ((rc = run_tri_band(d, plan, i0, i1, fit != 0, d_out, outBase, st))) return rc;
     if (tpair) tpair->end(st);
@@ -631,9 +624,9 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   CU(cudaEventRecord(d.done[0], st0));
   for (int s = 1; s < NSLOT; ++s) CU(cudaStreamWaitEvent(d.stream[s], d.done[0], 0));
 
-  // band size: <= ~32 MB of output per band, multiple of 32 rows
+  // band size: <= ~64 MB of output per band, multiple of 32 rows
   const size_t F = (size_t)nFrames;
-  int bandRows = (int)std::min<size_t>(512, std::max<size_t>(ROWG, ((size_t)32 << 20) / (4 * F) / ROWG * ROWG));
+  int bandRows = (int)std::min<size_t>(2048, std::max<size_t>(ROWG, ((size_t)64 << 20) / (4 * F) / ROWG * ROWG));
   const bool pinnedOut = host_ptr_is_pinned(outTri);
   size_t maxChunk = 0;
   for (int i0 = row0; i0 < row1; i0 += bandRows) {
@@ -1220,8 +1213,6 @@ int b200_set_i8_cta_group(int ctaGroup) {
   return B200_OK;
 }
 int b200_get_i8_cta_group(void) { return i8_cta_group(); }
-int b200_set_i8_resident(int on) { g_i8Res = on ? 1 : 0; return B200_OK; }
-int b200_get_i8_resident(void) { return i8_resident(); }
 int b200_last_pair_engine(int* fractionalBits) {
   if (fractionalBits) *fractionalBits = g_lastQs.load();
   return g_lastEngine.load();

@@ -35,28 +35,21 @@ constexpr int I8_BLK_BYTES = 128 * I8_KC;    // 8192
 /// Pipeline geometry per MMA CTA group.  CG = 1: one CTA computes a 14 x 28 tile (M128 N256), a stage
 /// holds 64 atoms of A (1 block) and B (2 blocks).  CG = 2: a CTA pair computes a 28 x 28 tile
 /// (tcgen05.mma.cta_group::2, M256 N256); each CTA stages its own A row group and ONE of the two B row
-/// groups.  RES (CG 2 only, <= 1024 atoms): the CTA's B row group stays RESIDENT in shared memory while the
-/// pair walks down a column of tiles, so only A is streamed through the ring: 128 KB instead of 256 KB of
-/// L2 -> SM traffic per tile and CTA (the measured limiter of this kernel, see profiles/).
-template <int CG, bool RES> struct I8Geom;
-template <> struct I8Geom<1, false> {
+/// groups, so shared-memory fill, operand reads and L2 -> SM traffic per SM drop by a third and a stage holds
+/// 128 atoms (4 MMAs) in the same footprint.
+template <int CG> struct I8Geom;
+template <> struct I8Geom<1> {
   static constexpr int BPS = 1;      // 64-atom blocks per stage
-  static constexpr int STAGES = 8;
+  static constexpr int STAGES = 5;
   static constexpr int BBLK = 2;     // B blocks per 64 atoms held by this CTA
 };
-template <> struct I8Geom<2, false> {
-  static constexpr int BPS = 2;
-  static constexpr int STAGES = 6;
-  static constexpr int BBLK = 1;
-};
-template <> struct I8Geom<2, true> {
+template <> struct I8Geom<2> {
   static constexpr int BPS = 2;
   static constexpr int STAGES = 4;
-  static constexpr int BBLK = 0;     // B is not in the ring
+  static constexpr int BBLK = 1;
 };
-constexpr int I8_RES_MAX_C = 16;     // 64-atom chunks a resident B row group may have (128 KB)
-template <int CG, bool RES> __host__ __device__ constexpr int i8_stage_bytes() {
-  return I8Geom<CG, RES>::BPS * (1 + I8Geom<CG, RES>::BBLK) * I8_BLK_BYTES;
+template <int CG> __host__ __device__ constexpr int i8_stage_bytes() {
+  return I8Geom<CG>::BPS * (1 + I8Geom<CG>::BBLK) * I8_BLK_BYTES;
 }
 constexpr int I8_TILE_I = I8_FR_PER_RG;      // 14
 constexpr int I8_TILE_J = 2 * I8_FR_PER_RG;  // 28
@@ -323,25 +316,23 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Tiles are enumerated column tile by column tile (valid row tiles only); the list is cut into
 // chunks of `chunkLen` consecutive tiles, chunk c going to CTA group c % groups: every group gets
 // the same number of tiles (+-1), groups running at the same time work on neighbouring columns
-// (their A rows stay in L2), and consecutive tiles of a group share the column operand (RES).
+// (their A rows stay in L2).
 // ----------------------------------------------------------------------------
 constexpr int I8_DRAIN_WARPS = 8;            // two per TMEM sub-partition: one per column half of the tile
 constexpr int I8_SOLVE_WARPS = 14;
 constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 22
 constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 23
 constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 768
-constexpr int I8_XSLOTS = 44;                // 42 (frame, plane) triples + 2 partial-sum slots
-constexpr int I8_XJ_DBL = 3 * I8_XSLOTS + 1; // 133 doubles per column frame: odd => conflict-free LDS.64 / STS.64
-constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 29792
+constexpr int I8_XJ_DBL = 128 * 3 + 11;      // int64 per column frame: 3 per operand row + pad; odd => conflict-free LDS.64 / STS.64
+constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 88480
 constexpr int I8_MAX_STAGES = 8;
 constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 1;
-template <int CG, bool RES> __host__ __device__ constexpr int i8_smem_bytes() {
-  return I8Geom<CG, RES>::STAGES * i8_stage_bytes<CG, RES>() + (RES ? I8_RES_MAX_C * I8_BLK_BYTES : 0) + I8_XBUF_BYTES + 32 + 256;
+template <int CG> __host__ __device__ constexpr int i8_smem_bytes() {
+  return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 32 + 256;
 }
 static_assert(I8_NBARS * 8 + 8 <= 256, "barrier block");
 static_assert(I8_XBUF_BYTES % 32 == 0, "barrier alignment");
-static_assert(i8_smem_bytes<1, false>() <= 232448 && i8_smem_bytes<2, false>() <= 232448 && i8_smem_bytes<2, true>() <= 232448,
-              "shared memory budget");
+static_assert(i8_smem_bytes<1>() <= 232448 && i8_smem_bytes<2>() <= 232448, "shared memory budget");
 
 struct PairI8Args {
   const uint8_t* PA;   // operand images of the row frames (i)
@@ -444,15 +435,24 @@ __device__ __forceinline__ double i8_scale2(double v, int e) {
   const int nx = ex + e;
   return (ex == 0 || nx <= 0) ? 0.0 : __hiloint2double((hi & 0x800fffff) | (nx << 20), __double2loint(v));
 }
-/// Smallest non-negative root of Q, returned as r2 = y * unit (unit = 2/M in integer units).  In the variable
-/// y' = y / 2^k, 2^k <= E0 < 2^(k+1), the coefficients are O(1): the monotone approach from y' = 0 runs in FP32
-/// (resolves y' to ~1e-7 RELATIVE whatever its magnitude), ONE final Newton correction is FP64.  Returns false
-/// when the root is ill-conditioned or the correction is not small: the caller then takes the guarded FP64 path.
-__device__ __forceinline__ bool i8_root(const I8Quartic& c, double unit, double& r2) {
+/// State of a pair between the FP32 approach to the root (under MMAs) and its FP64 polish (next FP64 window).
+struct I8Pending {
+  double q0, q1, q2, q3;   // quartic in y' = y / 2^k (coefficients O(1)); leading coefficient 1
+  double unit;             // r2 = y' * unit  (unit = 2^k * 2/M in integer units); or the final r2 when `final`
+  float y, dq;             // FP32 root estimate and Q'(y)
+  bool final;              // the guarded FP64 path already produced r2 (ill-conditioned root)
+};
+/// FP32 part: exponent scaling on the integer pipe, monotone Newton approach from y' = 0 (resolves y' to ~1e-7
+/// RELATIVE whatever its magnitude).  Returns false when the root is ill-conditioned (|Q'| tiny relative to
+/// lambda^3, or E0 not a positive integer-scale value): the caller then takes the guarded FP64 path.
+__device__ __forceinline__ bool i8_root_start(const I8Quartic& c, double unit, I8Pending& pd) {
   const int k = ((__double2hiint(c.e0) >> 20) & 0x7ff) - 1023;
-  const double q0 = i8_scale2(c.q0, -4 * k), q1 = i8_scale2(c.q1, -3 * k), q2 = i8_scale2(c.q2, -2 * k);
-  const double q3 = -4.0 * i8_scale2(c.e0, -k);
-  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2, f3 = (float)q3;
+  pd.q0 = i8_scale2(c.q0, -4 * k); pd.q1 = i8_scale2(c.q1, -3 * k); pd.q2 = i8_scale2(c.q2, -2 * k);
+  const double x0 = i8_scale2(c.e0, -k);   // E0 / 2^k in [1, 2)
+  pd.q3 = -4.0 * x0;                       // (exact: power-of-two multiple)
+  pd.unit = i8_scale2(unit, k);
+  pd.final = false;
+  const float f0 = (float)pd.q0, f1 = (float)pd.q1, f2 = (float)pd.q2, f3 = (float)pd.q3;
   const float g3 = 3.f * f3, g2 = 2.f * f2;
   float y = 0.f, dq = f1, step;
 #pragma unroll
@@ -469,15 +469,27 @@ __device__ __forceinline__ bool i8_root(const I8Quartic& c, double unit, double&
     y -= step;
     if (!__any_sync(0xffffffffu, fabsf(step) > 4e-7f * fabsf(y))) break;
   }
-  double yd = (double)y;
-  const double Q = fma(fma(fma(yd + q3, yd, q2), yd, q1), yd, q0);
-  dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
-  const double d = Q * (double)__frcp_rn(dq);
+  pd.y = y;
+  pd.dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
+  const float xf = -0.25f * f3;
+  return (fabsf(pd.dq) >= 7e-3f * xf * xf * xf) && (k > 0) && (y < 3.f);
+}
+/// FP64 part (8 instructions): one Newton correction of the FP32 estimate; a few more, in FP64, in the rare case
+/// that the FP32 approach had not converged.  Returns r2 = (E0 - lambda_max) * 2/M.
+__device__ __forceinline__ double i8_root_finish(const I8Pending& pd) {
+  if (pd.final) return pd.unit;
+  double yd = (double)pd.y;
+  const double Q = fma(fma(fma(yd + pd.q3, yd, pd.q2), yd, pd.q1), yd, pd.q0);
+  double d = Q * (double)__frcp_rn(pd.dq);
   yd -= d;
-  r2 = yd * i8_scale2(unit, k);
-  // conditioning (|P'| relative to lambda^3 ~ 1 here) and size of the correction (FP32 left ~1e-7 relative)
-  const float x0 = -0.25f * f3;   // E0 / 2^k in [1, 2): lambda^3 scale of the derivative
-  return (fabsf(dq) >= 7e-3f * x0 * x0 * x0) && (fabs(d) <= 1e-5 * fabs(yd) + 1e-14) && (yd < 3.0) && (k > 0);
+#pragma unroll 1
+  for (int it = 0; it < 30 && fabs(d) > 1e-5 * fabs(yd) + 1e-14; ++it) {
+    const double Qn = fma(fma(fma(yd + pd.q3, yd, pd.q2), yd, pd.q1), yd, pd.q0);
+    const double dQ = fma(fma(fma(4.0, yd, 3.0 * pd.q3), yd, 2.0 * pd.q2), yd, pd.q1);
+    d = Qn / dQ;
+    yd -= d;
+  }
+  return yd * pd.unit;
 }
 /// Guarded FP64 path (Newton on the unscaled quartic, SVD for double roots); rarely taken.  The covariance
 /// travels BY VALUE: a pointer parameter would force the caller's S into local memory on every pair.
@@ -487,16 +499,14 @@ __device__ __noinline__ double i8_relative_gap_slow(double s0, double s1, double
   return (e0 > 0.0) ? (e0 - largest_root(quartic_of(S), e0, S)) / e0 : 0.0;
 }
 
-template <bool TRI, int CG, bool RES, bool DBG>
+template <bool TRI, int CG, bool DBG>
 __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
-  static_assert(!RES || CG == 2, "the resident column operand needs the CTA-pair geometry");
-  using GEO = I8Geom<CG, RES>;
+  using GEO = I8Geom<CG>;
   constexpr int STAGES = GEO::STAGES, BPS = GEO::BPS, BBLK = GEO::BBLK;
-  constexpr int STAGE_BYTES = i8_stage_bytes<CG, RES>();
+  constexpr int STAGE_BYTES = i8_stage_bytes<CG>();
   extern __shared__ __align__(1024) unsigned char smem_i8[];
   unsigned char* stages = smem_i8;
-  unsigned char* bres = smem_i8 + STAGES * STAGE_BYTES;                     // RES: this CTA's column row group, all chunks
-  unsigned char* xbufRaw = bres + (RES ? I8_RES_MAX_C * I8_BLK_BYTES : 0);
+  unsigned char* xbufRaw = smem_i8 + STAGES * STAGE_BYTES;
   long long* xbuf = reinterpret_cast<long long*>(xbufRaw);   // exchange buffer: exact int64 covariance entries
   uint64_t* bars = reinterpret_cast<uint64_t*>(xbufRaw + I8_XBUF_BYTES);
   uint64_t* fullBar = bars;                            // [STAGES]  operands landed (CG 2: in both CTAs, seen by the leader)
@@ -512,8 +522,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();   // 0 = leader (issues the MMAs)
   const int dbgMode = DBG ? a.dbgMode : 0;
   long long* const dbgClk = DBG ? a.dbgClk : nullptr;
-  // Ring depth.  RES: a resident chunk may be overwritten (next column) only after the previous tile's MMAs on it
-  // are done; waiting for the ring slot proves that when a tile has at least `depth` stages.
+  // Ring depth: short selections (fewer stages per tile than ring slots) use a shallower ring.
   const int stagesPerTile = (a.nC + BPS - 1) / BPS;
   const int depth = stagesPerTile < STAGES ? stagesPerTile : STAGES;
 
@@ -542,17 +551,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     // ===================== TMA producer (one thread per CTA) =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t stage0 = smem_u32(stages);
-    const uint32_t bres0 = smem_u32(bres);
     long long cwEmpty = 0;
-    int lastJt = -1;
     while (tiles.next(a, it, jt)) {
       // this CTA's A row group, and the B row group(s) it stages: both (CG 1) or the rank-th (CG 2)
       const int itA = (DBG && dbgMode == 4) ? a.it0 : it;   // timing experiment 4: every CTA streams the same A rows
       const uint8_t* gA = a.PA + (size_t)(CG * itA + (int)rank) * a.nC * I8_BLK_BYTES;
       const uint8_t* gB0 = a.PB + (size_t)(2 * jt + (CG == 2 ? (int)rank : 0)) * a.nC * I8_BLK_BYTES;
       const uint8_t* gB1 = gB0 + (size_t)a.nC * I8_BLK_BYTES;   // CG 1 only
-      const bool newCol = RES && (jt != lastJt);
-      lastJt = jt;
       for (int c = 0; c < a.nC; c += BPS) {
         const int nb = (a.nC - c < BPS) ? a.nC - c : BPS;
         const long long c0 = (DBG && dbgClk) ? clock64() : 0;
@@ -564,10 +569,6 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
           // the other lanes only keep the loop converged
         } else if (DBG && dbgMode == 3) {
           mbar_arrive(bar);
-        } else if constexpr (RES) {
-          mbar_expect_tx(bar, (uint32_t)(nb * I8_BLK_BYTES * (newCol ? 2 : 1)));
-          bulk_g2s(dst, gA + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
-          if (newCol) bulk_g2s(bres0 + (uint32_t)c * I8_BLK_BYTES, gB0 + (size_t)c * I8_BLK_BYTES, (uint32_t)(nb * I8_BLK_BYTES), bar);
         } else {
           mbar_expect_tx(bar, (uint32_t)(nb * (1 + BBLK) * I8_BLK_BYTES));
           // consecutive 64-atom blocks of one row group are contiguous in the image: one bulk copy per operand
@@ -594,9 +595,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     // descriptor = constant high part (LBO 128 B, SBO 512 B, version 1) | (smem address >> 4)
     constexpr uint64_t descHi = ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46);
     const uint32_t stage0 = smem_u32(stages);
-    const uint32_t bres0 = smem_u32(bres);
     int stage = 0; uint32_t phase = 0; int n = 0;
-    long long cwAcc = 0, cwFull = 0;
+    long long cwAcc = 0, cwFull = 0, cwFpd = 0;
     const long long cStart = (DBG && dbgClk) ? clock64() : 0;
     while (tiles.next(a, it, jt)) {
       const int b = n & 1;
@@ -604,8 +604,9 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       if constexpr (CG == 2) mbar_wait_cluster(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       else mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       // FP64 window: the solve warps finished the FP64 part of tile n-2 (they started it when tile n-1's MMAs completed)
-      if (n >= 2) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1));
-      if (DBG && dbgClk) cwAcc += clock64() - c0;
+      const long long cA = (DBG && dbgClk) ? clock64() : 0;
+      if (n >= 2 && !(DBG && dbgMode >= 2 && dbgMode <= 5)) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1));
+      if (DBG && dbgClk) { const long long c2 = clock64(); cwAcc += c2 - c0; cwFpd += c2 - cA; }
       tc_fence_after();
       const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
       for (int c = 0; c < a.nC; c += BPS) {
@@ -616,15 +617,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         if (DBG && dbgClk) cwFull += clock64() - c0;
         tc_fence_after();
         const uint32_t sA = stage0 + (uint32_t)stage * STAGE_BYTES;
-        const uint32_t sB = RES ? bres0 + (uint32_t)c * I8_BLK_BYTES : sA + BPS * I8_BLK_BYTES;
-        constexpr int BSTEP = RES ? 1 : BBLK;   // blocks between consecutive 64-atom chunks of B
+        const uint32_t sB = sA + BPS * I8_BLK_BYTES;
         if (elect_one()) {
         if (!(DBG && dbgMode == 5))   // timing experiment 5: operand pipeline without the MMAs
 #pragma unroll
         for (int cc = 0; cc < BPS; ++cc) {
           if (cc < nb) {
             const uint64_t dA = descHi | (uint64_t)(((sA + cc * I8_BLK_BYTES) >> 4) & 0x3fff);
-            const uint64_t dB = descHi | (uint64_t)(((sB + cc * BSTEP * I8_BLK_BYTES) >> 4) & 0x3fff);
+            const uint64_t dB = descHi | (uint64_t)(((sB + cc * BBLK * I8_BLK_BYTES) >> 4) & 0x3fff);
 #pragma unroll
             for (int k = 0; k < I8_KC / 32; ++k)   // one K=32 step = two 16-byte core matrices = 256 B further on
               umma_i8<CG>(dTmem, dA + (uint64_t)(k * 16), dB + (uint64_t)(k * 16), idesc, (uint32_t)((c | cc | k) != 0));
@@ -641,6 +641,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     if (DBG && dbgClk && lane == 0) {
       dbgClk[16 * blockIdx.x + 1] += cwAcc; dbgClk[16 * blockIdx.x + 2] += cwFull;
       dbgClk[16 * blockIdx.x + 3] += clock64() - cStart; dbgClk[16 * blockIdx.x + 4] += n;
+      dbgClk[16 * blockIdx.x + 14] += cwFpd;
     }
   } else if (warp == I8_WARP_MMA) {
     // ===================== CG 2, peer CTA: relay "my operand half has landed" to the leader =====================
@@ -660,37 +661,18 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
     const int hh = warp >> 2;         // column half of the tile: exchange groups 2*hh, 2*hh+1
     const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit = 3*triple + digit
-    const int dg = r % 3, trip = r / 3;
-    const int wshift = 8 * dg;        // A digit weight 256^dg of this operand row
-    // rows r+1 / r+2 join this lane's sum when they belong to the same triple AND the same warp
-    const bool take1 = (lane + 1 < 32) && ((r + 1) / 3 == trip);
-    const bool take2 = (lane + 2 < 32) && ((r + 2) / 3 == trip);
-    // writers: the head row of every triple (whole, or the head part of a straddling one) and lane 0 when it is
-    // the tail part of a straddling triple (row 32: triple 10 -> slot 42; row 64: triple 21 -> slot 43)
-    const bool writer = (r < 3 * 42) && (dg == 0 || lane == 0);
-    const int slot = (dg == 0) ? trip : (sp == 1 ? 42 : 43);
-    long long* xdst = xbuf + 3 * slot;
+    long long* xdst = xbuf + 3 * r;
     int n = 0;
     long long cwAcc = 0, cwX = 0, cwLd = 0, cwFold = 0;
     const long long cStart = (DBG && dbgClk) ? clock64() : 0;
-    // One column frame: 9 accumulators (q-major, B digit minor) -> 3 exact int64 sums over the B digits, weighted
-    // by the A digit of this row and folded over the three rows of the triple with two shuffles.  INTEGER ONLY:
-    // on this part FP64 instructions share the tensor pipe with tcgen05.mma and crawl (~10 % of their rate)
-    // while MMAs are in flight (tools/microbench/mma_fp64_mix.cu), so the drain must not touch the FP64 pipe.
+    // One column frame: 9 accumulators (q-major, B digit minor) -> 3 exact int64 sums over the B digits.  INTEGER
+    // ONLY: on this part FP64 instructions share the tensor pipe with tcgen05.mma and crawl (~10 % of their rate)
+    // while MMAs are in flight (tools/microbench/mma_fp64_mix.cu), so the drain must not touch the FP64 pipe; and
+    // no cross-lane work either: the A digits (three operand rows = three lanes) are folded by the solve threads.
     auto fold_frame = [&](const int* v, long long* dst) {
 #pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const long long x0 = ((long long)v[3 * q] + (long long)v[3 * q + 1] * 256 + (long long)v[3 * q + 2] * 65536) << wshift;
-        long long x1 = x0, x2 = x0;
-        if (!(DBG && dbgMode == 7)) {   // timing experiment 7: no shuffles
-          x1 = __shfl_down_sync(0xffffffffu, x0, 1);
-          x2 = __shfl_down_sync(0xffffffffu, x0, 2);
-        }
-        long long tot = x0;
-        if (take1) tot += x1;
-        if (take2) tot += x2;
-        if (writer) dst[q] = tot;
-      }
+      for (int q = 0; q < 3; ++q)
+        dst[q] = (long long)v[3 * q] + (long long)v[3 * q + 1] * 256 + (long long)v[3 * q + 2] * 65536;
     };
     while (tiles.next(a, it, jt)) {
       const int b = n & 1;
@@ -768,25 +750,21 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     const int jl = I8_TILE_I * h + (laneOn ? jlRaw : I8_TILE_I - 1);
     const double outScale = 2.0 * a.invScale2 / a.totalMass[0];   // rmsd^2 = (E0 - lambda) * outScale (integer units)
     const double halfToInt = 0.5 / a.invScale2;                    // G (A^2) -> integer units, halved (exact power of two)
-    const long long* src = xbuf + (size_t)jl * I8_XJ_DBL + 9 * il;    // [3*il + p][q], p-major: S[3p+q] directly
-    // straddling triples: 10 = (frame 3, plane 1) and 21 = (frame 7, plane 0) have a second partial sum
-    const long long* srcX = xbuf + (size_t)jl * I8_XJ_DBL + 3 * (il == 3 ? 42 : 43);
-    const int xOff = (il == 3) ? 3 : ((il == 7) ? 0 : -1);
+    const long long* src = xbuf + (size_t)jl * I8_XJ_DBL + 27 * il;   // [row 9*il + 3*p + digit][q]
     const bool solveOff = DBG && dbgMode >= 2 && dbgMode <= 5;
     const uint32_t fpDoneAddr = CG == 2 ? cluster_map(smem_u32(fpDone), 0) : smem_u32(fpDone);
     int n = 0;
-    long long cwX = 0, cwWin = 0;
+    long long cwX = 0, cwWin = 0, cwFp = 0, cwRoot = 0;
     const long long cStart = (DBG && dbgClk) ? clock64() : 0;
+    I8Pending pd;
+    bool pdLive = false, pdValid = false;
+    size_t pdIdx = 0;
+    pd.q0 = pd.q1 = pd.q2 = pd.q3 = pd.unit = 0.0; pd.y = pd.dq = 0.f; pd.final = true;
     int itN, jtN;
     bool have = tiles.next(a, it, jt);
     while (have) {
       const bool hasNext = tiles.next(a, itN, jtN);   // one tile of look-ahead: is there an MMA to wait for?
-      if (solveOff) {
-        __syncwarp();
-        if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr); }
-        ++n; it = itN; jt = jtN; have = hasNext;
-        continue;
-      }
+      if (solveOff) { ++n; it = itN; jt = jtN; have = hasNext; continue; }   // (the MMA warp does not wait for fpDone in these modes)
       const int i = I8_TILE_I * (CG * it + (int)rank) + il, j = I8_TILE_J * jt + jl;
       const bool valid = laneOn && i < a.nRows && j < a.nCols && i >= a.rowLo && i < a.rowHi && (!TRI || j > i);
       double ga = 0.5, gb = 0.5;
@@ -800,14 +778,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       if (!(DBG && dbgMode == 6)) {
         long long SI[9];
 #pragma unroll
-        for (int x = 0; x < 9; ++x) SI[x] = src[x];
-        if (xOff >= 0) {
+        for (int p = 0; p < 3; ++p)
 #pragma unroll
-          for (int q = 0; q < 3; ++q) {
-            const long long e = srcX[q];
-            if (xOff == 3) SI[3 + q] += e; else SI[q] += e;
-          }
-        }
+          for (int q = 0; q < 3; ++q)   // fold the A digits: exact int64 (|S| < 2^63 for < 131072 atoms)
+            SI[3 * p + q] = src[9 * p + q] + (src[9 * p + 3 + q] << 8) + (src[9 * p + 6 + q] << 16);
 #pragma unroll
         for (int x = 0; x < 9; ++x) S[x] = __ll2double_rn(SI[x]);   // I2F.F64.S64: XU pipe, not the FP64 pipe
       } else {
@@ -831,45 +805,55 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       //         every solve warp of the CTA (pair) has arrived on fpDone), do all the FP64 work, let the MMAs go on
       c0 = (DBG && dbgClk) ? clock64() : 0;
       if (hasNext) mbar_wait(smem_u32(&accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
+      const long long cF = (DBG && dbgClk) ? clock64() : 0;
       I8Quartic cq;
-      if (!(DBG && (dbgMode == 6 || dbgMode == 1 || dbgMode == 7 || dbgMode == 8))) {
-        cq = i8_coeffs(S, (ga + gb) * halfToInt);
-        asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2) : "memory");   // computed before the arrive below
+      double r2Prev = 0.0;
+      const bool plain = !(DBG && (dbgMode == 6 || dbgMode == 1 || dbgMode == 7 || dbgMode == 8));
+      if (plain) {
+        if (pdLive) r2Prev = i8_root_finish(pd);     // tile n-1: FP64 polish of the root found under the last MMAs
+        cq = i8_coeffs(S, (ga + gb) * halfToInt);    // tile n: everything that must be FP64
+        asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2), "d"(r2Prev) : "memory");   // computed before the arrive below
       } else {
         cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0;
       }
       __syncwarp();
       if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr); }
-      if (DBG && dbgClk) cwWin += clock64() - c0;
+      if (DBG && dbgClk) { const long long c2 = clock64(); cwWin += c2 - c0; cwFp += c2 - cF; }
       ++n;
-      // ---- 3. root and store (under the MMAs of tile n+2)
-      if (!(DBG && dbgMode == 6)) {
-        float rms;
-        if (DBG && (dbgMode == 1 || dbgMode == 7 || dbgMode == 8)) {
-          rms = (float)(S[0] + S[4] + S[8]);
-        } else {
-          double r2;
-          const bool ok = i8_root(cq, outScale, r2);
-          if (valid && !ok)
-            r2 = i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale);
-          // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
-          // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
-          rms = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
+      // ---- 3. store tile n-1, FP32 root search for tile n (under the MMAs of tile n+2; no FP64 instructions unless
+      //         the root is ill-conditioned)
+      const long long cR = (DBG && dbgClk) ? clock64() : 0;
+      if (plain) {
+        // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
+        // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
+        if (pdLive && pdValid) a.out[pdIdx] = (r2Prev > 0.0) ? sqrtf((float)r2Prev) : 0.f;
+        const bool ok = i8_root_start(cq, outScale, pd);
+        if (valid && !ok) {
+          pd.unit = i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale);
+          pd.final = true;
         }
+        pdLive = true; pdValid = valid;
+        if (TRI)
+          pdIdx = valid ? tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase : 0;
+        else
+          pdIdx = (size_t)i * a.ldo + (size_t)j;
+      } else if (!(DBG && dbgMode == 6)) {
         if (valid) {
-          size_t idx;
-          if (TRI)
-            idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
-          else
-            idx = (size_t)i * a.ldo + (size_t)j;
-          a.out[idx] = rms;
+          const size_t idx = TRI ? tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase
+                                 : (size_t)i * a.ldo + (size_t)j;
+          a.out[idx] = (float)(S[0] + S[4] + S[8]);
         }
       }
+      if (DBG && dbgClk) cwRoot += clock64() - cR;
       it = itN; jt = jtN; have = hasNext;
+    }
+    if (pdLive && pdValid) {   // the last tile's pairs (no MMAs in flight any more)
+      const double r2 = i8_root_finish(pd);
+      a.out[pdIdx] = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
     }
     if (DBG && dbgClk && lane == 0 && u == 0) {
       dbgClk[16 * blockIdx.x + 8] += cwX; dbgClk[16 * blockIdx.x + 9] += clock64() - cStart;
-      dbgClk[16 * blockIdx.x + 12] += cwWin;
+      dbgClk[16 * blockIdx.x + 12] += cwWin; dbgClk[16 * blockIdx.x + 13] += cwFp; dbgClk[16 * blockIdx.x + 15] += cwRoot;
     }
   }
   // ---- teardown ----

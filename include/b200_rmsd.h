@@ -169,10 +169,6 @@ int b200_set_pair_engine(int engine);
  * 28 x 28 frame-pair tiles; 1 = single-CTA MMAs, 14 x 28 tiles.  Same results; a tuning/test knob. */
 int b200_set_i8_cta_group(int ctaGroup);
 int b200_get_i8_cta_group(void);
-/* CTA-pair kernel, selections of <= 1024 atoms: keep the column operand of a tile RESIDENT in shared memory while
- * the pair walks down a column of tiles (default on; halves the L2 -> SM operand traffic).  Same results. */
-int b200_set_i8_resident(int on);
-int b200_get_i8_resident(void);
 /* Engine the last rms2d call used (1 or 2; 0 = none yet) and, for 2, the number of
  * fractional bits of its fixed-point grid. */
 int b200_last_pair_engine(int* fractionalBits);

@@ -47,20 +47,17 @@ def numpy_quant(crd, sel, mass, qs):
     return v, np.rint(v * 2.0 ** qs).astype(np.int64)
 
 
-MODES = [(2, 1), (2, 0), (1, 0)]
-MODE_IDS = ["cta_pair_resident", "cta_pair_streamed", "single_cta"]
+MODES = [2, 1]
+MODE_IDS = ["cta_pair", "single_cta"]
 
 
 @pytest.fixture(params=MODES, ids=MODE_IDS)
 def i8(b200, request):
-    """tcgen05 engine forced, in its three kernel modes: CTA pairs (tcgen05.mma.cta_group::2) with the column
-    operand resident in shared memory or streamed, and single-CTA MMAs."""
+    """tcgen05 engine forced, in both MMA CTA-group modes (tcgen05.mma.cta_group::2 pairs / ::1)."""
     b200.set_pair_engine("i8")
-    b200.set_i8_cta_group(request.param[0])
-    b200.set_i8_resident(request.param[1])
+    b200.set_i8_cta_group(request.param)
     yield b200
     b200.set_i8_cta_group(2)
-    b200.set_i8_resident(1)
     b200.set_pair_engine("auto")
 
 
@@ -93,13 +90,11 @@ def test_packed_image_and_G(b200, nf, na, use_mass):
 @pytest.mark.parametrize("nf,na", [(20, 64), (30, 70), (61, 200), (90, 130), (130, 1000)])
 def test_integer_covariance_is_exact(b200, nf, na, mode):
     c, m, sel = synth_case(11 + nf, nf, na)
-    b200.set_i8_cta_group(mode[0])
-    b200.set_i8_resident(mode[1])
+    b200.set_i8_cta_group(mode)
     try:
         r = b200.debug_i8(c, sel, mass=m[sel])
     finally:
         b200.set_i8_cta_group(2)
-        b200.set_i8_resident(1)
     q = decode_image(r["image"][: r["image_bytes"]], nf, na)
     S = np.einsum("iap,jaq->ijpq", q, q).reshape(nf, nf, 9)    # int64, exact (|q| < 2^23, na small)
     iu = np.triu_indices(nf, 1)

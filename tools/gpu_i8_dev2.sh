@@ -1,7 +1,7 @@
 #!/bin/bash
 # tcgen05 pair kernel dev loop: exactness + parity under short timeouts, then per-mode timings.
 # usage: tools/gpu_i8_dev2.sh TAG ["cg:res cg:res ..."] ["dbg modes"]
-TAG=${1:-dev}; COMBOS=${2:-"2:1 2:0 1:0"}; MODES=${3:-"0"}
+TAG=${1:-dev}; COMBOS=${2:-"2:0 1:0"}; MODES=${3:-"0"}
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_i8.py -x -q --timeout 120 -k "integer_cov or packed" > gpurun_out/dev_stage1_$TAG.log 2>&1
 rc=$?; echo "stage1 exit $rc" >> gpurun_out/dev_stage1_$TAG.log

@@ -33,7 +33,7 @@ if os.environ.get("B200_I8_CLOCKS"):
     buf = np.zeros((148, 16), np.int64)
     L.b200_debug_i8_clocks(buf.ctypes.data_as(C.c_void_p), 148)
     names = ["prod_wait_empty", "mma_wait_accEmpty", "mma_wait_full", "mma_total", "mma_tiles",
-             "drain_wait_accFull", "drain_wait_xEmpty", "drain_total", "solve_wait_xFull", "solve_total", "drain_tmem_ld", "drain_fold", "solve_window"]
+             "drain_wait_accFull", "drain_wait_xEmpty", "drain_total", "solve_wait_xFull", "solve_total", "drain_tmem_ld", "drain_fold", "solve_window", "solve_fp64", "mma_wait_fpDone", "solve_root"]
     # counters accumulate over the 3 band launches of one step (last launch overwrites: use sums per CTA of last launch only)
     # with CTA pairs the MMA counters exist on the leader CTAs only: average over the CTAs that counted
     for k, nm in enumerate(names):

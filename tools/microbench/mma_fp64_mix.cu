@@ -5,7 +5,7 @@
 #include <cstdio>
 #include "pair_i8.cuh"
 using namespace b200;
-__global__ void __launch_bounds__(768, 1) mix(int mmaOn, int iters, int nFp, int fpIters, long long* out, double* sink) {
+__global__ void __launch_bounds__(768, 1) mix(int mmaOn, int iters, int nFp, int fpIters, long long* out, double* sink, int ldOn) {
   extern __shared__ __align__(1024) unsigned char smem_pk[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmemSlot;
@@ -28,6 +28,17 @@ __global__ void __launch_bounds__(768, 1) mix(int mmaOn, int iters, int nFp, int
     mbar_wait(smem_u32(&bar), 0);
     tc_fence_after();
     out[2 * blockIdx.x] = clock64() - t0;
+  }
+  if (ldOn && warp < 4) {   // TMEM reads (tcgen05.ld 32x32b.x32) back to back on all four sub-partitions
+    int v[32]; int acc = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < ldOn; ++i) {
+      tmem_ld32(tmemBase + ((uint32_t)(32 * warp) << 16) + (uint32_t)((i & 7) * 32), v);
+      tmem_ld_wait();
+      acc += v[i & 31];
+    }
+    if (acc == 0x7fffffff) sink[tid] = acc;
+    if (tid == 32) out[2 * blockIdx.x] = clock64() - t0;
   }
   if (warp >= 4 && warp < 4 + nFp) {
     double x[8];
@@ -58,11 +69,20 @@ int main() {
     for (int nFp : {0, 4, 8, 16, 20}) {
       if (!mmaOn && !nFp) continue;
       cudaMemset(out, 0, 148 * 16);
-      mix<<<148, 768, smem>>>(mmaOn, iters, nFp, fpIters, out, sink);
+      mix<<<148, 768, smem>>>(mmaOn, iters, nFp, fpIters, out, sink, 0);
       if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
       long long h[296]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
       double m = 0, f = 0; for (int i = 0; i < 148; ++i) { m += h[2 * i]; f += h[2 * i + 1]; } m /= 148; f /= 148;
       printf("%5d %4d | %12.0f %14.1f | %12.0f %16.1f\n", mmaOn, nFp, m, m / iters, f, f > 0 ? (double)nFp * 32 * 8 * fpIters / f : 0.0);
     }
+  printf("--- FP64 under TMEM reads only (no MMAs): ld iterations 20000\n");
+  for (int nFp : {4, 16}) {
+    cudaMemset(out, 0, 148 * 16);
+    mix<<<148, 768, smem>>>(0, iters, nFp, fpIters, out, sink, 20000);
+    if (cudaDeviceSynchronize() != cudaSuccess) { printf("error %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
+    long long h[296]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+    double m = 0, f = 0; for (int i = 0; i < 148; ++i) { m += h[2 * i]; f += h[2 * i + 1]; } m /= 148; f /= 148;
+    printf("ld cycles %12.0f (%.1f per x32 load) | nFp %2d fp cycles %12.0f  DFMA lanes/clk/SM %.1f\n", m, m / 20000, nFp, f, (double)nFp * 32 * 8 * fpIters / f);
+  }
   return 0;
 }
