@@ -302,7 +302,7 @@ def main():
             r.update({"peak": peak, "frac": achieved / peak if peak > 0 else None,
                       "executed": executed, "frac_executed": executed / peak if peak > 0 else None,
                       "kernel": ("pair_i8_kernel<tri, CG=2> (tcgen05.mma.cta_group::2 kind::i8 M256 N256 K32 on CTA pairs, int32 "
-                                 "accumulators in TMEM, 28x28 frame-pair tiles, fused FP64 solve)" if b.get_i8_cta_group() == 2 else
+                                 "accumulators in TMEM, 28x28 frame-pair tiles, int64 digit fold + fused per-pair solve)" if b.get_i8_cta_group() == 2 else
                                  "pair_i8_kernel<tri, CG=1> (tcgen05.mma kind::i8 M128 N256 K32, int32 accumulators in TMEM, "
                                  "14x28 frame-pair tiles, fused FP64 solve)"),
                       "cta_group": b.get_i8_cta_group(),

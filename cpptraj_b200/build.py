@@ -28,7 +28,8 @@ def stale():
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT] + SRC
+    extra = os.environ.get("B200_NVCC_EXTRA", "").split()
+    cmd = [NVCC] + FLAGS + extra + ["-o", OUT] + SRC
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout)

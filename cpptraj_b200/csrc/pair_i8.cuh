@@ -7,8 +7,8 @@
 //   * every integer is split into three balanced signed base-256 digits (int8),
 //   * the nine covariance entries of a frame pair are 81 int8 x int8 dot products over the atoms,
 //     computed by tcgen05.mma kind::i8 with int32 accumulators in TMEM (exact for < 131072 atoms),
-//   * the epilogue recombines the digits in integer/FP64 arithmetic (S and G carry < 2^-52
-//     relative error), and runs the same FP64 per-pair solve as the FP64 DMMA path.
+//   * the epilogue recombines the digits in exact int64 arithmetic (S is exact below 2^63, converted to
+//     FP64 once; G carries < 2^-52 relative error), then solves the key-matrix quartic per pair.
 // The cancellation E0 - lambda that defeats fp32/TF32 accumulation never
 // sees a rounding error larger than FP64's.  Replaces, like pair_kernel, the covariance loop of
 // Frame::RMSD_CenteredRef (src/Frame.cpp:1184-1208) + the eigen-solve (src/Frame.cpp:1215-1268).
@@ -21,8 +21,9 @@
 //   one K step, SBO = 512 B between 8-row groups.  Blocks are ordered [g][c], so an A operand
 //   stage (one row group, 64 atoms) is one contiguous 8 KB bulk copy and a B operand stage (two
 //   consecutive row groups = 28 frames = N 256) is two of them.
-// One MMA tile = 14 x 28 frame pairs = D[128 x 256] int32 = 256 TMEM columns; two accumulator
-// buffers fill the 512 columns, so the epilogue of tile n overlaps the MMAs of tile n+1.
+// One MMA tile = 14 x 28 frame pairs per CTA = D[128 x 256] int32 = 256 TMEM columns (a CTA pair computes
+// 28 x 28 with tcgen05.mma.cta_group::2); two accumulator buffers fill the 512 columns, so the epilogue of
+// tile n overlaps the MMAs of tile n+1.
 #pragma once
 #include "rmsd_kernels.cuh"
 
@@ -295,34 +296,42 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // ----------------------------------------------------------------------------
 // pair_i8_kernel
 //
-// Persistent, warp-specialised, one CTA per SM.  Roles (24 warps):
-//   warp 22       TMA producer: operand stages through a full/empty mbarrier ring
-//   warp 23       MMA issuer: tcgen05.mma kind::i8 K32 into one of two TMEM accumulators
-//                 (CG 2: the leader CTA issues for the pair; the peer's warp 23 relays "landed")
-//   warps 0..7    drain: two per TMEM sub-partition (one per column half of the tile); tcgen05.ld the
-//                 accumulator columns of 7 column frames (x 9) in three pieces, fold the three B digits in-thread (exact int64), apply the A digit
-//                 weight of the own operand row, fold the three A digits across the three lanes of
-//                 a (frame, plane) triple with two shuffles, hand 3 doubles per (triple, column
-//                 frame) to the exchange buffer
-//   warps 8..21   solve: one thread per frame pair (2 row frames x 14 column frames per warp):
-//                 read the 9 covariance entries of the pair, per-pair solve, store the float
-//                 straight into cpptraj's Matrix<float> layout
-// 128 rows = 42 triples + 2 padding rows, and 32 is no multiple of 3: triples 10 (rows 30..32) and
-// 21 (rows 63..65) straddle two drain warps.  Their tail lanes write a partial sum to two extra
-// slots which the solve threads of row frames 3 and 7 add.
-// The exchange buffer is a ring of four column groups (7 column frames each) with its own
-// full/empty mbarriers, so the drain of tile n+1 runs under the solve of tile n, both under the
-// MMAs of tile n+2: no CTA-wide barrier anywhere in the steady state.
+// Persistent, warp-specialised, one CTA per SM.  Roles (20 warps; warp w runs on SM sub-partition w % 4):
+//   warps 0..3    drain: one per TMEM sub-partition.  Per exchange group (7 column frames x 9 accumulator
+//                 columns, fetched with three tcgen05.ld) fold the three B digits of every (row, column
+//                 frame, plane) in-thread -- exact int64, integer pipe only -- and hand 3 int64 per operand
+//                 row and column frame to the exchange buffer
+//   warps 4..17   solve: one thread per frame pair (2 row frames x 14 column frames per warp): read the 27
+//                 partial sums of the pair, fold the three A digits (exact int64), convert once to FP64,
+//                 quartic coefficients in FP64 inside the FP64 window, FP32 Newton approach to the root under
+//                 the next MMAs, FP64 polish in the next window, float store straight into cpptraj's
+//                 Matrix<float> layout
+//   warp 18       TMA producer: operand stages through a full/empty mbarrier ring (whole warp loops so that
+//                 addresses stay in uniform registers; one elected lane issues)
+//   warp 19       MMA issuer: tcgen05.mma kind::i8 K32 into one of two TMEM accumulators, same elect scheme
+//                 (CG 2: the leader CTA issues for the pair; the peer's warp 19 relays "landed")
+// FP64 window: on this part FP64 instructions share the tensor pipe with tcgen05.mma and run at ~10 % of their
+// rate while MMAs are in flight (profiles/r1c_microbench_fp64_under_mma.txt).  The solve warps therefore do
+// all their FP64 work in a window that opens when the MMAs of tile n+1 have completed (accFull) and closes
+// when every solve warp of the CTA (pair) has arrived on fpDone; the MMA warp issues tile n+2 only then.
+// The exchange buffer is a ring of four column groups (7 column frames each) with its own full/empty
+// mbarriers, so the drain of tile n+1 runs under the solve of tile n, both under the MMAs of tile n+2: no
+// CTA-wide barrier anywhere in the steady state.
 // Tiles are enumerated column tile by column tile (valid row tiles only); the list is cut into
 // chunks of `chunkLen` consecutive tiles, chunk c going to CTA group c % groups: every group gets
 // the same number of tiles (+-1), groups running at the same time work on neighbouring columns
 // (their A rows stay in L2).
 // ----------------------------------------------------------------------------
-constexpr int I8_DRAIN_WARPS = 8;            // two per TMEM sub-partition: one per column half of the tile
+#ifndef B200_I8_DRAIN_WARPS
+#define B200_I8_DRAIN_WARPS 4   // measured: 4 (640 threads, 96 registers, no spills) beats 8 (768 threads, 80 registers)
+#endif
+constexpr int I8_DRAIN_WARPS = B200_I8_DRAIN_WARPS;   // 4 or 8: one or two per TMEM sub-partition (8: one per column half of the tile)
+static_assert(I8_DRAIN_WARPS == 4 || I8_DRAIN_WARPS == 8, "drain warps");
+constexpr int I8_GROUPS_PER_DRAIN_WARP = 16 / I8_DRAIN_WARPS;
 constexpr int I8_SOLVE_WARPS = 14;
-constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 22
-constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 23
-constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 768
+constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 18
+constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 19
+constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
 constexpr int I8_XJ_DBL = 128 * 3 + 11;      // int64 per column frame: 3 per operand row + pad; odd => conflict-free LDS.64 / STS.64
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 88480
 constexpr int I8_MAX_STAGES = 8;
@@ -533,7 +542,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       mbar_init(smem_u32(&emptyBar[s]), 1);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS * CG); }
-    for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), I8_DRAIN_WARPS / 2); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
+    for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), 4); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
     mbar_init(smem_u32(fpDone), I8_SOLVE_WARPS * CG);
     mbar_fence_init();
   }
@@ -659,7 +668,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   } else if (warp < I8_DRAIN_WARPS) {
     // ===================== drain warps =====================
     const int sp = warp & 3;          // TMEM sub-partition: lanes 32*sp .. 32*sp+31
-    const int hh = warp >> 2;         // column half of the tile: exchange groups 2*hh, 2*hh+1
+    const int hh = warp >> 2;         // 8 drain warps: column half of the tile (exchange groups 2*hh, 2*hh+1); 4: all groups
     const int r = 32 * sp + lane;     // operand row of this thread: 9*i + 3*p + digit = 3*triple + digit
     long long* xdst = xbuf + 3 * r;
     int n = 0;
@@ -691,10 +700,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         continue;
       }
 #pragma unroll 1
-      for (int gg = 0; gg < 2; ++gg) {
-        const int g = 2 * hh + gg;
+      for (int gg = 0; gg < I8_GROUPS_PER_DRAIN_WARP; ++gg) {
+        const int g = I8_GROUPS_PER_DRAIN_WARP * hh + gg;
         // column frames 7g .. 7g+6: accumulator columns 9*jl (frames 0..13) or 128 + 9*(jl-14) (frames 14..27)
-        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + hh * 128 + gg * 63) + ((uint32_t)(32 * sp) << 16);
+        const uint32_t tcol = tmemBase + (uint32_t)(b * 256 + (g >> 1) * 128 + (g & 1) * 63) + ((uint32_t)(32 * sp) << 16);
         long long* dst = xdst + (size_t)(7 * g) * I8_XJ_DBL;
         int v[32];
         long long c1 = (DBG && dbgClk) ? clock64() : 0;
@@ -720,7 +729,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         if (!(DBG && dbgMode == 8)) tmem_ld16(tcol + 47, v);                // columns 47..62: frame 6 is the last 9 (stays inside the accumulator)
         tmem_ld_wait();
         if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
-        if (gg == 1) {   // this warp is done reading accumulator buffer b
+        if (gg == I8_GROUPS_PER_DRAIN_WARP - 1) {   // this warp is done reading accumulator buffer b
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
