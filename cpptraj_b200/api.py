@@ -4,7 +4,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200rmsd.so")
+LIB_PATH = os.environ.get("B200_RMSD_LIB") or os.path.join(_HERE, "libb200rmsd.so")   # (override: kernel A/B experiments)
 
 ERRORS = {1: "B200_ERR_NO_DEVICE", 2: "B200_ERR_CUDA", 3: "B200_ERR_ARG", 4: "B200_ERR_NOMEM", 5: "B200_ERR_STATE"}
 

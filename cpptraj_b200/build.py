@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "b200_rmsd.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith((".cuh", ".h"))] + [
     os.path.join(os.path.dirname(HERE), "include", "b200_rmsd.h")]
-OUT = os.path.join(HERE, "libb200rmsd.so")
+OUT = os.environ.get("B200_RMSD_LIB_OUT") or os.path.join(HERE, "libb200rmsd.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-cudart", "static",

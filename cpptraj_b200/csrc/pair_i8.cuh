@@ -44,9 +44,13 @@ template <> struct I8Geom<1> {
   static constexpr int STAGES = 5;
   static constexpr int BBLK = 2;     // B blocks per 64 atoms held by this CTA
 };
+#ifndef B200_I8_CG2_BPS
+#define B200_I8_CG2_BPS 2
+#define B200_I8_CG2_STAGES 4
+#endif
 template <> struct I8Geom<2> {
-  static constexpr int BPS = 2;
-  static constexpr int STAGES = 4;
+  static constexpr int BPS = B200_I8_CG2_BPS;
+  static constexpr int STAGES = B200_I8_CG2_STAGES;
   static constexpr int BBLK = 1;
 };
 template <int CG> __host__ __device__ constexpr int i8_stage_bytes() {
