@@ -3,7 +3,7 @@
 // Idea ("exact integer covariance"): best-fit RMSD is 1-Lipschitz in the RMS coordinate
 // perturbation, so the centred, sqrt(mass)-scaled coordinates are rounded ONCE per frame to a
 // fixed-point grid of spacing 2^-qs (24-bit signed integers; qs chosen from the largest centred
-// coordinate so the worst-case RMSD change stays < 5.3e-5 A) and from then on everything is exact:
+// coordinate so the worst-case RMSD change stays < 8.5e-5 A) and from then on everything is exact:
 //   * every integer is split into three balanced signed base-256 digits (int8),
 //   * the nine covariance entries of a frame pair are 81 int8 x int8 dot products over the atoms,
 //     computed by tcgen05.mma kind::i8 with int32 accumulators in TMEM (exact for < 131072 atoms),

@@ -161,7 +161,7 @@ void b200_get_stats(b200_stats* out);
  *   2 = tcgen05 int8 tensor cores on coordinates rounded once per frame to a 24-bit
  *       fixed-point grid (exact integer covariance in TMEM), fit only, used when the
  *       selection's extent leaves enough fractional bits for a worst-case RMSD change
- *       < 5.3e-5 A;
+ *       < 8.5e-5 A;
  *   0 = automatic (2 when eligible, else 1) -- the default; env B200_PAIR_ENGINE.
  * Forcing 2 on an ineligible call fails with B200_ERR_ARG. */
 int b200_set_pair_engine(int engine);
