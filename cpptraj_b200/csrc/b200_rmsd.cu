@@ -958,7 +958,7 @@ struct b200_1vN {
   Device* dev = nullptr;
   int nAtoms = 0, fit = 1, wantRot = 0;
   std::vector<int> atomIdx;
-  DevBuf refw, refsum, idx, in[NSLOT], rms, rot, trans;
+  DevBuf refw, refsum, idx, in[NSLOT], rms, rot, trans, ws;
   PinBuf stage[NSLOT];
   cudaStream_t st = nullptr;         // single in-order stream (+ events for slot reuse)
   cudaEvent_t slotFree[NSLOT] = {nullptr, nullptr, nullptr};
@@ -993,20 +993,66 @@ static int onevn_grow(b200_1vN* h, long need) {
   return B200_OK;
 }
 
+/// Launches the one-vs-many kernels for `nFrames` frames at d_crd on stream st: chunk table, TMA streaming kernel +
+/// per-frame finish (sorted selections, 16-byte aligned base), then the general gather kernel, which returns at once
+/// when the streaming variant did the work (the choice is made on the device: no host round trip).
+/// ws: workspace of at least onevn_ws_bytes() bytes.
+static size_t onevn_ws_bytes(size_t stride, int nFrames) {
+  const size_t maxChunks = stride / 3 / (ONEVN_S_CHUNK_BYTES / 24) + 2;
+  return 64 + (maxChunks + 1) * sizeof(int) + 64 + (size_t)nFrames * ONEVN_REC * sizeof(double);
+}
+template <typename T>
+static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, int nAtoms,
+                     const double* refw, const double* refsum, int fit, double* rmsd, double* rot, double* trans,
+                     void* ws, cudaStream_t st) {
+  constexpr int APC = ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));
+  const int maxChunks = (int)std::min<size_t>(stride / 3 / APC + 2, 1u << 20);
+  int* hdr = (int*)ws;
+  int* kLo = hdr + 16;
+  double* rec = (double*)((char*)ws + ((64 + (size_t)(maxChunks + 1) * sizeof(int) + 63) & ~(size_t)63));
+  const bool aligned = (((uintptr_t)d_crd) & 15) == 0;
+  const char* env = getenv("B200_1VN_STREAM");
+  const bool stream = aligned && !(env && atoi(env) == 0);
+  if (stream) {
+    static bool attr[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr[dev & 63][sizeof(T) == 8]) {
+      CU(cudaFuncSetAttribute(onevn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONEVN_S_SMEM_BYTES));
+      attr[dev & 63][sizeof(T) == 8] = true;
+    }
+    COUNT_LAUNCH();
+    onevn_chunks_kernel<<<1, 256, 0, st>>>(d_atomIdx, nAtoms, APC, maxChunks, hdr, kLo);
+    OneVNStreamArgs sa;
+    sa.crd = d_crd; sa.stride = stride; sa.nFrames = nFrames; sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms;
+    sa.refw = refw; sa.hdr = hdr; sa.kLo = kLo; sa.fit = fit; sa.rec = rec;
+    const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
+    COUNT_LAUNCH();
+    onevn_stream_kernel<T><<<std::min(nGroups, numSMs > 0 ? numSMs : 148), ONEVN_THREADS, ONEVN_S_SMEM_BYTES, st>>>(sa);
+    COUNT_LAUNCH();
+    onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
+  }
+  OneVNArgs a;
+  a.crd = d_crd; a.stride = stride; a.nFrames = nFrames; a.atomIdx = d_atomIdx; a.nAtoms = nAtoms;
+  a.refw = refw; a.refsum = refsum; a.skipIf = stream ? hdr : nullptr; a.fit = fit;
+  a.rmsd = rmsd; a.rot = rot; a.trans = trans;
+  COUNT_LAUNCH();
+  onevn_kernel<T><<<(nFrames + ONEVN_FB - 1) / ONEVN_FB, ONEVN_THREADS, 0, st>>>(a);
+  CU(cudaGetLastError());
+  return B200_OK;
+}
+
 template <typename T>
 static int onevn_launch(b200_1vN* h, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, long outOffset) {
-  OneVNArgs a;
-  a.crd = d_crd; a.stride = stride; a.nFrames = nFrames; a.atomIdx = d_atomIdx; a.nAtoms = h->nAtoms;
-  a.refw = (const double*)h->refw.p; a.refsum = (const double*)h->refsum.p; a.fit = h->fit;
-  a.rmsd = (double*)h->rms.p + outOffset;
-  a.rot = h->wantRot ? (double*)h->rot.p + 9 * outOffset : nullptr;
-  a.trans = h->wantRot ? (double*)h->trans.p + 3 * outOffset : nullptr;
-  const int grid = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
+  int rc;
+  if ((rc = h->ws.reserve(onevn_ws_bytes(stride, nFrames)))) return rc;
   h->timer.begin(h->st);
-  COUNT_LAUNCH();
-  onevn_kernel<T><<<grid, ONEVN_THREADS, 0, h->st>>>(a);
+  rc = onevn_run<T>(h->dev->numSMs, d_crd, stride, nFrames, d_atomIdx, h->nAtoms, (const double*)h->refw.p,
+                    (const double*)h->refsum.p, h->fit, (double*)h->rms.p + outOffset,
+                    h->wantRot ? (double*)h->rot.p + 9 * outOffset : nullptr,
+                    h->wantRot ? (double*)h->trans.p + 3 * outOffset : nullptr, h->ws.p, h->st);
   h->timer.end(h->st);
-  CU(cudaGetLastError());
+  if (rc) return rc;
   h->launches++;
   return B200_OK;
 }
@@ -1143,7 +1189,7 @@ int b200_rmsd_1vN_end(b200_1vN* h) {
   cudaSetDevice(h->dev->id);
   if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
   for (int s = 0; s < NSLOT; ++s) { if (h->slotFree[s]) cudaEventDestroy(h->slotFree[s]); h->in[s].release(); h->stage[s].release(); }
-  h->refw.release(); h->refsum.release(); h->idx.release(); h->rms.release(); h->rot.release(); h->trans.release();
+  h->refw.release(); h->refsum.release(); h->idx.release(); h->rms.release(); h->rot.release(); h->trans.release(); h->ws.release();
   h->timer.resolve();
   delete h;
   return B200_OK;
@@ -1163,21 +1209,18 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   for (auto& x : g_devs) if (x.id == dev) d = &x;
   if (!d) return fail(B200_ERR_STATE, "current device %d was not initialised by b200_init", dev);
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = d->onevnWs.reserve((size_t)nAtoms * 32 + 64))) return rc;
+  const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
+  if ((rc = d->onevnWs.reserve(refBytes + onevn_ws_bytes(frameStrideFloats, nFrames)))) return rc;
   double* refw = (double*)d->onevnWs.p;
   double* refsum = refw + (size_t)4 * nAtoms;
   COUNT_LAUNCH();
   onevn_setup_kernel<<<1, 32, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum);
-  OneVNArgs a;
-  a.crd = d_crd; a.stride = frameStrideFloats; a.nFrames = nFrames; a.atomIdx = d_atomIdx; a.nAtoms = nAtoms;
-  a.refw = refw; a.refsum = refsum; a.fit = fit ? 1 : 0; a.rmsd = d_rmsdOut;
-  a.rot = fit ? d_rotOut : nullptr; a.trans = fit ? d_transOut : nullptr;
   Timer t;
   if (g_profiling) t.begin(st);
-  COUNT_LAUNCH();
-  onevn_kernel<float><<<(nFrames + ONEVN_FB - 1) / ONEVN_FB, ONEVN_THREADS, 0, st>>>(a);
+  rc = onevn_run<float>(d->numSMs, d_crd, frameStrideFloats, nFrames, d_atomIdx, nAtoms, refw, refsum, fit ? 1 : 0, d_rmsdOut,
+                        fit ? d_rotOut : nullptr, fit ? d_transOut : nullptr, (char*)d->onevnWs.p + refBytes, st);
   if (g_profiling) t.end(st);
-  CU(cudaGetLastError());
+  if (rc) return rc;
   if (g_profiling) {
     CU(cudaStreamSynchronize(st));
     const double ms = t.resolve();

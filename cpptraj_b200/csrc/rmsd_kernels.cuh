@@ -533,6 +533,7 @@ struct OneVNArgs {
   int nAtoms;
   const double* refw;       // 4 doubles per atom: rx, ry, rz, m   (ref as given)
   const double* refsum;     // [0..2] = sum m r, [3] = M, [4] = sum m |r|^2
+  const int* skipIf;        // nullable: hdr of the streaming variant; [2] != 0 => that variant did the work
   int fit;
   double* rmsd;
   double* rot;              // nullable, 9 per frame
@@ -587,6 +588,7 @@ __device__ inline void rotation_from_cov(const double* S, double lam, double* U)
 template <typename T>
 __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
   __shared__ double red[ONEVN_THREADS / 32][ONEVN_FB][14];
+  if (a.skipIf && a.skipIf[2] != 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fbase = blockIdx.x * ONEVN_FB;
   const T* crd = reinterpret_cast<const T*>(a.crd);
@@ -671,6 +673,245 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
         }
       }
     }
+  }
+}
+
+// ----------------------------------------------------------------------------
+// One-vs-many, streaming variant (the HBM-bound path of Action_Rmsd::DoAction, src/Action_Rmsd.cpp:361-417).
+// Frames are contiguous rows of COORDS, so the span of a frame that holds the selected atoms is moved by the
+// TMA engine (cp.async.bulk, SASS UBLKCP) into a 2-stage shared-memory ring -- 4 frames x 12 KB plus the chunk's
+// reference atoms (32 KB) and atom numbers per stage -- one thread issuing the next stage while the 256 threads work
+// on the current one: every operand of the inner loop comes from shared memory (ncu: the L2 latency of the
+// reference / index loads was the top stall when they were ordinary loads).
+// The 256 threads gather the selected atoms of the staged chunk from shared memory (conflict-free: consecutive
+// atoms are 12 or 24 bytes apart), accumulate the same 13 FP64 sums per frame as onevn_kernel and write them
+// (plus the frame's origin shift) to a 16-double record per frame; onevn_finish_kernel (one thread per frame)
+// does the per-frame solve, rotation and translation.  Needs a sorted selection (AtomMask::Selected() is) and a
+// 16-byte aligned COORDS base; the host checks the alignment, the device the order (hdr[2]), and onevn_kernel
+// remains the general path.
+// ----------------------------------------------------------------------------
+constexpr int ONEVN_S_STAGES = 2;
+constexpr int ONEVN_S_CHUNK_BYTES = 12288;                       // per frame and stage
+constexpr int ONEVN_S_BUF_BYTES = ONEVN_S_CHUNK_BYTES + 32;      // + alignment slack at both ends
+constexpr int ONEVN_S_MAX_APC = ONEVN_S_CHUNK_BYTES / 12;        // selected atoms a chunk can hold (float frames)
+constexpr int ONEVN_S_REF_OFF = ONEVN_FB * ONEVN_S_BUF_BYTES;    // reference (rx, ry, rz, m) of the chunk's selected atoms
+constexpr int ONEVN_S_IDX_OFF = ONEVN_S_REF_OFF + ONEVN_S_MAX_APC * 32;   // their atom numbers
+constexpr int ONEVN_S_STAGE_BYTES = ONEVN_S_IDX_OFF + ONEVN_S_MAX_APC * 4 + 32;
+constexpr int ONEVN_S_SMEM_BYTES = ONEVN_S_STAGES * ONEVN_S_STAGE_BYTES + 64;
+constexpr int ONEVN_REC = 16;                                    // doubles per frame record: 13 sums + origin
+
+struct OneVNStreamArgs {
+  const void* crd;
+  size_t stride;            // elements per frame
+  int nFrames;
+  const int* atomIdx;       // nullable (identity)
+  int nAtoms;
+  const double* refw;       // 4 doubles per selected atom: rx, ry, rz, m
+  const int* hdr;           // [0] first atom of the span, [1] chunks per frame, [2] 1 = selection sorted (usable)
+  const int* kLo;           // [chunks + 1]: first selected-atom index of every chunk
+  int fit;
+  double* rec;              // ONEVN_REC doubles per frame
+};
+
+/// Chunk table of the streaming kernel.  One block.  atomsPerChunk = ONEVN_S_CHUNK_BYTES / (3 * sizeof(T)).
+__global__ void __launch_bounds__(256) onevn_chunks_kernel(const int* atomIdx, int nAtoms, int atomsPerChunk, int maxChunks,
+                                                           int* hdr, int* kLo) {
+  __shared__ int sMin, sMax, sSorted;
+  if (threadIdx.x == 0) { sMin = 0x7fffffff; sMax = -1; sSorted = 1; }
+  __syncthreads();
+  int mn = 0x7fffffff, mx = -1, ok = 1;
+  for (int k = threadIdx.x; k < nAtoms; k += blockDim.x) {
+    const int a = atomIdx ? atomIdx[k] : k;
+    mn = min(mn, a); mx = max(mx, a);
+    if (k + 1 < nAtoms && atomIdx && atomIdx[k + 1] <= a) ok = 0;
+  }
+  atomicMin(&sMin, mn); atomicMax(&sMax, mx);
+  if (!ok) atomicAnd(&sSorted, 0);
+  __syncthreads();
+  const int a0 = sMin;
+  const int nCh = (sMax - sMin) / atomsPerChunk + 1;
+  const bool usable = sSorted && nCh <= maxChunks;
+  if (threadIdx.x == 0) { hdr[0] = a0; hdr[1] = usable ? nCh : 0; hdr[2] = usable ? 1 : 0; }
+  if (!usable) return;
+  for (int c = threadIdx.x; c <= nCh; c += blockDim.x) {
+    const long target = (long)a0 + (long)c * atomsPerChunk;   // first k with atom >= target
+    int lo = 0, hi = nAtoms;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const long a = atomIdx ? atomIdx[mid] : mid;
+      if (a < target) lo = mid + 1; else hi = mid;
+    }
+    kLo[c] = lo;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStreamArgs a) {
+  if (a.hdr[2] == 0) return;   // selection not sorted: onevn_kernel (launched next) does the work
+  constexpr int APC = ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));   // atoms per chunk
+  extern __shared__ __align__(128) unsigned char smem_ov[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_ov + ONEVN_S_STAGES * ONEVN_S_STAGE_BYTES);
+  __shared__ double red[ONEVN_THREADS / 32][ONEVN_FB][13];
+  __shared__ double oS[ONEVN_FB][3];   // origin shifts of the current frame group (for the records; `o` stays in registers)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a0 = a.hdr[0], nCh = a.hdr[1];
+  const int nGroups = (a.nFrames + ONEVN_FB - 1) / ONEVN_FB;
+  const int myGroups = ((int)blockIdx.x < nGroups) ? (nGroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const long total = (long)myGroups * nCh;   // (group, chunk) steps of this CTA
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(a.crd);
+  const int spanAtoms = a.kLo[nCh] > 0 ? ((a.atomIdx ? a.atomIdx[a.nAtoms - 1] : a.nAtoms - 1) - a0 + 1) : 0;
+  if (tid == 0) {
+    for (int s = 0; s < ONEVN_S_STAGES; ++s) mbar_init(smem_u32(&full[s]), 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // Producer side (thread 0): stage `step` of this CTA's sequence.  Bytes below a 16-byte boundary at the end of a
+  // chunk (at most 3 floats) are copied with ordinary loads; the barrier at the end of every step orders them.
+  auto issue = [&](long step) {
+    const int g = (int)blockIdx.x + (int)(step / nCh) * (int)gridDim.x;
+    const int c = (int)(step % nCh);
+    const int st = (int)(step % ONEVN_S_STAGES);
+    const int nAt = min(APC, spanAtoms - c * APC);
+    unsigned char* sbuf = smem_ov + st * ONEVN_S_STAGE_BYTES;
+    uint32_t bytes[ONEVN_FB], tot = 0;
+    const unsigned char* src[ONEVN_FB];
+#pragma unroll
+    for (int f = 0; f < ONEVN_FB; ++f) {
+      const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+      const size_t off = ((size_t)fr * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
+      const size_t s0 = off & ~(size_t)15;
+      const uint32_t len = (uint32_t)(off - s0) + (uint32_t)nAt * 3u * (uint32_t)sizeof(T);
+      bytes[f] = len & ~15u; src[f] = base + s0; tot += bytes[f];
+      for (uint32_t t = bytes[f]; t < len; t += 4)   // tail: whole 4-byte words
+        *reinterpret_cast<uint32_t*>(sbuf + f * ONEVN_S_BUF_BYTES + t) = *reinterpret_cast<const uint32_t*>(base + s0 + t);
+    }
+    // reference atoms and atom numbers of the chunk's selected atoms [kLo[c], kLo[c+1])
+    const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
+    const uint32_t refBytes = (uint32_t)nSel * 32u;
+    uint32_t idxBytes = 0;
+    const unsigned char* idxSrc = nullptr;
+    if (a.atomIdx && nSel > 0) {
+      const size_t off = (size_t)kA * 4, s0 = off & ~(size_t)15;
+      const uint32_t len = (uint32_t)(off - s0) + (uint32_t)nSel * 4u;
+      idxBytes = len & ~15u; idxSrc = reinterpret_cast<const unsigned char*>(a.atomIdx) + s0;
+      for (uint32_t t = idxBytes; t < len; t += 4)
+        *reinterpret_cast<uint32_t*>(sbuf + ONEVN_S_IDX_OFF + t) = *reinterpret_cast<const uint32_t*>(idxSrc + t);
+    }
+    tot += refBytes + idxBytes;
+    const uint32_t bar = smem_u32(&full[st]);
+    mbar_expect_tx(bar, tot);
+    if (refBytes) bulk_g2s(smem_u32(sbuf + ONEVN_S_REF_OFF), reinterpret_cast<const unsigned char*>(a.refw) + (size_t)kA * 32, refBytes, bar);
+    if (idxBytes) bulk_g2s(smem_u32(sbuf + ONEVN_S_IDX_OFF), idxSrc, idxBytes, bar);
+#pragma unroll
+    for (int f = 0; f < ONEVN_FB; ++f)
+      if (bytes[f]) bulk_g2s(smem_u32(sbuf + f * ONEVN_S_BUF_BYTES), src[f], bytes[f], bar);
+    if (tot == 0) { /* nothing to land: the expect_tx arrive alone completes the phase */ }
+  };
+  if (tid == 0)
+    for (long s = 0; s < ONEVN_S_STAGES - 1 && s < total; ++s) issue(s);
+  __syncthreads();   // the producer's ordinary (tail) stores of the first stages are visible to everyone
+
+  double acc[ONEVN_FB][13];
+  double o[ONEVN_FB][3];
+  for (long step = 0; step < total; ++step) {
+    const int gi = (int)(step / nCh), c = (int)(step % nCh);
+    const int g = (int)blockIdx.x + gi * (int)gridDim.x;
+    const int st = (int)(step % ONEVN_S_STAGES);
+    if (c == 0) {
+      const int at0 = a.atomIdx ? a.atomIdx[0] : 0;
+#pragma unroll
+      for (int f = 0; f < ONEVN_FB; ++f) {
+        const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+        const T* row = reinterpret_cast<const T*>(a.crd) + (size_t)fr * a.stride + (size_t)3 * at0;
+        o[f][0] = (double)row[0]; o[f][1] = (double)row[1]; o[f][2] = (double)row[2];
+        if (tid == 0) { oS[f][0] = o[f][0]; oS[f][1] = o[f][1]; oS[f][2] = o[f][2]; }   // read after the group's barriers
+#pragma unroll
+        for (int x = 0; x < 13; ++x) acc[f][x] = 0.0;
+      }
+    }
+    if (tid == 0 && step + ONEVN_S_STAGES - 1 < total) issue(step + ONEVN_S_STAGES - 1);
+    const int chunkA0 = a0 + c * APC;
+    const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
+    mbar_wait(smem_u32(&full[st]), (uint32_t)((step / ONEVN_S_STAGES) & 1));
+    const unsigned char* sbuf = smem_ov + st * ONEVN_S_STAGE_BYTES;
+    const T* fp[ONEVN_FB];
+#pragma unroll
+    for (int f = 0; f < ONEVN_FB; ++f) {
+      const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+      const size_t off = ((size_t)fr * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
+      fp[f] = reinterpret_cast<const T*>(sbuf + f * ONEVN_S_BUF_BYTES + (off & 15));
+    }
+    const double4* sref = reinterpret_cast<const double4*>(sbuf + ONEVN_S_REF_OFF);
+    const int* sidx = reinterpret_cast<const int*>(sbuf + ONEVN_S_IDX_OFF + (((size_t)kA * 4) & 15));
+    for (int kk = tid; kk < nSel; kk += ONEVN_THREADS) {
+      const int at = (a.atomIdx ? sidx[kk] : kA + kk) - chunkA0;
+      const double4 rw = sref[kk];
+#pragma unroll
+      for (int f = 0; f < ONEVN_FB; ++f) {
+        const T* p = fp[f] + 3 * at;
+        if (a.fit) {
+          const double x = (double)p[0] - o[f][0], y = (double)p[1] - o[f][1], z = (double)p[2] - o[f][2];
+          const double mx = rw.w * x, my = rw.w * y, mz = rw.w * z;
+          acc[f][0] += mx * rw.x; acc[f][1] += mx * rw.y; acc[f][2] += mx * rw.z;
+          acc[f][3] += my * rw.x; acc[f][4] += my * rw.y; acc[f][5] += my * rw.z;
+          acc[f][6] += mz * rw.x; acc[f][7] += mz * rw.y; acc[f][8] += mz * rw.z;
+          acc[f][9] += mx; acc[f][10] += my; acc[f][11] += mz;
+          acc[f][12] += mx * x + my * y + mz * z;
+        } else {
+          const double dx = rw.x - (double)p[0], dy = rw.y - (double)p[1], dz = rw.z - (double)p[2];
+          acc[f][0] += rw.w * (dx * dx + dy * dy + dz * dz);
+        }
+      }
+    }
+    if (c == nCh - 1) {   // frame group complete: block reduction, one record per frame
+      const int nred = a.fit ? 13 : 1;
+#pragma unroll
+      for (int f = 0; f < ONEVN_FB; ++f)
+        for (int x = 0; x < nred; ++x) {
+          const double v = warp_sum(acc[f][x]);
+          if (lane == 0) red[warp][f][x] = v;
+        }
+      __syncthreads();
+      if (tid < ONEVN_FB * ONEVN_REC) {
+        const int f = tid / ONEVN_REC, x = tid % ONEVN_REC, fr = g * ONEVN_FB + f;
+        if (fr < a.nFrames) {
+          double v = 0.0;
+          if (x < nred) { for (int w = 0; w < ONEVN_THREADS / 32; ++w) v += red[w][f][x]; }
+          else if (x >= 13) v = oS[f][x - 13];
+          a.rec[(size_t)fr * ONEVN_REC + x] = v;
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with this stage (and with `red`): it may be refilled
+  }
+}
+
+/// One thread per frame: record -> RMSD (+ rotation, translation).  Same arithmetic as the tail of onevn_kernel.
+__global__ void __launch_bounds__(128) onevn_finish_kernel(const double* rec, const int* hdr, int nFrames, const double* refsum, int fit,
+                                                           double* rmsd, double* rot, double* trans) {
+  if (hdr[2] == 0) return;
+  const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fr >= nFrames) return;
+  const double* v = rec + (size_t)fr * ONEVN_REC;
+  const double M = refsum[3];
+  if (!fit) { rmsd[fr] = (v[0] < 0.0) ? 0.0 : sqrt(v[0] / M); return; }
+  const double cx = v[9] / M, cy = v[10] / M, cz = v[11] / M;
+  double S[9];
+  S[0] = v[0] - cx * refsum[0]; S[1] = v[1] - cx * refsum[1]; S[2] = v[2] - cx * refsum[2];
+  S[3] = v[3] - cy * refsum[0]; S[4] = v[4] - cy * refsum[1]; S[5] = v[5] - cy * refsum[2];
+  S[6] = v[6] - cz * refsum[0]; S[7] = v[7] - cz * refsum[1]; S[8] = v[8] - cz * refsum[2];
+  const double gt = v[12] - M * (cx * cx + cy * cy + cz * cz);
+  const double e0 = 0.5 * (gt + refsum[4]);
+  const Quartic q = quartic_of(S);
+  const double lam = largest_root(q, e0, S);
+  const double e = e0 - lam;
+  rmsd[fr] = (e < 0.0) ? 0.0 : sqrt(2.0 * e / M);
+  if (rot) rotation_from_cov(S, lam, rot + 9 * (size_t)fr);
+  if (trans) {
+    trans[3 * (size_t)fr] = -(cx + v[13]);
+    trans[3 * (size_t)fr + 1] = -(cy + v[14]);
+    trans[3 * (size_t)fr + 2] = -(cz + v[15]);
   }
 }
 
