@@ -17,10 +17,11 @@ One JSON line is printed by rank 0:
                result triangle left in HBM.
     e2e        same metric through the C ABI (b200_rms2d_tri_shard) with pinned HOST buffers:
                H2D of the COORDS, kernels, D2H of the float triangle all inside the timed region.
-    roofline   pair-tile kernel: algorithmic flop (18*N per fitted pair) / CUDA-event kernel time,
-               against this device's FP64 tensor (DMMA) peak measured live by a register-only
-               mma.sync probe (MEASURED_PEAKS.json has no FP64 figure; the bf16 fraction is
-               reported beside it for context).
+    roofline   pair-tile kernel of the engine the library chose (tcgen05 int8 when eligible, else FP64 DMMA):
+               algorithmic flop (18*N per fitted pair) / CUDA-event kernel time; `executed` counts the 81 int8
+               digit products per pair the tensor pipe actually runs; peak = this device's tcgen05 kind::i8
+               (or FP64 DMMA) issue peak measured live by a probe kernel (MEASURED_PEAKS.json holds bf16 only;
+               the fraction of 2x the measured bf16 figure is reported beside it).
     cpu_baseline  the reference's own Frame::RMSD_CenteredRef loop (oracle/_ref, OpenMP, all host
                threads) on a bounded prefix of the same trajectory (N == 1, rank 0 only).
 
@@ -46,7 +47,7 @@ SEEDS = {"cfg2": 20261017, "cfg5": 20261020}
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="override frame count")
@@ -107,7 +108,7 @@ class ClockSampler(threading.Thread):
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self.stop_evt.wait(0.1)
+            self.stop_evt.wait(0.01)
 
     def result(self):
         self.stop_evt.set()
@@ -290,7 +291,10 @@ def main():
         ms_per_launch = stt["pair_ms"] / launches
         flop_per_launch = 18.0 * nA * (stt["pairs"] / launches)       # algorithmic: SURVEY 8(d), 18*N per fitted pair
         achieved = flop_per_launch / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch > 0 else 0.0
-        r = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": None,
+        # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed ncu --set full
+        # capture of this exact workload (profiles/r1d_pair_i8_kernel.md: 55.9 MB + 45.6 MB); null for other shapes
+        traffic = 101.5e6 if (engine == 2 and name == "cfg2" and world == 1) else None
+        r = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": traffic,
              "launches": int(stt["pair_launches"]), "avg_launch_ms": ms_per_launch,
              "kernel_share_of_step": stt["pair_ms"] / own_ms if own_ms > 0 else None}
         bf16 = peaks_file.get("bf16_tflops_sustained")
