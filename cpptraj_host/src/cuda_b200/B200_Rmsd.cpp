@@ -1,0 +1,108 @@
+#include "B200_Rmsd.h"
+#include "b200_rmsd.h"
+#include <cstdlib>
+#include "../AtomMask.h"
+#include "../CpptrajStdio.h"
+#include "../DataSet_Coords_CRD.h"
+#include "../DataSet_MatrixFlt.h"
+#include "../DataSet_double.h"
+#include "../Frame.h"
+#include "../Cluster/Cframes.h"
+
+static int b200_err(const char* what) {
+  mprinterr("Error: B200 RMSD (%s): %s\n", what, b200_last_error());
+  return 1;
+}
+
+int Cpptraj::B200::Init() {
+  static bool initialised = false;
+  if (initialised) return 0;
+  int want = 0, used = 0;
+  const char* env = getenv("CPPTRAJ_B200_NGPU");
+  if (env != 0) want = atoi(env);
+  if (b200_init(want, &used)) return b200_err("device probe");
+  mprintf("\tB200 RMSD path: %i device(s).\n", used);
+  initialised = true;
+  return 0;
+}
+
+std::vector<double> Cpptraj::B200::MassesOf(Frame const& frm) {
+  std::vector<double> m( (size_t)frm.Natom() );
+  for (int i = 0; i < frm.Natom(); i++) m[i] = frm.Mass(i);
+  return m;
+}
+
+static inline const double* ptr_or_null(std::vector<double> const& v) { return v.empty() ? 0 : &v[0]; }
+
+int Cpptraj::B200::Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask, std::vector<double> const& tgtMass,
+                         DataSet_Coords_CRD const& ref, AtomMask const& refMask, std::vector<double> const& refMass,
+                         bool fullMatrix, bool fit, DataSet_MatrixFlt& out)
+{
+  if (Init()) return 1;
+  if (tgtMask.Nselected() != refMask.Nselected()) {
+    mprinterr("Error: B200 RMSD: # target atoms (%i) != # reference atoms (%i)\n", tgtMask.Nselected(), refMask.Nselected());
+    return 1;
+  }
+  if (tgt.Size() < 1 || tgtMask.Nselected() < 1) return 0;
+  float* mat = static_cast<float*>( out.MatrixPtr() );
+  int err;
+  if (!fullMatrix)
+    err = b200_rms2d_tri(tgt.RawFrames(), tgt.FrameStride(), (int)tgt.Size(), 0, (int)tgt.Size(),
+                         &tgtMask.Selected()[0], tgtMask.Nselected(), ptr_or_null(tgtMass), fit ? 1 : 0, mat);
+  else
+    err = b200_rms2d_full(tgt.RawFrames(), tgt.FrameStride(), (int)tgt.Size(), &tgtMask.Selected()[0],
+                          ref.RawFrames(), ref.FrameStride(), (int)ref.Size(), &refMask.Selected()[0],
+                          tgtMask.Nselected(), ptr_or_null(tgtMass), ptr_or_null(refMass), fit ? 1 : 0, mat);
+  return err ? b200_err("rms2d") : 0;
+}
+
+int Cpptraj::B200::CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+                             bool fit, Cluster::Cframes const& framesToCache, float* triangle)
+{
+  if (Init()) return 1;
+  if (framesToCache.size() < 2) return 0;
+  if (b200_rms2d_tri(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &(*framesToCache.begin()),
+                     (int)framesToCache.size(), &mask.Selected()[0], mask.Nselected(), ptr_or_null(mass), fit ? 1 : 0,
+                     triangle))
+    return b200_err("pairwise cache");
+  return 0;
+}
+
+// -----------------------------------------------------------------------------
+Cpptraj::B200::Rmsd1vN::~Rmsd1vN() { if (handle_ != 0) b200_rmsd_1vN_end(handle_); }
+
+int Cpptraj::B200::Rmsd1vN::Begin(Frame const& selectedRef, AtomMask const& tgtMask, bool fit, bool useMass,
+                                  bool wantRotation)
+{
+  if (Init()) return 1;
+  if (handle_ != 0) { b200_rmsd_1vN_end(handle_); handle_ = 0; }
+  nPushed_ = 0; best_ = -1; wantRot_ = (wantRotation && fit);
+  if (selectedRef.Natom() != tgtMask.Nselected()) {
+    mprinterr("Error: B200 RMSD: # reference atoms (%i) != # target atoms (%i)\n", selectedRef.Natom(), tgtMask.Nselected());
+    return 1;
+  }
+  std::vector<double> mass;
+  if (useMass) mass = MassesOf(selectedRef);
+  if (b200_rmsd_1vN_begin(selectedRef.xAddress(), &tgtMask.Selected()[0], tgtMask.Nselected(), ptr_or_null(mass),
+                          fit ? 1 : 0, wantRot_ ? 1 : 0, &handle_))
+    return b200_err("rmsd setup");
+  return 0;
+}
+
+int Cpptraj::B200::Rmsd1vN::Push(Frame const& frm) {
+  if (b200_rmsd_1vN_push_f64(handle_, frm.xAddress(), (size_t)3 * (size_t)frm.Natom(), 1)) return b200_err("rmsd push");
+  ++nPushed_;
+  return 0;
+}
+
+int Cpptraj::B200::Rmsd1vN::Flush(DataSet_double& rmsd, std::vector<double>* rot, std::vector<double>* trans) {
+  if (nPushed_ == 0) return 0;
+  std::vector<double> r(nPushed_), u, t;
+  if (wantRot_) { u.resize((size_t)9 * nPushed_); t.resize((size_t)3 * nPushed_); }
+  if (b200_rmsd_1vN_flush(handle_, &r[0], wantRot_ ? &u[0] : 0, wantRot_ ? &t[0] : 0, &best_)) return b200_err("rmsd flush");
+  for (unsigned int i = 0; i != nPushed_; i++) rmsd.AddElement( r[i] );   // append-only, push order (DataSet_double.cpp:14-20)
+  if (rot != 0) rot->insert(rot->end(), u.begin(), u.end());
+  if (trans != 0) trans->insert(trans->end(), t.begin(), t.end());
+  nPushed_ = 0;
+  return 0;
+}

@@ -1,0 +1,62 @@
+#ifndef INC_CUDA_B200_RMSD_H
+#define INC_CUDA_B200_RMSD_H
+/** Host glue between cpptraj's RMSD plugins and the C ABI of the B200 library (b200_rmsd.h).
+  * Compiled only with -DCUDA_B200.  The plugins keep parsing keywords and masks and own the
+  * DataSets; these functions hand their raw buffers to the device path and map error codes to
+  * mprinterr + a non-zero return (Analysis::ERR / Action::ERR at the call sites).
+  * There is no CPU fallback: a failure here is an error of the command.
+  */
+#include <vector>
+#include <cstddef>
+class DataSet_Coords_CRD;
+class DataSet_MatrixFlt;
+class DataSet_double;
+class AtomMask;
+class Frame;
+struct b200_1vN;
+namespace Cpptraj {
+namespace Cluster { class Cframes; }
+namespace B200 {
+/// One-time device probe (pattern of Cpptraj.cpp:120-135). CPPTRAJ_B200_NGPU limits the device count. \return 0 if OK.
+int Init();
+/// Per-selected-atom masses of a Frame set up with SetupFrameFromMask (Frame.cpp:502-512).
+std::vector<double> MassesOf(Frame const&);
+/** rms2d (Analysis_Rms2d::Calculate_2D, Analysis_Rms2d.cpp:196-295). \a out must already be allocated by the caller
+  * (AllocateTriangle(totaltgt) or Allocate2D(totalref,totaltgt)). Empty mass vectors mean no mass weighting.
+  * \return 0 if OK, 1 after mprinterr.
+  */
+int Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask, std::vector<double> const& tgtMass,
+          DataSet_Coords_CRD const& ref, AtomMask const& refMask, std::vector<double> const& refMass,
+          bool fullMatrix, bool fit, DataSet_MatrixFlt& out);
+/** Pairwise-cache fill (MetricArray::calcFrameDistances, Cluster/MetricArray.cpp:766-801) for a single Metric_RMS.
+  * \a triangle is DataSet_PairwiseCache_MEM::Ptr() after SetupCache sized it for framesToCache.size() frames.
+  */
+int CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+              bool fit, Cluster::Cframes const& framesToCache, float* triangle);
+/** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417): frames are pushed as they arrive, results are
+  * appended to the DataSets in push order at every Flush().
+  */
+class Rmsd1vN {
+  public:
+    Rmsd1vN() : handle_(0), nPushed_(0) {}
+    ~Rmsd1vN();
+    /// \param selectedRef REF_.SelectedRef(): selected atoms, already centred when fitting (ReferenceAction.cpp:155-169)
+    int Begin(Frame const& selectedRef, AtomMask const& tgtMask, bool fit, bool useMass, bool wantRotation);
+    /// Push one trajectory frame (all atoms, double, Frame::xAddress()).
+    int Push(Frame const& frm);
+    /// Append pending results. rot/trans may be null. \return 0 if OK.
+    int Flush(DataSet_double& rmsd, std::vector<double>* rot, std::vector<double>* trans);
+    /// Index (over all frames pushed) of the smallest RMSD so far.
+    long BestFrame() const { return best_; }
+    unsigned int Npending() const { return nPushed_; }
+  private:
+    Rmsd1vN(Rmsd1vN const&);
+    Rmsd1vN& operator=(Rmsd1vN const&);
+    b200_1vN* handle_;
+    unsigned int nPushed_;
+    long best_;
+    bool wantRot_;
+};
+}
+}
+#endif
