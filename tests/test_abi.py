@@ -80,3 +80,17 @@ def test_fails_loudly_without_gpu(built):
     assert ei.value.code == 1
     with pytest.raises(b.B200Error):
         b.rms2d_tri(np.zeros((4, 9), np.float32), np.arange(3, dtype=np.int32))
+
+
+def test_cpptraj_host_glue_compiles_against_reference():
+    """cpptraj_host/ (C++ glue + reference.patch) applies to the reference tree and compiles against its headers
+    (-fsyntax-only, -DCUDA_B200).  Needs /root/reference: skipped on the GPU box."""
+    import subprocess
+    ref = os.environ.get("CPPTRAJ_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["bash", os.path.join(root, "tools", "build_cpptraj_b200.sh"), "--check", ref],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert r.stdout.count("syntax ok") == 3

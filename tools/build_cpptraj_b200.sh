@@ -10,10 +10,11 @@ set -e
 MODE=--check
 if [ "$1" == "--check" ] || [ "$1" == "--build" ]; then MODE=$1; shift; fi
 REF=${1:-/root/reference}
-OUT=${2:-/tmp/cpptraj_b200_build}
+if [ "$MODE" == "--check" ]; then OUT=${2:-/tmp/cpptraj_b200_check}; else OUT=${2:-/tmp/cpptraj_b200_build}; fi
 HERE=$(cd "$(dirname "$0")/.." && pwd)
 rm -rf "$OUT" && mkdir -p "$OUT"
-cp -r "$REF"/. "$OUT"/ && chmod -R u+w "$OUT"
+if [ "$MODE" == "--check" ]; then cp -r "$REF"/src "$OUT"/src; else cp -r "$REF"/. "$OUT"/; fi
+chmod -R u+w "$OUT"
 ( cd "$OUT" && patch -p1 -s < "$HERE/cpptraj_host/reference.patch" )
 mkdir -p "$OUT/src/cuda_b200"
 cp "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.h "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.cpp "$HERE"/include/b200_rmsd.h "$OUT/src/cuda_b200/"
