@@ -1,0 +1,47 @@
+"""End to end through cpptraj itself: the reference's own Test_2DRMS decks run by a cpptraj binary whose rms2d pair
+loops were replaced by the B200 path (cpptraj_host/ glue + reference.patch, built by tools/build_cpptraj_b200.sh --build
+into oracle/_ref/cpptraj_b200/, which travels to the GPU box).  Outputs are compared with the reference's golden
+`*.save` files (test/Test_2DRMS/RunTest.sh tests 1, 2, 5, 6; tz2.crd instead of tz2.nc: this build has no NetCDF).
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGE = os.path.join(ROOT, "oracle", "_ref", "cpptraj_b200")
+BIN = os.path.join(STAGE, "cpptraj.B200")
+
+
+def table(path):
+    rows = [l.split() for l in open(path) if l.strip() and not l.lstrip().startswith("#")]
+    return np.array([[float(x) for x in r] for r in rows])
+
+
+DECKS = [
+    ("fit", "2drms crd1 :3-7 rmsout OUT", "rmsd.dat.save"),
+    ("mass", "2drms crd1 :3-7 rmsout OUT mass", "rmsd.mass.dat.save"),
+    ("refmask_full_matrix", "2drms :2 :11 out OUT", "trp.dat.save"),
+    ("nofit", "rms first :2-12@CA\n2drms crd1 :2 nofit out OUT", "nofit.dat.save"),
+]
+
+
+@pytest.mark.parametrize("name,cmd,save", DECKS, ids=[d[0] for d in DECKS])
+def test_cpptraj_2drms_decks_on_b200(tmp_path, name, cmd, save):
+    if not os.path.exists(BIN):
+        pytest.skip("cpptraj.B200 not staged (tools/build_cpptraj_b200.sh --build needs the reference tree)")
+    out = tmp_path / "out.dat"
+    deck = "noprogress\nparm %s\ntrajin %s 1 10\n%s\n" % (os.path.join(STAGE, "tz2.parm7"), os.path.join(STAGE, "tz2.crd"),
+                                                          cmd.replace("OUT", str(out)))
+    (tmp_path / "rms.in").write_text(deck)
+    r = subprocess.run([BIN, "-i", str(tmp_path / "rms.in")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    got, want = table(out), table(os.path.join(STAGE, save))
+    assert got.shape == want.shape
+    # goldens are printed with 3 decimals from NetCDF (float) coordinates; tz2.crd carries 3-decimal ASCII coordinates
+    assert np.abs(got - want).max() <= 1.1e-3, np.abs(got - want).max()

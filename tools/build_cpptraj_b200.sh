@@ -42,3 +42,13 @@ sed -i "s|^LDFLAGS=|LDFLAGS=$OUT/src/cuda_b200/B200_Rmsd.o -L$HERE/cpptraj_b200 
 /usr/bin/g++ -std=c++11 -O2 -fopenmp -DCUDA_B200 -Isrc -Isrc/cuda_b200 -c src/cuda_b200/B200_Rmsd.cpp -o src/cuda_b200/B200_Rmsd.o
 make -j"$(nproc)" install > make.log 2>&1 || { tail -30 make.log; exit 1; }
 ls -la bin/
+# stage the binary and the reference's own Test_2DRMS inputs / golden outputs where they travel to the GPU box
+# (oracle/_ref/ is git-ignored: nothing of the reference enters the history)
+STAGE="$HERE/oracle/_ref/cpptraj_b200"
+mkdir -p "$STAGE"
+cp bin/cpptraj.OMP "$STAGE"/cpptraj.B200
+cp "$REF"/test/tz2.parm7 "$REF"/test/tz2.crd "$STAGE"/
+cp "$REF"/test/Test_2DRMS/rmsd.dat.save "$REF"/test/Test_2DRMS/rmsd.mass.dat.save "$REF"/test/Test_2DRMS/trp.dat.save \
+   "$REF"/test/Test_2DRMS/nofit.dat.save "$STAGE"/
+chmod u+w "$STAGE"/*
+ls -la "$STAGE"
