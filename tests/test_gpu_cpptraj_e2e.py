@@ -45,3 +45,28 @@ def test_cpptraj_2drms_decks_on_b200(tmp_path, name, cmd, save):
     assert got.shape == want.shape
     # goldens are printed with 3 decimals from NetCDF (float) coordinates; tz2.crd carries 3-decimal ASCII coordinates
     assert np.abs(got - want).max() <= 1.1e-3, np.abs(got - want).max()
+
+
+def test_cpptraj_cluster_pairwise_cache_on_b200(tmp_path):
+    """test/Test_Cluster/RunTest.sh, first deck: hierarchical agglomerative clustering whose in-memory pairwise cache
+    (MetricArray::calcFrameDistances) is filled by the B200 path; cluster number vs time must match the golden exactly."""
+    if not os.path.exists(BIN):
+        pytest.skip("cpptraj.B200 not staged")
+    deck = ("noprogress\nparm %s\ntrajin %s\n"
+            "cluster C1 :2-10 clusters 3 epsilon 4.0 out cnumvtime.dat summary avg.summary.dat nofit\n"
+            "cluster crd1 :2-10 clusters 3 epsilon 4.0 summary summary.dat complete nofit\n"
+            % (os.path.join(STAGE, "tz2.parm7"), os.path.join(STAGE, "tz2.crd")))
+    (tmp_path / "cluster.in").write_text(deck)
+    r = subprocess.run([BIN, "-i", str(tmp_path / "cluster.in")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    got, want = table(tmp_path / "cnumvtime.dat"), table(os.path.join(STAGE, "cnumvtime.dat.save"))
+    assert np.array_equal(got, want)
+    # complete-linkage summary: numeric columns (cluster, frames, fraction, avg dist, stdev, centroid frame, avg c-dist)
+    gs = [l.split() for l in open(tmp_path / "summary.dat") if not l.startswith("#")]
+    ws = [l.split() for l in open(os.path.join(STAGE, "summary.dat.save")) if not l.startswith("#")]
+    assert len(gs) == len(ws)
+    for g, w in zip(gs, ws):
+        assert g[0] == w[0] and g[1] == w[1] and g[5] == w[5]
+        assert abs(float(g[3]) - float(w[3])) <= 2e-3 and abs(float(g[6]) - float(w[6])) <= 2e-3

@@ -49,6 +49,6 @@ mkdir -p "$STAGE"
 cp bin/cpptraj.OMP "$STAGE"/cpptraj.B200
 cp "$REF"/test/tz2.parm7 "$REF"/test/tz2.crd "$STAGE"/
 cp "$REF"/test/Test_2DRMS/rmsd.dat.save "$REF"/test/Test_2DRMS/rmsd.mass.dat.save "$REF"/test/Test_2DRMS/trp.dat.save \
-   "$REF"/test/Test_2DRMS/nofit.dat.save "$STAGE"/
+   "$REF"/test/Test_2DRMS/nofit.dat.save "$REF"/test/Test_Cluster/cnumvtime.dat.save "$REF"/test/Test_Cluster/summary.dat.save "$STAGE"/
 chmod u+w "$STAGE"/*
 ls -la "$STAGE"
