@@ -1,6 +1,7 @@
 #include "B200_Rmsd.h"
 #include "b200_rmsd.h"
 #include <cstdlib>
+#include <algorithm>
 #include "../AtomMask.h"
 #include "../CpptrajStdio.h"
 #include "../DataSet_Coords_CRD.h"
@@ -71,38 +72,47 @@ int Cpptraj::B200::CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask
 // -----------------------------------------------------------------------------
 Cpptraj::B200::Rmsd1vN::~Rmsd1vN() { if (handle_ != 0) b200_rmsd_1vN_end(handle_); }
 
-int Cpptraj::B200::Rmsd1vN::Begin(Frame const& selectedRef, AtomMask const& tgtMask, bool fit, bool useMass,
-                                  bool wantRotation)
-{
+int Cpptraj::B200::Rmsd1vN::Begin(Frame const& selectedRef, Frame const& massFrame, bool fit, bool useMass) {
   if (Init()) return 1;
   if (handle_ != 0) { b200_rmsd_1vN_end(handle_); handle_ = 0; }
-  nPushed_ = 0; best_ = -1; wantRot_ = (wantRotation && fit);
-  if (selectedRef.Natom() != tgtMask.Nselected()) {
-    mprinterr("Error: B200 RMSD: # reference atoms (%i) != # target atoms (%i)\n", selectedRef.Natom(), tgtMask.Nselected());
-    return 1;
-  }
+  nAtoms_ = selectedRef.Natom();
+  nBuffered_ = 0; best_ = -1;
+  if (nAtoms_ < 1) { mprinterr("Error: B200 RMSD: empty reference selection.\n"); return 1; }
+  buffer_.resize( (size_t)BATCH * 3 * (size_t)nAtoms_ );
+  std::vector<int> identity( nAtoms_ );           // frames arrive already gathered (tgtFrame_.SetCoordinates)
+  for (int i = 0; i < nAtoms_; i++) identity[i] = i;
   std::vector<double> mass;
-  if (useMass) mass = MassesOf(selectedRef);
-  if (b200_rmsd_1vN_begin(selectedRef.xAddress(), &tgtMask.Selected()[0], tgtMask.Nselected(), ptr_or_null(mass),
-                          fit ? 1 : 0, wantRot_ ? 1 : 0, &handle_))
+  if (useMass) mass = MassesOf(massFrame);
+  if (b200_rmsd_1vN_begin(selectedRef.xAddress(), &identity[0], nAtoms_, ptr_or_null(mass), fit ? 1 : 0, 0, &handle_))
     return b200_err("rmsd setup");
   return 0;
 }
 
-int Cpptraj::B200::Rmsd1vN::Push(Frame const& frm) {
-  if (b200_rmsd_1vN_push_f64(handle_, frm.xAddress(), (size_t)3 * (size_t)frm.Natom(), 1)) return b200_err("rmsd push");
-  ++nPushed_;
+int Cpptraj::B200::Rmsd1vN::pushBuffer() {
+  if (nBuffered_ == 0) return 0;
+  if (b200_rmsd_1vN_push_f64(handle_, &buffer_[0], (size_t)3 * (size_t)nAtoms_, (int)nBuffered_)) return b200_err("rmsd push");
+  nBuffered_ = 0;
   return 0;
 }
 
-int Cpptraj::B200::Rmsd1vN::Flush(DataSet_double& rmsd, std::vector<double>* rot, std::vector<double>* trans) {
-  if (nPushed_ == 0) return 0;
-  std::vector<double> r(nPushed_), u, t;
-  if (wantRot_) { u.resize((size_t)9 * nPushed_); t.resize((size_t)3 * nPushed_); }
-  if (b200_rmsd_1vN_flush(handle_, &r[0], wantRot_ ? &u[0] : 0, wantRot_ ? &t[0] : 0, &best_)) return b200_err("rmsd flush");
-  for (unsigned int i = 0; i != nPushed_; i++) rmsd.AddElement( r[i] );   // append-only, push order (DataSet_double.cpp:14-20)
-  if (rot != 0) rot->insert(rot->end(), u.begin(), u.end());
-  if (trans != 0) trans->insert(trans->end(), t.begin(), t.end());
-  nPushed_ = 0;
+int Cpptraj::B200::Rmsd1vN::Push(Frame const& selectedTgt) {
+  if (selectedTgt.Natom() != nAtoms_) {
+    mprinterr("Error: B200 RMSD: frame has %i selected atoms, reference %i\n", selectedTgt.Natom(), nAtoms_);
+    return 1;
+  }
+  const double* x = selectedTgt.xAddress();
+  std::copy(x, x + (size_t)3 * (size_t)nAtoms_, buffer_.begin() + (size_t)nBuffered_ * 3 * (size_t)nAtoms_);
+  if (++nBuffered_ == BATCH) return pushBuffer();
+  return 0;
+}
+
+int Cpptraj::B200::Rmsd1vN::Flush(DataSet_double& rmsd) {
+  if (handle_ == 0) return 0;
+  if (pushBuffer()) return 1;
+  const long n = b200_rmsd_1vN_pending(handle_);
+  if (n < 1) return 0;
+  std::vector<double> r( (size_t)n );
+  if (b200_rmsd_1vN_flush(handle_, &r[0], 0, 0, &best_)) return b200_err("rmsd flush");
+  for (long i = 0; i != n; i++) rmsd.AddElement( r[i] );   // append-only, frame order (DataSet_double.cpp:14-20)
   return 0;
 }

@@ -33,29 +33,34 @@ int Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask, std::vector<do
   */
 int CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
               bool fit, Cluster::Cframes const& framesToCache, float* triangle);
-/** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417): frames are pushed as they arrive, results are
-  * appended to the DataSets in push order at every Flush().
+/** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417) when coordinates are not modified (nomod / nofit):
+  * the selected atoms of every frame (Action_Rmsd::tgtFrame_ after SetCoordinates) are buffered on the host and
+  * pushed to the device in batches; results are appended to the DataSet in frame order at Flush().
   */
 class Rmsd1vN {
   public:
-    Rmsd1vN() : handle_(0), nPushed_(0) {}
+    Rmsd1vN() : handle_(0), nAtoms_(0), nBuffered_(0), best_(-1) {}
     ~Rmsd1vN();
     /// \param selectedRef REF_.SelectedRef(): selected atoms, already centred when fitting (ReferenceAction.cpp:155-169)
-    int Begin(Frame const& selectedRef, AtomMask const& tgtMask, bool fit, bool useMass, bool wantRotation);
-    /// Push one trajectory frame (all atoms, double, Frame::xAddress()).
-    int Push(Frame const& frm);
-    /// Append pending results. rot/trans may be null. \return 0 if OK.
-    int Flush(DataSet_double& rmsd, std::vector<double>* rot, std::vector<double>* trans);
+    /// \param massFrame Frame whose per-atom masses weight the fit (the TARGET frame's, Frame.cpp:1184-1208)
+    int Begin(Frame const& selectedRef, Frame const& massFrame, bool fit, bool useMass);
+    bool Active() const { return handle_ != 0; }
+    /// Buffer the selected atoms of one frame (Frame set up from the target mask).
+    int Push(Frame const& selectedTgt);
+    /// Push what is buffered, wait, append all pending RMSDs to \a rmsd in push order. \return 0 if OK.
+    int Flush(DataSet_double& rmsd);
     /// Index (over all frames pushed) of the smallest RMSD so far.
     long BestFrame() const { return best_; }
-    unsigned int Npending() const { return nPushed_; }
   private:
     Rmsd1vN(Rmsd1vN const&);
     Rmsd1vN& operator=(Rmsd1vN const&);
+    int pushBuffer();
+    static const unsigned int BATCH = 512;   ///< frames per device push
     b200_1vN* handle_;
-    unsigned int nPushed_;
+    int nAtoms_;
+    unsigned int nBuffered_;
     long best_;
-    bool wantRot_;
+    std::vector<double> buffer_;             ///< BATCH x 3*nAtoms_ selected coordinates
 };
 }
 }

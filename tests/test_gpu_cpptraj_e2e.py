@@ -70,3 +70,21 @@ def test_cpptraj_cluster_pairwise_cache_on_b200(tmp_path):
     for g, w in zip(gs, ws):
         assert g[0] == w[0] and g[1] == w[1] and g[5] == w[5]
         assert abs(float(g[3]) - float(w[3])) <= 2e-3 and abs(float(g[6]) - float(w[6])) <= 2e-3
+
+
+def test_cpptraj_rms_nomod_on_b200(tmp_path):
+    """test/Test_RMSD/RunTest.sh "RMS nomod": the rmsd action, coordinates not modified, batched through the one-vs-many
+    path by Action_Rmsd and appended in Print()."""
+    if not os.path.exists(BIN) or not os.path.exists(os.path.join(STAGE, "NoMod.dat.save")):
+        pytest.skip("cpptraj.B200 (with the Action_Rmsd branch) not staged")
+    deck = "parm %s\ntrajin %s\nrms First_CA :2-12@CA out NoMod.dat nomod\n" % (
+        os.path.join(STAGE, "tz2.parm7"), os.path.join(STAGE, "tz2.crd"))
+    (tmp_path / "rms.in").write_text(deck)
+    r = subprocess.run([BIN, "-i", str(tmp_path / "rms.in")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    got, want = table(tmp_path / "NoMod.dat"), table(os.path.join(STAGE, "NoMod.dat.save"))
+    assert got.shape == want.shape == (101, 2)
+    # golden printed with 4 decimals from NetCDF coordinates; tz2.crd carries 3-decimal ASCII coordinates
+    assert np.abs(got - want).max() <= 2.1e-4, np.abs(got - want).max()

@@ -19,7 +19,7 @@ chmod -R u+w "$OUT"
 mkdir -p "$OUT/src/cuda_b200"
 cp "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.h "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.cpp "$HERE"/include/b200_rmsd.h "$OUT/src/cuda_b200/"
 cd "$OUT/src"
-for f in cuda_b200/B200_Rmsd.cpp Analysis_Rms2d.cpp Cluster/MetricArray.cpp; do
+for f in cuda_b200/B200_Rmsd.cpp Analysis_Rms2d.cpp Cluster/MetricArray.cpp Action_Rmsd.cpp; do
   /usr/bin/g++ -std=c++11 -fsyntax-only -fopenmp -DCUDA_B200 -DNO_MATHLIB -DNONETCDF -I. -Icuda_b200 "$f"
   echo "syntax ok: $f"
 done
@@ -49,6 +49,6 @@ mkdir -p "$STAGE"
 cp bin/cpptraj.OMP "$STAGE"/cpptraj.B200
 cp "$REF"/test/tz2.parm7 "$REF"/test/tz2.crd "$STAGE"/
 cp "$REF"/test/Test_2DRMS/rmsd.dat.save "$REF"/test/Test_2DRMS/rmsd.mass.dat.save "$REF"/test/Test_2DRMS/trp.dat.save \
-   "$REF"/test/Test_2DRMS/nofit.dat.save "$REF"/test/Test_Cluster/cnumvtime.dat.save "$REF"/test/Test_Cluster/summary.dat.save "$STAGE"/
+   "$REF"/test/Test_2DRMS/nofit.dat.save "$REF"/test/Test_Cluster/cnumvtime.dat.save "$REF"/test/Test_Cluster/summary.dat.save "$REF"/test/Test_RMSD/NoMod.dat.save "$STAGE"/
 chmod u+w "$STAGE"/*
 ls -la "$STAGE"
