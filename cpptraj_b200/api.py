@@ -50,6 +50,8 @@ def lib():
     L.b200_rmsd_1vN_flush.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_long)]
     L.b200_rmsd_1vN_end.argtypes = [vp]
     L.b200_dev_rms2d_tri.argtypes = [vp, sz, vp, i, vp, i, vp, i, i, i, vp, vp]
+    L.b200_rmsd_frames_to_centroids.argtypes = [vp, sz, i, vp, i, vp, i, vp, i, vp, i, vp, vp, vp]
+    L.b200_rmsd_frames_to_centroids.restype = i
     L.b200_dev_rmsd_1vN.argtypes = [vp, sz, i, vp, i, vp, vp, i, vp, vp, vp, vp]
     L.b200_set_pair_engine.argtypes = [i]
     L.b200_set_i8_cta_group.argtypes = [i]
@@ -224,6 +226,23 @@ def rmsd_1vN(crd, atom_idx, ref_selected, mass=None, fit=True, want_rot=False, c
         else:
             h.push(crd)
         return h.flush()
+
+
+def frames_to_centroids(crd, atom_idx, centroids, mass=None, fit=True, frame_idx=None, want_dist=True):
+    """Frame-to-centroid RMSDs (Metric_RMS::FrameCentroidDist for many frames): returns (dist [nF, K] or None,
+    closest [nF] int32, closest_dist [nF])."""
+    crd = _crd2d(crd)
+    sel = _arr(atom_idx, np.int32)
+    cen = np.ascontiguousarray(centroids, np.float64).reshape(-1, 3 * len(sel))
+    mass = _arr(mass, np.float64)
+    fidx = _arr(frame_idx, np.int32)
+    nF = len(fidx) if fidx is not None else crd.shape[0]
+    dist = np.empty((nF, cen.shape[0]), np.float64) if want_dist else None
+    closest = np.empty(nF, np.int32)
+    cdist = np.empty(nF, np.float64)
+    _check(lib().b200_rmsd_frames_to_centroids(_p(crd), crd.shape[1], crd.shape[0], _p(fidx), nF, _p(sel), len(sel), _p(mass),
+                                               int(bool(fit)), _p(cen), cen.shape[0], _p(dist), _p(closest), _p(cdist)))
+    return dist, closest, cdist
 
 
 def set_profiling(on):

@@ -1004,7 +1004,7 @@ static size_t onevn_ws_bytes(size_t stride, int nFrames) {
 template <typename T>
 static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, int nAtoms,
                      const double* refw, const double* refsum, int fit, double* rmsd, double* rot, double* trans,
-                     void* ws, cudaStream_t st) {
+                     void* ws, cudaStream_t st, const int* d_frameIdx = nullptr, long srcBase = 0) {
   constexpr int APC = ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));
   const int maxChunks = (int)std::min<size_t>(stride / 3 / APC + 2, 1u << 20);
   int* hdr = (int*)ws;
@@ -1024,7 +1024,8 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
     COUNT_LAUNCH();
     onevn_chunks_kernel<<<1, 256, 0, st>>>(d_atomIdx, nAtoms, APC, maxChunks, hdr, kLo);
     OneVNStreamArgs sa;
-    sa.crd = d_crd; sa.stride = stride; sa.nFrames = nFrames; sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms;
+    sa.crd = d_crd; sa.stride = stride; sa.frameIdx = d_frameIdx; sa.srcBase = srcBase; sa.nFrames = nFrames;
+    sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms;
     sa.refw = refw; sa.hdr = hdr; sa.kLo = kLo; sa.fit = fit; sa.rec = rec;
     const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
     COUNT_LAUNCH();
@@ -1033,7 +1034,8 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
     onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
   }
   OneVNArgs a;
-  a.crd = d_crd; a.stride = stride; a.nFrames = nFrames; a.atomIdx = d_atomIdx; a.nAtoms = nAtoms;
+  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = nFrames;
+  a.atomIdx = d_atomIdx; a.nAtoms = nAtoms;
   a.refw = refw; a.refsum = refsum; a.skipIf = stream ? hdr : nullptr; a.fit = fit;
   a.rmsd = rmsd; a.rot = rot; a.trans = trans;
   COUNT_LAUNCH();
@@ -1230,6 +1232,80 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   return B200_OK;
 }
 
+
+int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal, const int* frameIdx, int nFrames,
+                                  const int* atomIdx, int nAtoms, const double* mass, int fit, const double* centroids,
+                                  int nCentroids, double* distOut, int* closestOut, double* closestDistOut) {
+  if (!crd || !centroids || nCentroids <= 0) return fail(B200_ERR_ARG, "bad argument");
+  if (nFrames <= 0) return B200_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  int maxAtom = 0;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  int sLo = 0, sHi = nFrames;
+  if (frameIdx) {
+    sLo = nFramesTotal; sHi = 0;
+    for (int f = 0; f < nFrames; ++f) {
+      if (frameIdx[f] < 0 || frameIdx[f] >= nFramesTotal) return fail(B200_ERR_ARG, "frameIdx[%d]=%d out of range", f, frameIdx[f]);
+      sLo = std::min(sLo, frameIdx[f]); sHi = std::max(sHi, frameIdx[f] + 1);
+    }
+  } else if (nFrames > nFramesTotal) {
+    return fail(B200_ERR_ARG, "nFrames %d > nFramesTotal %d", nFrames, nFramesTotal);
+  }
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  if ((rc = upload_crd(d.crd, crd, frameStrideFloats, sLo, sHi, width, st, &h2d))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
+  if (frameIdx && (rc = upload_vec(d.frameIdx, frameIdx, (size_t)nFrames, st))) return rc;
+  DevBuf cen;
+  if ((rc = upload_vec(cen, centroids, (size_t)nCentroids * 3 * (size_t)nAtoms, st))) return rc;
+  // workspace: refw + refsum | one-vs-many workspace | dist [K][nFrames] | outputs
+  const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
+  const size_t wsBytes = (onevn_ws_bytes(width, nFrames) + 63) & ~(size_t)63;
+  const size_t distBytes = (size_t)nCentroids * (size_t)nFrames * sizeof(double);
+  const size_t outBytes = distBytes + (size_t)nFrames * (sizeof(int) + sizeof(double)) + 64;
+  if ((rc = d.onevnWs.reserve(refBytes + wsBytes + distBytes + outBytes))) { cen.release(); return rc; }
+  char* base = (char*)d.onevnWs.p;
+  double* refw = (double*)base;
+  double* refsum = refw + (size_t)4 * nAtoms;
+  void* ws = base + refBytes;
+  double* dist = (double*)(base + refBytes + wsBytes);
+  double* dOutT = (double*)((char*)dist + distBytes);
+  double* dClosestDist = dOutT + (size_t)nCentroids * nFrames;
+  int* dClosest = (int*)(dClosestDist + nFrames);
+  const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
+  Timer t;
+  t.begin(st);
+  for (int k = 0; k < nCentroids; ++k) {
+    COUNT_LAUNCH();
+    onevn_setup_kernel<<<1, 32, 0, st>>>((const double*)cen.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
+    if ((rc = onevn_run<float>(d.numSMs, d.crd.p, width, nFrames, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
+                               dist + (size_t)k * nFrames, nullptr, nullptr, ws, st,
+                               frameIdx ? (const int*)d.frameIdx.p : nullptr, (long)sLo))) { cen.release(); return rc; }
+  }
+  COUNT_LAUNCH();
+  centroid_argmin_kernel<<<(nFrames + 255) / 256, 256, 0, st>>>(dist, nFrames, nCentroids, distOut ? dOutT : nullptr, dClosest,
+                                                                 dClosestDist);
+  t.end(st);
+  double d2h = 0.0;
+  if (distOut) { CU(cudaMemcpyAsync(distOut, dOutT, distBytes, cudaMemcpyDeviceToHost, st)); d2h += (double)distBytes; }
+  if (closestOut) { CU(cudaMemcpyAsync(closestOut, dClosest, (size_t)nFrames * sizeof(int), cudaMemcpyDeviceToHost, st)); d2h += 4.0 * nFrames; }
+  if (closestDistOut) { CU(cudaMemcpyAsync(closestDistOut, dClosestDist, (size_t)nFrames * sizeof(double), cudaMemcpyDeviceToHost, st)); d2h += 8.0 * nFrames; }
+  CU(cudaStreamSynchronize(st));
+  cen.release();
+  {
+    const double ms = t.resolve();
+    std::lock_guard<std::mutex> sl(g_statMu);
+    g_stats.onevn_ms += ms; g_stats.onevn_launches += nCentroids; g_stats.frames_1vN += (double)nFrames * nCentroids;
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h;
+  }
+  return B200_OK;
+}
 
 int b200_debug_i8_clocks(long long* out, int ctas) {
   // Arms (out == NULL) or reads back (out != NULL) the per-CTA cycle counters of pair_i8_kernel: 16 per CTA.

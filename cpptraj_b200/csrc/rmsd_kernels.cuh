@@ -528,6 +528,8 @@ constexpr int ONEVN_THREADS = 256;
 struct OneVNArgs {
   const void* crd;
   size_t stride;            // elements per frame
+  const int* frameIdx;      // nullable: frame n is row frameIdx[n] - srcBase of crd (sieved frame lists)
+  long srcBase;
   int nFrames;
   const int* atomIdx;       // nullable
   int nAtoms;
@@ -598,7 +600,8 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
 #pragma unroll
   for (int f = 0; f < ONEVN_FB; ++f) {
     const int fr = min(fbase + f, a.nFrames - 1);
-    src[f] = crd + (size_t)fr * a.stride;
+    const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+    src[f] = crd + row * a.stride;
     o[f][0] = (double)src[f][3 * (size_t)at0];
     o[f][1] = (double)src[f][3 * (size_t)at0 + 1];
     o[f][2] = (double)src[f][3 * (size_t)at0 + 2];
@@ -703,6 +706,8 @@ constexpr int ONEVN_REC = 16;                                    // doubles per 
 struct OneVNStreamArgs {
   const void* crd;
   size_t stride;            // elements per frame
+  const int* frameIdx;      // nullable: frame n is row frameIdx[n] - srcBase of crd
+  long srcBase;
   int nFrames;
   const int* atomIdx;       // nullable (identity)
   int nAtoms;
@@ -779,7 +784,8 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
 #pragma unroll
     for (int f = 0; f < ONEVN_FB; ++f) {
       const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
-      const size_t off = ((size_t)fr * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
+      const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+      const size_t off = (row * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
       const size_t s0 = off & ~(size_t)15;
       const uint32_t len = (uint32_t)(off - s0) + (uint32_t)nAt * 3u * (uint32_t)sizeof(T);
       bytes[f] = len & ~15u; src[f] = base + s0; tot += bytes[f];
@@ -823,7 +829,8 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
 #pragma unroll
       for (int f = 0; f < ONEVN_FB; ++f) {
         const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
-        const T* row = reinterpret_cast<const T*>(a.crd) + (size_t)fr * a.stride + (size_t)3 * at0;
+        const size_t rowI = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+        const T* row = reinterpret_cast<const T*>(a.crd) + rowI * a.stride + (size_t)3 * at0;
         o[f][0] = (double)row[0]; o[f][1] = (double)row[1]; o[f][2] = (double)row[2];
         if (tid == 0) { oS[f][0] = o[f][0]; oS[f][1] = o[f][1]; oS[f][2] = o[f][2]; }   // read after the group's barriers
 #pragma unroll
@@ -839,7 +846,8 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
 #pragma unroll
     for (int f = 0; f < ONEVN_FB; ++f) {
       const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
-      const size_t off = ((size_t)fr * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
+      const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+      const size_t off = (row * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
       fp[f] = reinterpret_cast<const T*>(sbuf + f * ONEVN_S_BUF_BYTES + (off & 15));
     }
     const double4* sref = reinterpret_cast<const double4*>(sbuf + ONEVN_S_REF_OFF);
@@ -913,6 +921,25 @@ __global__ void __launch_bounds__(128) onevn_finish_kernel(const double* rec, co
     trans[3 * (size_t)fr + 1] = -(cy + v[14]);
     trans[3 * (size_t)fr + 2] = -(cz + v[15]);
   }
+}
+
+/// Frame-to-centroid distances: dist[k * nFrames + f] (one column per centroid, as the one-vs-many passes wrote them)
+/// -> nearest centroid per frame (first minimum wins, as List::AddFramesByCentroid's `dist < mindist`,
+/// src/Cluster/List.cpp:183-189) and, optionally, the frame-major table distOut[f * K + k].
+__global__ void __launch_bounds__(256) centroid_argmin_kernel(const double* dist, int nFrames, int K, double* distOut, int* closest,
+                                                              double* closestDist) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nFrames) return;
+  double best = dist[f];
+  int bk = 0;
+  if (distOut) distOut[(size_t)f * K] = best;
+  for (int k = 1; k < K; ++k) {
+    const double d = dist[(size_t)k * nFrames + f];
+    if (distOut) distOut[(size_t)f * K + k] = d;
+    if (d < best) { best = d; bk = k; }
+  }
+  if (closest) closest[f] = bk;
+  if (closestDist) closestDist[f] = best;
 }
 
 /// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One warp.

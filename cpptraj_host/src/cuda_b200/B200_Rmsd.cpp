@@ -69,6 +69,31 @@ int Cpptraj::B200::CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask
   return 0;
 }
 
+int Cpptraj::B200::ClosestCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+                                    bool fit, Cluster::Cframes const& frames,
+                                    std::vector<Frame const*> const& centroidFrames,
+                                    std::vector<int>& closest, std::vector<double>& closestDist)
+{
+  if (Init()) return 1;
+  closest.assign(frames.size(), -1);
+  closestDist.assign(frames.size(), 0.0);
+  if (frames.size() < 1 || centroidFrames.empty()) return 0;
+  const size_t n3 = (size_t)3 * (size_t)mask.Nselected();
+  std::vector<double> cen( centroidFrames.size() * n3 );
+  for (size_t k = 0; k != centroidFrames.size(); k++) {
+    if (centroidFrames[k]->Natom() != mask.Nselected()) {
+      mprinterr("Error: B200 RMSD: centroid %zu has %i atoms, mask selects %i\n", k, centroidFrames[k]->Natom(), mask.Nselected());
+      return 1;
+    }
+    std::copy(centroidFrames[k]->xAddress(), centroidFrames[k]->xAddress() + n3, cen.begin() + k * n3);
+  }
+  if (b200_rmsd_frames_to_centroids(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &(*frames.begin()), (int)frames.size(),
+                                    &mask.Selected()[0], mask.Nselected(), ptr_or_null(mass), fit ? 1 : 0,
+                                    &cen[0], (int)centroidFrames.size(), 0, &closest[0], &closestDist[0]))
+    return b200_err("frame-centroid distances");
+  return 0;
+}
+
 // -----------------------------------------------------------------------------
 Cpptraj::B200::Rmsd1vN::~Rmsd1vN() { if (handle_ != 0) b200_rmsd_1vN_end(handle_); }
 

@@ -33,6 +33,14 @@ int Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask, std::vector<do
   */
 int CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
               bool fit, Cluster::Cframes const& framesToCache, float* triangle);
+/** Frame-to-centroid RMSDs for a single Metric_RMS (Metric_RMS::FrameCentroidDist, Cluster/Metric_RMS.cpp:75-81), all
+  * frames of \a frames at once: the body of List::AddFramesByCentroid (Cluster/List.cpp:160-207) and of the k-means
+  * assignment step.  \a centroidFrames: Centroid_Coord::Cframe() of every cluster, in cluster order.
+  * \a closest receives, per frame, the index of the nearest centroid (first minimum wins).
+  */
+int ClosestCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
+                     Cluster::Cframes const& frames, std::vector<Frame const*> const& centroidFrames,
+                     std::vector<int>& closest, std::vector<double>& closestDist);
 /** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417) when coordinates are not modified (nomod / nofit):
   * the selected atoms of every frame (Action_Rmsd::tgtFrame_ after SetCoordinates) are buffered on the host and
   * pushed to the device in batches; results are appended to the DataSet in frame order at Flush().

@@ -115,6 +115,20 @@ int b200_rmsd_1vN_flush(b200_1vN* h, double* rmsdOut, double* rotOut, double* tr
                         long* argminFrame);
 int b200_rmsd_1vN_end(b200_1vN* h);
 
+/* ---- cluster: frame-to-centroid distances ----------------------------------------
+ * Metric_RMS::FrameCentroidDist (src/Cluster/Metric_RMS.cpp:75-81) for many frames at once: the consumers are the
+ * sieve restore List::AddFramesByCentroid (src/Cluster/List.cpp:160-207), k-means assignment
+ * (src/Cluster/Algorithm_Kmeans.cpp:223,298) and the representative-frame search.  centroids: nCentroids x 3*nAtoms
+ * doubles, the selected atoms of each Centroid_Coord::Cframe() (already centred on the origin when fitting, as cpptraj
+ * keeps them).  frameIdx (nullable) lists the frames, e.g. the sieved-out ones.  Outputs (each nullable):
+ * distOut[f*nCentroids + k]; closestOut[f] = nearest centroid, first minimum wins (List.cpp:183-189);
+ * closestDistOut[f] its distance.  Runs on device 0. */
+int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal,
+                                  const int* frameIdx, int nFrames,
+                                  const int* atomIdx, int nAtoms, const double* mass, int fit,
+                                  const double* centroids, int nCentroids,
+                                  double* distOut, int* closestOut, double* closestDistOut);
+
 /* ---- device-resident variants (benchmarks, pipelines that keep COORDS in HBM)
  * All pointers are DEVICE pointers on the current device; `stream` is a
  * cudaStream_t (NULL = default stream); asynchronous w.r.t. the host.

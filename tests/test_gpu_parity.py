@@ -301,3 +301,35 @@ def test_config2_full_size_properties(b200, oracle):
     P, Q = perm[pi].astype(np.int64), perm[pj].astype(np.int64)
     lo, hi = np.minimum(P, Q), np.maximum(P, Q)
     assert maxdiff(a, out[nf * lo - (lo + 1) * lo // 2 + hi - lo - 1]) <= 2e-6
+
+
+@pytest.mark.parametrize("fit,use_mass", [(True, False), (True, True), (False, False)])
+def test_frames_to_centroids(b200, oracle, fit, use_mass):
+    """SURVEY 8(f) rank 1: Metric_RMS::FrameCentroidDist for many frames (src/Cluster/Metric_RMS.cpp:75-81) and the nearest
+    centroid per frame as List::AddFramesByCentroid picks it (first minimum wins, src/Cluster/List.cpp:183-189)."""
+    c, m, sel = synth_case(4242, 301, 150, 170, 3)
+    mass = m[sel] if use_mass else None
+    K = 5
+    # centroids: selected atoms of a few frames, averaged with a neighbour and centred (cpptraj keeps centroids at the origin)
+    X = c[:, : 3 * 170].reshape(301, 170, 3)[:, sel].astype(np.float64)
+    w = np.ones(len(sel)) if mass is None else mass
+    cen = []
+    for k in range(K):
+        a = 0.5 * (X[40 * k] + X[40 * k + 1])
+        if fit:
+            a = a - (w[:, None] * a).sum(0) / w.sum()
+        cen.append(a)
+    cen = np.array(cen)
+    fidx = np.arange(2, 301, 2, dtype=np.int32)[::-1].copy()          # a sieved, unordered frame list
+    for frame_idx in (None, fidx):
+        dist, closest, cdist = b200.frames_to_centroids(c, sel, cen, mass=mass, fit=fit, frame_idx=frame_idx)
+        frames = c if frame_idx is None else c[frame_idx]
+        want = np.stack([oracle.rmsd_1vN(frames, sel, cen[k], mass=mass, fit=fit) for k in range(K)], axis=1)
+        assert dist.shape == want.shape
+        assert np.abs(dist - want).max() <= TOL
+        assert np.abs(cdist - want.min(1)).max() <= TOL
+        # nearest centroid: exact where the two best are separated by more than the tolerance
+        srt = np.sort(want, axis=1)
+        clear = (srt[:, 1] - srt[:, 0]) > 2 * TOL
+        assert np.array_equal(closest[clear], want.argmin(1)[clear])
+        assert np.array_equal(closest, dist.argmin(1))               # first minimum of the table it returned
