@@ -214,51 +214,6 @@ __device__ __forceinline__ double largest_root(const Quartic& q, double e0, cons
   if (!converged || fabs(dP) < 7e-3 * fabs(lam * lam * lam)) lam = lambda_by_svd(S);
   return lam;
 }
-/// Latency-lean solve for the tcgen05 epilogue (FP64 instructions have a long dependent-issue latency on
-/// this part, so the FP64 chain is kept as short as the cancellation allows).  With everything divided by E0
-/// the key-matrix quartic becomes P(x) = x^4 + c2 x^2 + c1 x + c0 with the wanted root x = lambda/E0 in (0,1];
-/// substituting x = 1 - y gives
-///     Q(y) = y^4 - 4 y^3 + (6 + c2) y^2 - (4 + 2 c2 + c1) y + (1 + c2 + c1 + c0),
-/// whose smallest non-negative root y = (E0 - lambda)/E0 is the quantity the RMSD needs.  Only the coefficients
-/// (q0 is a cancellation down to ~y) and ONE Newton correction are FP64; the approach to the root (monotone
-/// from y = 0) runs in FP32, which resolves y to ~1e-7 RELATIVE whatever its magnitude.  Returns false when the
-/// root is ill-conditioned or the correction is not small: the caller then takes the guarded FP64 path.
-__device__ __forceinline__ bool relative_gap_fast(const double* S, double e0, double& gap) {
-  const double s = 1.0 / e0;
-  double T[9];
-#pragma unroll
-  for (int x = 0; x < 9; ++x) T[x] = S[x] * s;
-  const double m00 = T[0] * T[0] + T[3] * T[3] + T[6] * T[6];
-  const double m11 = T[1] * T[1] + T[4] * T[4] + T[7] * T[7];
-  const double m22 = T[2] * T[2] + T[5] * T[5] + T[8] * T[8];
-  const double m01 = T[0] * T[1] + T[3] * T[4] + T[6] * T[7];
-  const double m02 = T[0] * T[2] + T[3] * T[5] + T[6] * T[8];
-  const double m12 = T[1] * T[2] + T[4] * T[5] + T[7] * T[8];
-  const double p1 = (m00 + m11) + m22;
-  const double trM2 = (m00 * m00 + m11 * m11) + (m22 * m22 + 2.0 * (m01 * m01 + (m02 * m02 + m12 * m12)));
-  const double det = T[0] * (T[4] * T[8] - T[5] * T[7]) - T[1] * (T[3] * T[8] - T[5] * T[6]) +
-                     T[2] * (T[3] * T[7] - T[4] * T[6]);
-  const double c2 = -2.0 * p1, c1 = -8.0 * det, c0 = 2.0 * trM2 - p1 * p1;
-  const double q0 = ((1.0 + c2) + c1) + c0;
-  const double q1 = -((4.0 + 2.0 * c2) + c1);
-  const double q2 = 6.0 + c2;
-  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2;
-  float y = 0.f, dq = f1;
-#pragma unroll
-  for (int it = 0; it < 10; ++it) {   // ~45 cycles each; 10 cover gaps up to y ~ 0.5 (RMSD ~ radius of gyration)
-    const float qy = (((y - 4.f) * y + f2) * y + f1) * y + f0;
-    dq = ((4.f * y - 12.f) * y + 2.f * f2) * y + f1;
-    y -= __fdividef(qy, dq);
-  }
-  double yd = (double)y;
-  const double Q = (((yd - 4.0) * yd + q2) * yd + q1) * yd + q0;
-  dq = ((4.f * y - 12.f) * y + 2.f * f2) * y + f1;
-  const double d = Q * (double)__frcp_rn(dq);
-  yd -= d;
-  gap = yd;
-  // conditioning (|P'| relative to lambda^3 = 1 here) and size of the correction (FP32 left ~1e-7 relative)
-  return (fabsf(dq) >= 7e-3f) && (fabs(d) <= 1e-5 * fabs(yd) + 1e-14) && (yd < 1.5);
-}
 /// Best-fit RMSD from the 3x3 covariance S, E0 = (Ga+Gb)/2 and total mass M.
 __device__ __forceinline__ double rmsd_fit_from_cov(const double* S, double e0, double invM) {
   const Quartic q = quartic_of(S);
