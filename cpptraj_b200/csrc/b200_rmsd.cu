@@ -538,6 +538,14 @@ int dev_rms2d_tri(Device& d, const float* d_crd, size_t stride, const int* d_fra
   if ((rc = prepare_tri(d, d_crd, stride, d_frameIdx, srcBase, nFrames, d_atomIdx, nAtoms, d_mass, fit, row0, st, tpack, plan)))
     return rc;
   if (bandRows <= 0) bandRows = 512;
+  // tcgen05 engine: size the band so that its row operands (9 bytes per atom and frame, padded) stay in L2 while the
+  // columns stream: ~38 MB (4096 rows at 1,000 atoms; measured against 2048 / 8192 / one launch per shard)
+  if (plan.i8) {
+    const double bytesPerFrame = (double)plan.q.nC * I8_BLK_BYTES / I8_FR_PER_RG;
+    const char* e = getenv("B200_I8_BAND_MB");
+    const double mb = e ? atof(e) : 38.4;
+    bandRows = std::max(512, (int)(mb * 1e6 / bytesPerFrame) / 512 * 512);
+  }
   // (one launch per shard was measured slower than 4096-row bands for the tcgen05 kernel: the row operands of a band,
   //  ~37 MB at 1000 atoms, stay in L2 while the columns stream)
   for (long i0l = row0; i0l < row1; i0l += bandRows) {
