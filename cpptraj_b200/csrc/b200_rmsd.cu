@@ -305,12 +305,13 @@ int i8_reserve(I8Set& S, DevBuf& img, DevBuf& G, DevBuf& cen, int nFrames, int n
 
 int i8_stats(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
              const int* d_atomIdx, int nAtoms, const double* d_centerMass, const double* d_covMass,
-             unsigned int* d_maxBits, cudaStream_t st) {
+             unsigned int* d_maxBits, cudaStream_t st, int fEnd = -1) {
+  if (fEnd < 0) fEnd = S.nFrames;
   I8StatsArgs a;
-  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = S.nFrames; a.f0 = f0;
+  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = fEnd; a.f0 = f0;
   a.atomIdx = d_atomIdx; a.nAtoms = nAtoms; a.centerMass = d_centerMass; a.covMass = d_covMass;
   a.centers = S.centers; a.maxAbsBits = d_maxBits;
-  const int nb = (S.nFrames - f0 + 7) / 8;
+  const int nb = (fEnd - f0 + 7) / 8;
   if (nb <= 0) return B200_OK;
   COUNT_LAUNCH();
   i8_stats_kernel<<<nb, 256, 0, st>>>(a);
@@ -318,16 +319,22 @@ int i8_stats(const I8Set& S, const float* d_crd, size_t stride, const int* d_fra
   return B200_OK;
 }
 
-int i8_quant(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
-             const int* d_atomIdx, int nAtoms, const double* d_covMass, int qs, cudaStream_t st) {
+/// Zero image and G (padding atoms, rows and frames must read as zeros) before the first i8_quant of a set.
+int i8_clear(const I8Set& S, cudaStream_t st) {
   CU(cudaMemsetAsync(S.image, 0, i8_image_bytes(S.nRg, S.nC), st));
   CU(cudaMemsetAsync(S.G, 0, (size_t)S.nRg * I8_FR_PER_RG * sizeof(double), st));
+  return B200_OK;
+}
+
+int i8_quant(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
+             const int* d_atomIdx, int nAtoms, const double* d_covMass, int qs, cudaStream_t st, int fEnd = -1) {
+  if (fEnd < 0) fEnd = S.nFrames;
   I8QuantArgs a;
-  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = S.nFrames; a.f0 = f0;
+  a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = fEnd; a.f0 = f0;
   a.atomIdx = d_atomIdx; a.nAtoms = nAtoms; a.nC = S.nC; a.covMass = d_covMass; a.centers = S.centers;
   a.scale = std::ldexp(1.0, qs); a.invScale2 = std::ldexp(1.0, -2 * qs);
   a.image = S.image; a.G = S.G;
-  const int nb = (S.nFrames - f0 + 7) / 8;
+  const int nb = (fEnd - f0 + 7) / 8;
   if (nb <= 0) return B200_OK;
   COUNT_LAUNCH();
   i8_quant_kernel<<<nb, 256, 0, st>>>(a);
@@ -496,6 +503,7 @@ int prepare_tri(Device& d, const float* d_crd, size_t stride, const int* d_frame
     bool ok = false;
     if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &plan.qs, &ok))) return rc;
     if (ok) {
+      if ((rc = i8_clear(plan.q, st))) return rc;
       if ((rc = i8_quant(plan.q, d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, nAtoms, d_mass, plan.qs, st))) return rc;
       plan.i8 = true;
     } else if (engine == 2) {
@@ -597,6 +605,148 @@ int validate_sel(const int* atomIdx, int nAtoms, size_t stride, int* maxAtom) {
   return B200_OK;
 }
 
+// Pipelined host path of the tcgen05 engine (pinned COORDS, no frame list).  Frames are uploaded from the END of the
+// trajectory towards the start, chunk by chunk.  Rows [a, b) of the triangle pair only with frames >= a, so as soon as a
+// chunk has landed and is quantised its band of rows can be computed and its slice of the triangle copied back while the
+// next chunk uploads: H2D, compute and D2H overlap (PCIe is full duplex) instead of upload -> compute/download.
+// The fixed-point scale must be known before the first chunk is quantised: it is taken from the first chunk's extent
+// with 25 % headroom, every later chunk keeps feeding the running maximum, and if at the end the headroom turned out
+// too small (or the scale leaves too few fractional bits) *done stays false and the caller runs the two-pass path.
+int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrames, const int* atomIdx, int nAtoms,
+                          const double* mass, int row0, int row1, float* outTri, bool* done) {
+  *done = false;
+  int maxAtom = 0, rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
+  const size_t F = (size_t)nFrames;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  const int f0 = (row0 / I8_TILE_J) * I8_TILE_J;           // first frame needed (tile aligned)
+  // chunk = band: <= 64 MB of output, a multiple of the 28-frame tile
+  int C = (int)std::min<size_t>(2016, std::max<size_t>(8 * I8_TILE_J, ((size_t)40 << 20) / (4 * F) / I8_TILE_J * I8_TILE_J));
+  { const char* e = getenv("B200_PIPE_ROWS"); if (e && atoi(e) >= I8_TILE_J) C = atoi(e) / I8_TILE_J * I8_TILE_J; }
+  cudaStream_t sIn = d.stream[0];
+  if ((rc = d.crd.reserve((size_t)(nFrames - f0) * width * sizeof(float)))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, sIn))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, sIn))) return rc;
+  const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
+  if ((rc = d.scal.reserve(64))) return rc;
+  double* d_total = (double*)d.scal.p;
+  unsigned int* d_maxBits = (unsigned int*)(d_total + 4);
+  COUNT_LAUNCH();
+  mass_sum_kernel<<<1, 32, 0, sIn>>>(d_mass, nAtoms, d_total);
+  CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), sIn));
+  I8Set q;
+  if ((rc = i8_reserve(q, d.imgA, d.GA, d.cenA, nFrames, nAtoms))) return rc;
+  if ((rc = i8_clear(q, sIn))) return rc;
+  // chunk list, last chunk of the trajectory first.  The first chunk to be uploaded (top of the trajectory) and the
+  // last bands to be computed (lowest rows = longest rows) are smaller: nothing overlaps the first upload and the
+  // last download.
+  struct Chunk { int fa, fb; };
+  std::vector<Chunk> chunks;
+  {
+    std::vector<int> bnd;   // ascending boundaries from f0
+    const int small = std::max(I8_TILE_J, C / 4 / I8_TILE_J * I8_TILE_J);
+    int at = f0, step = small;
+    while (at < nFrames) {
+      bnd.push_back(at);
+      at += step;
+      if (step < C) step = std::min(C, step + small);
+    }
+    // split a small piece off the top
+    if (nFrames - bnd.back() > 2 * small) bnd.push_back(std::max(bnd.back() + small, (nFrames - small) / I8_TILE_J * I8_TILE_J));
+    bnd.push_back(nFrames);
+    for (size_t i = bnd.size() - 1; i > 0; --i)
+      if (bnd[i] > bnd[i - 1]) chunks.push_back({bnd[i - 1], bnd[i]});
+  }
+  size_t maxChunk = 0;
+  for (const Chunk& c : chunks) {
+    const int lo = std::max(c.fa, row0), hi = std::min(c.fb, row1);
+    if (hi > lo) maxChunk = std::max(maxChunk, tri_row_start(F, hi) - tri_row_start(F, lo));
+  }
+  const bool pinnedOut = host_ptr_is_pinned(outTri);
+  for (int s = 1; s < NSLOT; ++s) {
+    if ((rc = d.outChunk[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
+    if (!pinnedOut && (rc = d.outStage[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
+  }
+  struct Pending { size_t base = 0, n = 0; bool live = false; } pend[NSLOT];
+  auto retire = [&](int s) -> int {
+    if (!pend[s].live) return B200_OK;
+    CU(cudaEventSynchronize(d.done[s]));
+    if (!pinnedOut) std::memcpy(outTri + pend[s].base, d.outStage[s].p, pend[s].n * sizeof(float));
+    pend[s].live = false;
+    return B200_OK;
+  };
+  std::vector<cudaEvent_t> evs;
+  auto cleanup = [&]() { for (cudaEvent_t e : evs) cudaEventDestroy(e); evs.clear(); };
+  const float* d_crd = (const float*)d.crd.p;
+  const long srcBase = (long)f0;      // row r of the device copy is frame f0 + r
+  Timer tpair;
+  double h2d = (double)nAtoms * 4 + (mass ? (double)nAtoms * 8 : 0), d2h = 0.0;
+  int qs = 0, band = 0;
+  long nLaunch = 0;
+  for (size_t k = 0; k < chunks.size(); ++k) {
+    const int fa = chunks[k].fa, fb = chunks[k].fb;
+    CU(cudaMemcpy2DAsync((float*)d.crd.p + (size_t)(fa - f0) * width, width * sizeof(float), crd + (size_t)fa * stride,
+                         stride * sizeof(float), width * sizeof(float), (size_t)(fb - fa), cudaMemcpyHostToDevice, sIn));
+    h2d += (double)(fb - fa) * width * sizeof(float);
+    if ((rc = i8_stats(q, d_crd, width, nullptr, srcBase, fa, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, sIn, fb))) { cleanup(); return rc; }
+    if (k == 0) {
+      // scale from the first chunk, with headroom for the frames not seen yet
+      if ((rc = d.hostScal.reserve(64))) { cleanup(); return rc; }
+      unsigned int* hBits = (unsigned int*)d.hostScal.p;
+      double* hTotal = (double*)((char*)d.hostScal.p + 8);
+      CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, sIn));
+      CU(cudaMemcpyAsync(hTotal, d_total, sizeof(double), cudaMemcpyDeviceToHost, sIn));
+      CU(cudaStreamSynchronize(sIn));
+      float mx;
+      std::memcpy(&mx, hBits, 4);
+      const double total = *hTotal;
+      if (!(total > 0.0) || !std::isfinite(mx) || !(mx > 0.f)) { cleanup(); return B200_OK; }
+      qs = std::min(30, (int)std::floor(std::log2((double)I8_QMAX / (1.25 * (double)mx))));
+      if (qs < 0 || i8_worst_error(qs, nAtoms, total) > I8_MAX_WORST_ERROR) { cleanup(); return B200_OK; }
+    }
+    if ((rc = i8_quant(q, d_crd, width, nullptr, srcBase, fa, (const int*)d.idxA.p, nAtoms, d_mass, qs, sIn, fb))) { cleanup(); return rc; }
+    const int lo = std::max(fa, row0), hi = std::min(fb, row1);
+    if (hi <= lo) continue;           // frames above this shard's rows: columns only
+    cudaEvent_t ev;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    evs.push_back(ev);
+    CU(cudaEventRecord(ev, sIn));
+    const int s = 1 + (band++ % (NSLOT - 1));
+    if ((rc = retire(s))) { cleanup(); return rc; }
+    cudaStream_t st = d.stream[s];
+    CU(cudaStreamWaitEvent(st, ev, 0));
+    const size_t base = tri_row_start(F, lo), n = tri_row_start(F, hi) - base;
+    tpair.begin(st);
+    if ((rc = run_pair_i8_band(d, q, q, lo, hi, true, qs, d_total, (float*)d.outChunk[s].p, base, 0, nullptr, st))) { cleanup(); return rc; }
+    tpair.end(st);
+    ++nLaunch;
+    if (n) {
+      float* dst = pinnedOut ? outTri + base : (float*)d.outStage[s].p;
+      CU(cudaMemcpyAsync(dst, d.outChunk[s].p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      d2h += (double)n * sizeof(float);
+    }
+    CU(cudaEventRecord(d.done[s], st));
+    pend[s].base = base; pend[s].n = n; pend[s].live = true;
+  }
+  // did the headroom hold?
+  {
+    unsigned int* hBits = (unsigned int*)d.hostScal.p;
+    CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, sIn));
+    CU(cudaStreamSynchronize(sIn));
+    for (int s = 1; s < NSLOT; ++s) if ((rc = retire(s))) { cleanup(); return rc; }
+    for (int s = 1; s < NSLOT; ++s) CU(cudaStreamSynchronize(d.stream[s]));
+    cleanup();
+    float mx;
+    std::memcpy(&mx, hBits, 4);
+    if (!((double)mx * std::ldexp(1.0, qs) <= (double)I8_QMAX)) return B200_OK;   // *done == false: two-pass path recomputes
+  }
+  const double pairs = (double)(tri_row_start(F, row1) - tri_row_start(F, row0));
+  add_stats(0.0, 1, tpair.resolve(), nLaunch, pairs, h2d, d2h);
+  g_lastEngine.store(2); g_lastQs.store(qs);
+  *done = true;
+  return B200_OK;
+}
+
 // One shard of the triangle on one device, host buffers.
 int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTotal, const int* frameIdx, int nFrames,
                        const int* atomIdx, int nAtoms, const double* mass, int fit, int row0, int row1, float* outTri) {
@@ -604,6 +754,15 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   if (row1 <= row0 || nFrames < 2) return B200_OK;
   int maxAtom = 0, rc;
   if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
+  {
+    const char* e = getenv("B200_HOST_PIPELINE");
+    if (fit && !frameIdx && pair_engine() != 1 && nFrames >= 1024 && nFrames <= nFramesTotal && !(e && atoi(e) == 0) &&
+        host_ptr_is_pinned(crd)) {
+      bool done = false;
+      if ((rc = host_tri_pipelined_i8(d, crd, stride, nFrames, atomIdx, nAtoms, mass, row0, row1, outTri, &done))) return rc;
+      if (done) return B200_OK;
+    }
+  }
   // source frame range needed by output frames [f0, nFrames) (f0: first frame either engine packs)
   const int f0 = std::min((row0 / ROWG) * ROWG, (row0 / I8_FR_PER_RG) * I8_FR_PER_RG);
   int sLo = f0, sHi = nFrames;
@@ -860,6 +1019,7 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
     if ((rc = i8_stats(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_maxBits, st0))) return rc;
     if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st0, &qs, &useI8))) return rc;
     if (useI8) {
+      if ((rc = i8_clear(qA, st0)) || (rc = i8_clear(qB, st0))) return rc;
       if ((rc = i8_quant(qA, (const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, dmT, qs, st0))) return rc;
       if ((rc = i8_quant(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmT, qs, st0))) return rc;
     } else if (engine == 2) {
@@ -1377,6 +1537,7 @@ int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames, const
   int qs = 0; bool ok = false;
   if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &qs, &ok))) return rc;
   if (qsOut) *qsOut = qs;
+  if ((rc = i8_clear(q, st))) return rc;
   if ((rc = i8_quant(q, (const float*)d.crd.p, width, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, d_mass, qs, st))) return rc;
   const size_t ib = i8_image_bytes(q.nRg, q.nC);
   if (imageBytes) *imageBytes = ib;

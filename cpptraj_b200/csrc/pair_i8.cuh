@@ -69,7 +69,7 @@ __host__ __device__ inline size_t i8_image_bytes(int nRowGroups, int nC) {
 // ----------------------------------------------------------------------------
 struct I8StatsArgs {
   const float* crd; size_t stride; const int* frameIdx; long srcBase;
-  int nFrames; int f0;
+  int nFrames; int f0;      // frames [f0, nFrames) of the set are processed by this launch
   const int* atomIdx; int nAtoms;
   const double* centerMass; const double* covMass;
   double* centers;          // 3 per frame

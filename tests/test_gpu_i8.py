@@ -184,3 +184,49 @@ def test_i8_matches_fp64_engine_on_config2_prefix(b200, oracle):
     want = oracle.rms2d_tri(crd[sub], sel)
     got = tri_to_square(b, 2000)[np.ix_(sub, sub)][np.triu_indices(len(sub), 1)]
     assert maxdiff(got, want) <= TOL
+
+
+def _pinned(a):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    return t, t.numpy()
+
+
+@pytest.mark.parametrize("nf,na", [(1500, 64), (3001, 130)])
+def test_pipelined_host_path_matches_two_pass(b200, oracle, nf, na, monkeypatch):
+    """Pinned COORDS take the pipelined host path (reverse-order chunk upload overlapped with compute and download, scale
+    fixed from the first chunk): it must give what the two-pass path gives (same rounding grid or one bit coarser), and
+    the oracle's values; shards included."""
+    c, m, sel = synth_case(900 + nf, nf, na, na + 7, 2)
+    keep, cp = _pinned(c)
+    b200.set_pair_engine("auto")
+    monkeypatch.setenv("B200_HOST_PIPELINE", "0")
+    two_pass = b200.rms2d_tri(cp, sel, mass=m[sel])
+    assert b200.last_pair_engine()[0] == 2
+    monkeypatch.setenv("B200_HOST_PIPELINE", "1")
+    piped = b200.rms2d_tri(cp, sel, mass=m[sel])
+    assert b200.last_pair_engine()[0] == 2
+    assert maxdiff(piped, two_pass) <= 5e-5
+    sub = np.r_[0:30, nf // 2:nf // 2 + 30, nf - 30:nf]
+    want = oracle.rms2d_tri(c[sub], sel, mass=m[sel])
+    got = tri_to_square(piped, nf)[np.ix_(sub, sub)][np.triu_indices(len(sub), 1)]
+    assert maxdiff(got, want) <= TOL
+    whole = np.zeros_like(piped)
+    for r in range(3):
+        part, first, n = b200.rms2d_tri_shard(cp, sel, r, 3, mass=m[sel])
+        whole[first:first + n] = part[first:first + n]
+    assert np.array_equal(whole, piped)
+
+
+def test_pipelined_host_path_headroom_fallback(b200, oracle, monkeypatch):
+    """The last frames (uploaded first) are compact, earlier ones 3x more extended: the scale guessed from the first chunk
+    does not hold, the call must notice and recompute on the two-pass path."""
+    c, m, sel = synth_case(31, 2200, 40)
+    X = c.reshape(2200, -1, 3)
+    X[:600] = (X[:600] - X[:600].mean(1, keepdims=True)) * 3.0 + X[:600].mean(1, keepdims=True)
+    keep, cp = _pinned(X.reshape(2200, -1))
+    monkeypatch.setenv("B200_HOST_PIPELINE", "1")
+    got = b200.rms2d_tri(cp, sel)
+    sub = np.r_[0:25, 590:615, 2175:2200]
+    want = oracle.rms2d_tri(cp[sub], sel)
+    assert maxdiff(tri_to_square(got, 2200)[np.ix_(sub, sub)][np.triu_indices(len(sub), 1)], want) <= TOL
