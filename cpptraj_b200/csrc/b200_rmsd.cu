@@ -1166,7 +1166,7 @@ static int onevn_grow(b200_1vN* h, long need) {
 /// when the streaming variant did the work (the choice is made on the device: no host round trip).
 /// ws: workspace of at least onevn_ws_bytes() bytes.
 static size_t onevn_ws_bytes(size_t stride, int nFrames) {
-  const size_t maxChunks = stride / 3 / (ONEVN_S_CHUNK_BYTES / 24) + 2;
+  const size_t maxChunks = stride / 3 / (ONEVN_S_CHUNK_BYTES / 24) + 2;   // (double frames: the smaller chunk)
   return 64 + (maxChunks + 1) * sizeof(int) + 64 + (size_t)nFrames * ONEVN_REC * sizeof(double);
 }
 template <typename T>
@@ -1197,7 +1197,7 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
     sa.refw = refw; sa.hdr = hdr; sa.kLo = kLo; sa.fit = fit; sa.rec = rec;
     const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
     COUNT_LAUNCH();
-    onevn_stream_kernel<T><<<std::min(nGroups, numSMs > 0 ? numSMs : 148), ONEVN_THREADS, ONEVN_S_SMEM_BYTES, st>>>(sa);
+    onevn_stream_kernel<T><<<std::min(nGroups, numSMs > 0 ? numSMs : 148), ONEVN_S_THREADS, ONEVN_S_SMEM_BYTES, st>>>(sa);
     COUNT_LAUNCH();
     onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
   }
@@ -1253,7 +1253,7 @@ int b200_rmsd_1vN_begin(const double* refSelected, const int* atomIdx, int nAtom
   if ((rc = h->refw.reserve((size_t)nAtoms * 32))) { delete h; return rc; }
   if ((rc = h->refsum.reserve(64))) { delete h; return rc; }
   COUNT_LAUNCH();
-  onevn_setup_kernel<<<1, 32, 0, h->st>>>((const double*)ref.p, mass ? (const double*)m.p : nullptr, nAtoms, (double*)h->refw.p,
+  onevn_setup_kernel<<<1, 256, 0, h->st>>>((const double*)ref.p, mass ? (const double*)m.p : nullptr, nAtoms, (double*)h->refw.p,
                                           (double*)h->refsum.p);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(h->st));
@@ -1384,7 +1384,7 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   double* refw = (double*)d->onevnWs.p;
   double* refsum = refw + (size_t)4 * nAtoms;
   COUNT_LAUNCH();
-  onevn_setup_kernel<<<1, 32, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum);
+  onevn_setup_kernel<<<1, 256, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum);
   Timer t;
   if (g_profiling) t.begin(st);
   rc = onevn_run<float>(d->numSMs, d_crd, frameStrideFloats, nFrames, d_atomIdx, nAtoms, refw, refsum, fit ? 1 : 0, d_rmsdOut,
@@ -1451,7 +1451,7 @@ int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, in
   t.begin(st);
   for (int k = 0; k < nCentroids; ++k) {
     COUNT_LAUNCH();
-    onevn_setup_kernel<<<1, 32, 0, st>>>((const double*)cen.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
+    onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)cen.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
     if ((rc = onevn_run<float>(d.numSMs, d.crd.p, width, nFrames, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
                                dist + (size_t)k * nFrames, nullptr, nullptr, ws, st,
                                frameIdx ? (const int*)d.frameIdx.p : nullptr, (long)sLo))) { cen.release(); return rc; }

@@ -648,7 +648,7 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
 // 16-byte aligned COORDS base; the host checks the alignment, the device the order (hdr[2]), and onevn_kernel
 // remains the general path.
 // ----------------------------------------------------------------------------
-constexpr int ONEVN_S_STAGES = 2;
+constexpr int ONEVN_S_STAGES = 2;                                // (5 stages of half the size measured slower: per-step costs dominate)
 constexpr int ONEVN_S_CHUNK_BYTES = 12288;                       // per frame and stage
 constexpr int ONEVN_S_BUF_BYTES = ONEVN_S_CHUNK_BYTES + 32;      // + alignment slack at both ends
 constexpr int ONEVN_S_MAX_APC = ONEVN_S_CHUNK_BYTES / 12;        // selected atoms a chunk can hold (float frames)
@@ -705,15 +705,19 @@ __global__ void __launch_bounds__(256) onevn_chunks_kernel(const int* atomIdx, i
   }
 }
 
+constexpr int ONEVN_S_THREADS = 2 * ONEVN_THREADS;   // 16 warps: threads [0,256) take frames 0,1 of the stage, [256,512) frames 2,3
+constexpr int ONEVN_S_FT = ONEVN_FB / 2;             // frames per thread (more warps per scheduler hide the FP64 / LDS latencies)
+
 template <typename T>
-__global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStreamArgs a) {
+__global__ void __launch_bounds__(ONEVN_S_THREADS, 1) onevn_stream_kernel(OneVNStreamArgs a) {
   if (a.hdr[2] == 0) return;   // selection not sorted: onevn_kernel (launched next) does the work
   constexpr int APC = ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));   // atoms per chunk
   extern __shared__ __align__(128) unsigned char smem_ov[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_ov + ONEVN_S_STAGES * ONEVN_S_STAGE_BYTES);
-  __shared__ double red[ONEVN_THREADS / 32][ONEVN_FB][13];
+  __shared__ double red[ONEVN_S_THREADS / 32][ONEVN_S_FT][13];
   __shared__ double oS[ONEVN_FB][3];   // origin shifts of the current frame group (for the records; `o` stays in registers)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = tid / ONEVN_THREADS, tk = tid % ONEVN_THREADS;   // frame pair of this thread, index within the pair's 256 threads
   const int a0 = a.hdr[0], nCh = a.hdr[1];
   const int nGroups = (a.nFrames + ONEVN_FB - 1) / ONEVN_FB;
   const int myGroups = ((int)blockIdx.x < nGroups) ? (nGroups - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -728,53 +732,50 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
 
   // Producer side (thread 0): stage `step` of this CTA's sequence.  Bytes below a 16-byte boundary at the end of a
   // chunk (at most 3 floats) are copied with ordinary loads; the barrier at the end of every step orders them.
+  // Whole warp 0: lanes 0..3 copy one frame's chunk each, lane 4 the reference atoms, lane 5 the atom numbers (a 1-D
+  // bulk copy costs ~225 cycles of issue whatever its size: six lanes issue side by side instead of one after the other).
   auto issue = [&](long step) {
     const int g = (int)blockIdx.x + (int)(step / nCh) * (int)gridDim.x;
     const int c = (int)(step % nCh);
     const int st = (int)(step % ONEVN_S_STAGES);
     const int nAt = min(APC, spanAtoms - c * APC);
     unsigned char* sbuf = smem_ov + st * ONEVN_S_STAGE_BYTES;
-    uint32_t bytes[ONEVN_FB], tot = 0;
-    const unsigned char* src[ONEVN_FB];
-#pragma unroll
-    for (int f = 0; f < ONEVN_FB; ++f) {
-      const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+    const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
+    uint32_t bytes = 0, len = 0, dstOff = 0;
+    const unsigned char* src = nullptr;
+    if (lane < ONEVN_FB) {
+      const int fr = min(g * ONEVN_FB + lane, a.nFrames - 1);
       const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
       const size_t off = (row * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
       const size_t s0 = off & ~(size_t)15;
-      const uint32_t len = (uint32_t)(off - s0) + (uint32_t)nAt * 3u * (uint32_t)sizeof(T);
-      bytes[f] = len & ~15u; src[f] = base + s0; tot += bytes[f];
-      for (uint32_t t = bytes[f]; t < len; t += 4)   // tail: whole 4-byte words
-        *reinterpret_cast<uint32_t*>(sbuf + f * ONEVN_S_BUF_BYTES + t) = *reinterpret_cast<const uint32_t*>(base + s0 + t);
-    }
-    // reference atoms and atom numbers of the chunk's selected atoms [kLo[c], kLo[c+1])
-    const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
-    const uint32_t refBytes = (uint32_t)nSel * 32u;
-    uint32_t idxBytes = 0;
-    const unsigned char* idxSrc = nullptr;
-    if (a.atomIdx && nSel > 0) {
+      len = (uint32_t)(off - s0) + (uint32_t)nAt * 3u * (uint32_t)sizeof(T);
+      src = base + s0; dstOff = (uint32_t)lane * ONEVN_S_BUF_BYTES;
+    } else if (lane == ONEVN_FB) {
+      len = (uint32_t)nSel * 32u;
+      src = reinterpret_cast<const unsigned char*>(a.refw) + (size_t)kA * 32; dstOff = ONEVN_S_REF_OFF;
+    } else if (lane == ONEVN_FB + 1 && a.atomIdx && nSel > 0) {
       const size_t off = (size_t)kA * 4, s0 = off & ~(size_t)15;
-      const uint32_t len = (uint32_t)(off - s0) + (uint32_t)nSel * 4u;
-      idxBytes = len & ~15u; idxSrc = reinterpret_cast<const unsigned char*>(a.atomIdx) + s0;
-      for (uint32_t t = idxBytes; t < len; t += 4)
-        *reinterpret_cast<uint32_t*>(sbuf + ONEVN_S_IDX_OFF + t) = *reinterpret_cast<const uint32_t*>(idxSrc + t);
+      len = (uint32_t)(off - s0) + (uint32_t)nSel * 4u;
+      src = reinterpret_cast<const unsigned char*>(a.atomIdx) + s0; dstOff = ONEVN_S_IDX_OFF;
     }
-    tot += refBytes + idxBytes;
-    const uint32_t bar = smem_u32(&full[st]);
-    mbar_expect_tx(bar, tot);
-    if (refBytes) bulk_g2s(smem_u32(sbuf + ONEVN_S_REF_OFF), reinterpret_cast<const unsigned char*>(a.refw) + (size_t)kA * 32, refBytes, bar);
-    if (idxBytes) bulk_g2s(smem_u32(sbuf + ONEVN_S_IDX_OFF), idxSrc, idxBytes, bar);
+    bytes = len & ~15u;
+    for (uint32_t t = bytes; t < len; t += 4)   // tail below a 16-byte boundary: whole 4-byte words, ordinary loads
+      *reinterpret_cast<uint32_t*>(sbuf + dstOff + t) = *reinterpret_cast<const uint32_t*>(src + t);
+    uint32_t tot = bytes;
 #pragma unroll
-    for (int f = 0; f < ONEVN_FB; ++f)
-      if (bytes[f]) bulk_g2s(smem_u32(sbuf + f * ONEVN_S_BUF_BYTES), src[f], bytes[f], bar);
-    if (tot == 0) { /* nothing to land: the expect_tx arrive alone completes the phase */ }
+    for (int o2 = 4; o2 > 0; o2 >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o2);   // lanes 0..7 hold the sum of lanes 0..7
+    const uint32_t bar = smem_u32(&full[st]);
+    if (lane == 0) mbar_expect_tx(bar, tot);
+    __syncwarp();
+    if (bytes) bulk_g2s(smem_u32(sbuf + dstOff), src, bytes, bar);
+    __syncwarp();
   };
-  if (tid == 0)
+  if (warp == 0)
     for (long s = 0; s < ONEVN_S_STAGES - 1 && s < total; ++s) issue(s);
   __syncthreads();   // the producer's ordinary (tail) stores of the first stages are visible to everyone
 
-  double acc[ONEVN_FB][13];
-  double o[ONEVN_FB][3];
+  double acc[ONEVN_S_FT][13];
+  double o[ONEVN_S_FT][3];
   for (long step = 0; step < total; ++step) {
     const int gi = (int)(step / nCh), c = (int)(step % nCh);
     const int g = (int)blockIdx.x + gi * (int)gridDim.x;
@@ -782,36 +783,36 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
     if (c == 0) {
       const int at0 = a.atomIdx ? a.atomIdx[0] : 0;
 #pragma unroll
-      for (int f = 0; f < ONEVN_FB; ++f) {
-        const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+      for (int f = 0; f < ONEVN_S_FT; ++f) {
+        const int fr = min(g * ONEVN_FB + ONEVN_S_FT * half + f, a.nFrames - 1);
         const size_t rowI = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
         const T* row = reinterpret_cast<const T*>(a.crd) + rowI * a.stride + (size_t)3 * at0;
         o[f][0] = (double)row[0]; o[f][1] = (double)row[1]; o[f][2] = (double)row[2];
-        if (tid == 0) { oS[f][0] = o[f][0]; oS[f][1] = o[f][1]; oS[f][2] = o[f][2]; }   // read after the group's barriers
+        if (tk == 0) { oS[ONEVN_S_FT * half + f][0] = o[f][0]; oS[ONEVN_S_FT * half + f][1] = o[f][1]; oS[ONEVN_S_FT * half + f][2] = o[f][2]; }   // read after the group's barriers
 #pragma unroll
         for (int x = 0; x < 13; ++x) acc[f][x] = 0.0;
       }
     }
-    if (tid == 0 && step + ONEVN_S_STAGES - 1 < total) issue(step + ONEVN_S_STAGES - 1);
+    if (warp == 0 && step + ONEVN_S_STAGES - 1 < total) issue(step + ONEVN_S_STAGES - 1);
     const int chunkA0 = a0 + c * APC;
     const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
     mbar_wait(smem_u32(&full[st]), (uint32_t)((step / ONEVN_S_STAGES) & 1));
     const unsigned char* sbuf = smem_ov + st * ONEVN_S_STAGE_BYTES;
-    const T* fp[ONEVN_FB];
+    const T* fp[ONEVN_S_FT];
 #pragma unroll
-    for (int f = 0; f < ONEVN_FB; ++f) {
-      const int fr = min(g * ONEVN_FB + f, a.nFrames - 1);
+    for (int f = 0; f < ONEVN_S_FT; ++f) {
+      const int fr = min(g * ONEVN_FB + ONEVN_S_FT * half + f, a.nFrames - 1);
       const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
       const size_t off = (row * a.stride + (size_t)3 * ((size_t)a0 + (size_t)c * APC)) * sizeof(T);
-      fp[f] = reinterpret_cast<const T*>(sbuf + f * ONEVN_S_BUF_BYTES + (off & 15));
+      fp[f] = reinterpret_cast<const T*>(sbuf + (ONEVN_S_FT * half + f) * ONEVN_S_BUF_BYTES + (off & 15));
     }
     const double4* sref = reinterpret_cast<const double4*>(sbuf + ONEVN_S_REF_OFF);
     const int* sidx = reinterpret_cast<const int*>(sbuf + ONEVN_S_IDX_OFF + (((size_t)kA * 4) & 15));
-    for (int kk = tid; kk < nSel; kk += ONEVN_THREADS) {
+    for (int kk = tk; kk < nSel; kk += ONEVN_THREADS) {
       const int at = (a.atomIdx ? sidx[kk] : kA + kk) - chunkA0;
       const double4 rw = sref[kk];
 #pragma unroll
-      for (int f = 0; f < ONEVN_FB; ++f) {
+      for (int f = 0; f < ONEVN_S_FT; ++f) {
         const T* p = fp[f] + 3 * at;
         if (a.fit) {
           const double x = (double)p[0] - o[f][0], y = (double)p[1] - o[f][1], z = (double)p[2] - o[f][2];
@@ -830,7 +831,7 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
     if (c == nCh - 1) {   // frame group complete: block reduction, one record per frame
       const int nred = a.fit ? 13 : 1;
 #pragma unroll
-      for (int f = 0; f < ONEVN_FB; ++f)
+      for (int f = 0; f < ONEVN_S_FT; ++f)
         for (int x = 0; x < nred; ++x) {
           const double v = warp_sum(acc[f][x]);
           if (lane == 0) red[warp][f][x] = v;
@@ -840,7 +841,10 @@ __global__ void __launch_bounds__(ONEVN_THREADS, 1) onevn_stream_kernel(OneVNStr
         const int f = tid / ONEVN_REC, x = tid % ONEVN_REC, fr = g * ONEVN_FB + f;
         if (fr < a.nFrames) {
           double v = 0.0;
-          if (x < nred) { for (int w = 0; w < ONEVN_THREADS / 32; ++w) v += red[w][f][x]; }
+          if (x < nred) {   // the 8 warps of the half that owns frame f
+            const int w0 = (f / ONEVN_S_FT) * (ONEVN_THREADS / 32);
+            for (int w = 0; w < ONEVN_THREADS / 32; ++w) v += red[w0 + w][f % ONEVN_S_FT][x];
+          }
           else if (x >= 13) v = oS[f][x - 13];
           a.rec[(size_t)fr * ONEVN_REC + x] = v;
         }
@@ -897,17 +901,25 @@ __global__ void __launch_bounds__(256) centroid_argmin_kernel(const double* dist
   if (closestDist) closestDist[f] = best;
 }
 
-/// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One warp.
-__global__ void onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum) {
+/// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One block.
+__global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum) {
+  __shared__ double part[8][5];
   double s0 = 0, s1 = 0, s2 = 0, sm = 0, sg = 0;
-  for (int k = threadIdx.x; k < n; k += 32) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const double m = mass ? mass[k] : 1.0;
     const double x = ref[3 * k], y = ref[3 * k + 1], z = ref[3 * k + 2];
     refw[4 * k] = x; refw[4 * k + 1] = y; refw[4 * k + 2] = z; refw[4 * k + 3] = m;
     s0 += m * x; s1 += m * y; s2 += m * z; sm += m; sg += m * (x * x + y * y + z * z);
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sm = warp_sum(sm); sg = warp_sum(sg);
-  if (threadIdx.x == 0) { refsum[0] = s0; refsum[1] = s1; refsum[2] = s2; refsum[3] = sm; refsum[4] = sg; }
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) { part[w][0] = s0; part[w][1] = s1; part[w][2] = s2; part[w][3] = sm; part[w][4] = sg; }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double t = 0.0;
+    for (int i = 0; i < nw; ++i) t += part[i][threadIdx.x];   // fixed order: deterministic
+    refsum[threadIdx.x] = t;
+  }
 }
 
 // ----------------------------------------------------------------------------
