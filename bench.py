@@ -292,8 +292,8 @@ def main():
         flop_per_launch = 18.0 * nA * (stt["pairs"] / launches)       # algorithmic: SURVEY 8(d), 18*N per fitted pair
         achieved = flop_per_launch / (ms_per_launch * 1e-3) / 1e12 if ms_per_launch > 0 else 0.0
         # dram__bytes_read + dram__bytes_write of one launch of the dominant kernel, from the committed ncu --set full
-        # capture of this exact workload (profiles/r1d_pair_i8_kernel.md: 55.9 MB + 45.6 MB); null for other shapes
-        traffic = 101.5e6 if (engine == 2 and name == "cfg2" and world == 1) else None
+        # capture of this exact workload (profiles/r1d_pair_i8_kernel.md: 56.0 MB + 45.7 MB); null for other shapes
+        traffic = 101.7e6 if (engine == 2 and name == "cfg2" and world == 1) else None
         r = {"bound": "tensor", "achieved": achieved, "unit": "TFLOP/s", "traffic": traffic,
              "launches": int(stt["pair_launches"]), "avg_launch_ms": ms_per_launch,
              "kernel_share_of_step": stt["pair_ms"] / own_ms if own_ms > 0 else None}
