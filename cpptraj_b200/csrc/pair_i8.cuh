@@ -452,7 +452,8 @@ __device__ __forceinline__ double i8_scale2(double v, int e) {
 struct I8Pending {
   double q0, q1, q2, q3;   // quartic in y' = y / 2^k (coefficients O(1)); leading coefficient 1
   double unit;             // r2 = y' * unit  (unit = 2^k * 2/M in integer units); or the final r2 when `final`
-  float y, dq;             // FP32 root estimate and Q'(y)
+  double yd, rdq;          // FP32 root estimate and 1/Q'(y), already converted (the conversions stay out of the FP64 window)
+  float dq;
   bool final;              // the guarded FP64 path already produced r2 (ill-conditioned root)
 };
 /// FP32 part: exponent scaling on the integer pipe, monotone Newton approach from y' = 0 (resolves y' to ~1e-7
@@ -482,8 +483,9 @@ __device__ __forceinline__ bool i8_root_start(const I8Quartic& c, double unit, I
     y -= step;
     if (!__any_sync(0xffffffffu, fabsf(step) > 4e-7f * fabsf(y))) break;
   }
-  pd.y = y;
   pd.dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
+  pd.yd = (double)y;
+  pd.rdq = (double)__frcp_rn(pd.dq);
   const float xf = -0.25f * f3;
   return (fabsf(pd.dq) >= 7e-3f * xf * xf * xf) && (k > 0) && (y < 3.f);
 }
@@ -491,9 +493,9 @@ __device__ __forceinline__ bool i8_root_start(const I8Quartic& c, double unit, I
 /// that the FP32 approach had not converged.  Returns r2 = (E0 - lambda_max) * 2/M.
 __device__ __forceinline__ double i8_root_finish(const I8Pending& pd) {
   if (pd.final) return pd.unit;
-  double yd = (double)pd.y;
+  double yd = pd.yd;
   const double Q = fma(fma(fma(yd + pd.q3, yd, pd.q2), yd, pd.q1), yd, pd.q0);
-  double d = Q * (double)__frcp_rn(pd.dq);
+  double d = Q * pd.rdq;
   yd -= d;
 #pragma unroll 1
   for (int it = 0; it < 30 && fabs(d) > 1e-5 * fabs(yd) + 1e-14; ++it) {
@@ -772,7 +774,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     I8Pending pd;
     bool pdLive = false, pdValid = false;
     size_t pdIdx = 0;
-    pd.q0 = pd.q1 = pd.q2 = pd.q3 = pd.unit = 0.0; pd.y = pd.dq = 0.f; pd.final = true;
+    pd.q0 = pd.q1 = pd.q2 = pd.q3 = pd.unit = pd.yd = pd.rdq = 0.0; pd.dq = 0.f; pd.final = true;
     int itN, jtN;
     bool have = tiles.next(a, it, jt);
     while (have) {
@@ -824,7 +826,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       const bool plain = !(DBG && (dbgMode == 6 || dbgMode == 1 || dbgMode == 7 || dbgMode == 8));
       if (plain) {
         if (pdLive) r2Prev = i8_root_finish(pd);     // tile n-1: FP64 polish of the root found under the last MMAs
-        cq = i8_coeffs(S, (ga + gb) * halfToInt);    // tile n: everything that must be FP64
+        cq = i8_coeffs(S, (ga + gb) * halfToInt);    // tile n: everything that must be FP64 (E0 too: outside the
+                                                     // window its two instructions crawl on the solve's critical path)
         asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2), "d"(r2Prev) : "memory");   // computed before the arrive below
       } else {
         cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0;
