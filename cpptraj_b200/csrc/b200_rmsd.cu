@@ -556,9 +556,16 @@ int dev_rms2d_tri(Device& d, const float* d_crd, size_t stride, const int* d_fra
   }
   // (one launch per shard was measured slower than 4096-row bands for the tcgen05 kernel: the row operands of a band,
   //  ~37 MB at 1000 atoms, stay in L2 while the columns stream)
-  for (long i0l = row0; i0l < row1; i0l += bandRows) {
+  const int tileRows = I8_TILE_I * i8_cta_group();
+  const int groups = std::max(1, (d.numSMs > 0 ? d.numSMs : 148) / i8_cta_group());
+  for (long i0l = row0; i0l < row1; ) {
     const int i0 = (int)i0l;
-    const int i1 = (int)std::min<long>(row1, i0l + bandRows);
+    int i1 = (int)std::min<long>(row1, i0l + bandRows);
+    // A band whose number of row tiles is a multiple of the CTA-group count deals every group the same row tiles in
+    // every column: all groups then change columns in lockstep and hit the same L2 lines of the new column operand at
+    // the same instant (measured: 25 % slower on two of eight cfg5 shards).  One tile row less breaks the lockstep.
+    if (plan.i8 && i1 - i0 > 2 * tileRows && ((i1 + tileRows - 1) / tileRows - i0 / tileRows) % groups == 0) i1 -= tileRows;
+    i0l = i1;
     if (tpair) tpair->begin(st);
     if ((rc = run_tri_band(d, plan, i0, i1, fit != 0, d_out, outBase, st))) return rc;
     if (tpair) tpair->end(st);
