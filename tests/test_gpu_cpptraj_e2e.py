@@ -26,6 +26,7 @@ DECKS = [
     ("mass", "2drms crd1 :3-7 rmsout OUT mass", "rmsd.mass.dat.save"),
     ("refmask_full_matrix", "2drms :2 :11 out OUT", "trp.dat.save"),
     ("nofit", "rms first :2-12@CA\n2drms crd1 :2 nofit out OUT", "nofit.dat.save"),
+    ("qrmsd_same_quantity", "2drms crd1 :3-7 rmsout OUT qrmsd", "rmsd.dat.save"),
 ]
 
 
@@ -88,3 +89,29 @@ def test_cpptraj_rms_nomod_on_b200(tmp_path):
     assert got.shape == want.shape == (101, 2)
     # golden printed with 4 decimals from NetCDF coordinates; tz2.crd carries 3-decimal ASCII coordinates
     assert np.abs(got - want).max() <= 2.1e-4, np.abs(got - want).max()
+
+
+def test_cpptraj_cluster_sieve_restore_on_b200(tmp_path):
+    """SURVEY 8(f) rank 1 through cpptraj itself: `cluster ... sieve 5` clusters every 5th frame (pairwise cache on the B200
+    path) and restores the sieved-out frames by their nearest centroid (List::AddFramesByCentroid, src/Cluster/List.cpp:160-207),
+    here computed by b200_rmsd_frames_to_centroids.  Golden: the UNMODIFIED reference on the CPU, same deck
+    (tools/make_golden_cluster_sieve.sh -> tests/golden/cluster_sieve5.*)."""
+    gold = os.path.join(ROOT, "tests", "golden", "cluster_sieve5.out")
+    if not os.path.exists(BIN) or not os.path.exists(gold):
+        pytest.skip("cpptraj.B200 not staged or golden missing")
+    deck = ("noprogress\nparm %s\ntrajin %s\n"
+            "cluster crd1 @CA clusters 5 rms out sieve5.out summary sieve5.summary.dat sieve 5 bestrep cumulative includesieveincalc\n"
+            % (os.path.join(STAGE, "tz2.parm7"), os.path.join(STAGE, "tz2.crd")))
+    (tmp_path / "cluster.in").write_text(deck)
+    r = subprocess.run([BIN, "-i", str(tmp_path / "cluster.in")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    got, want = table(tmp_path / "sieve5.out"), table(gold)
+    assert np.array_equal(got, want), "cluster number vs time differs from the CPU reference"
+    gs = [l.split() for l in open(tmp_path / "sieve5.summary.dat") if not l.startswith("#")]
+    ws = [l.split() for l in open(os.path.join(ROOT, "tests", "golden", "cluster_sieve5.summary.dat")) if not l.startswith("#")]
+    assert len(gs) == len(ws)
+    for g, w in zip(gs, ws):
+        assert g[0] == w[0] and g[1] == w[1] and g[5] == w[5]
+        assert abs(float(g[3]) - float(w[3])) <= 2e-3 and abs(float(g[6]) - float(w[6])) <= 2e-3

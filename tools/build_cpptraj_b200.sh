@@ -19,7 +19,7 @@ chmod -R u+w "$OUT"
 mkdir -p "$OUT/src/cuda_b200"
 cp "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.h "$HERE"/cpptraj_host/src/cuda_b200/B200_Rmsd.cpp "$HERE"/include/b200_rmsd.h "$OUT/src/cuda_b200/"
 cd "$OUT/src"
-for f in cuda_b200/B200_Rmsd.cpp Analysis_Rms2d.cpp Cluster/MetricArray.cpp Action_Rmsd.cpp; do
+for f in cuda_b200/B200_Rmsd.cpp Analysis_Rms2d.cpp Cluster/MetricArray.cpp Action_Rmsd.cpp Cluster/List.cpp; do
   /usr/bin/g++ -std=c++11 -fsyntax-only -fopenmp -DCUDA_B200 -DNO_MATHLIB -DNONETCDF -I. -Icuda_b200 "$f"
   echo "syntax ok: $f"
 done
