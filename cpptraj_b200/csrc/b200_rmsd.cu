@@ -669,7 +669,7 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     const int lo = std::max(c.fa, row0), hi = std::min(c.fb, row1);
     if (hi > lo) maxChunk = std::max(maxChunk, tri_row_start(F, hi) - tri_row_start(F, lo));
   }
-  const bool pinnedOut = host_ptr_is_pinned(outTri);
+  const bool pinnedOut = host_ptr_is_pinned(outTri + tri_row_start(F, (size_t)row0));   // (the shard's own range: the base may lie outside the caller's buffer)
   for (int s = 1; s < NSLOT; ++s) {
     if ((rc = d.outChunk[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
     if (!pinnedOut && (rc = d.outStage[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
@@ -804,7 +804,7 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   // band size: <= ~64 MB of output per band, multiple of 32 rows
   const size_t F = (size_t)nFrames;
   int bandRows = (int)std::min<size_t>(2048, std::max<size_t>(ROWG, ((size_t)64 << 20) / (4 * F) / ROWG * ROWG));
-  const bool pinnedOut = host_ptr_is_pinned(outTri);
+  const bool pinnedOut = host_ptr_is_pinned(outTri + tri_row_start(F, (size_t)row0));   // (the shard's own range: the base may lie outside the caller's buffer)
   size_t maxChunk = 0;
   for (int i0 = row0; i0 < row1; i0 += bandRows) {
     const int i1 = std::min(row1, i0 + bandRows);
