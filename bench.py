@@ -314,7 +314,10 @@ def main():
                                      "(operands resident in smem); MEASURED_PEAKS.json holds bf16 only (int8 nominal = 2x bf16). "
                                      "achieved/frac are ALGORITHMIC (18N flop per pair); executed/frac_executed count the 81 "
                                      "int8 dot products per pair incl. tile padding, i.e. tensor-pipe utilisation",
-                      "frac_executed_of_2x_bf16_measured": executed / (2 * bf16) if bf16 else None})
+                      "frac_executed_of_2x_bf16_measured": executed / (2 * bf16) if bf16 else None,
+                      "note": "frac = algorithmic / peak as the bench contract defines it; the exact-integer method executes 9x the "
+                              "algorithmic flop by design (3 x 3 digits), so tensor-pipe utilisation -- the figure SURVEY.md 8(d) ties "
+                              "north_star's >= 50 % target to -- is frac_executed"})
         else:
             peak = max(b.measure_fp64_mma_peak(0), b.measure_fp64_mma_peak(3))
             r.update({"peak": peak, "frac": achieved / peak if peak > 0 else None,
