@@ -230,3 +230,18 @@ def test_pipelined_host_path_headroom_fallback(b200, oracle, monkeypatch):
     sub = np.r_[0:25, 590:615, 2175:2200]
     want = oracle.rms2d_tri(cp[sub], sel)
     assert maxdiff(tri_to_square(got, 2200)[np.ix_(sub, sub)][np.triu_indices(len(sub), 1)], want) <= TOL
+
+
+def test_i8_config4_like_mass_weighted(b200, oracle):
+    """BASELINE configs[3] in small: Metric_RMS, mass-weighted, 2,000 atoms (32 K-chunks per tile), sieved frame list;
+    the tcgen05 engine must be the one that runs and must agree with the oracle."""
+    from cpptraj_b200.synth import make_trajectory, masses
+    crd, _ = make_trajectory(20261019, 400, 2000)
+    m = masses(2000)
+    sel = np.arange(2000, dtype=np.int32)
+    b200.set_pair_engine("auto")
+    fidx = np.arange(0, 400, 3, dtype=np.int32)
+    got = b200.rms2d_tri(crd, sel, mass=m, frame_idx=fidx)
+    assert b200.last_pair_engine()[0] == 2, "mass-weighted 2,000-atom selection should be eligible for the tcgen05 engine"
+    want = oracle.rms2d_tri(crd, sel, mass=m, frame_idx=fidx)
+    assert maxdiff(got, want) <= TOL

@@ -102,21 +102,12 @@ if "cfg4" in which:
     s = b.get_stats(); b.set_profiling(False)
     ms = e0.elapsed_time(e1) / K
     eng, qs = b.last_pair_engine()
-    # parity on sampled rows against the CPU oracle (mass-weighted, Metric_RMS semantics)
-    from oracle.pyoracle import Oracle
-    sub = np.r_[0:24, nF // 2:nF // 2 + 24, nF - 24:nF]
-    want = Oracle().rms2d_tri(h.numpy()[sub], np.arange(nA, dtype=np.int32), mass=m)
-    rows = []
-    F = nF
-    for a_i, i in enumerate(sub):
-        for j in sub[a_i + 1:]:
-            rows.append(F * i - i * (i + 1) // 2 + j - i - 1)
-    got = d_out[torch.tensor(rows, device="cuda")].cpu().numpy().astype(np.float64)
+    # (parity of this configuration: tests/test_gpu_i8.py::test_i8_config4_like_mass_weighted -- the oracle is test-only)
     line = {"config": "cfg4: cluster pairwise cache (Metric_RMS, mass-weighted), %d frames x %d atoms, %d pairs, 1 GPU, device-resident" % (nF, nA, npairs),
             "metric": "pair-RMSDs/s", "value": npairs / ms * 1e3, "unit": "pair-RMSDs/s", "ms_per_step": ms,
             "engine": {1: "fp64-dmma", 2: "tcgen05-int8"}.get(eng), "fixed_point_fraction_bits": qs,
             "pair_kernel_ms": s["pair_ms"] / K, "pack_ms": s["pack_ms"] / K,
             "algorithmic_TFLOP/s": 18.0 * nA * npairs / (s["pair_ms"] / K * 1e-3) / 1e12,
-            "parity_max_abs_diff_A_sampled": float(np.abs(got - want).max()), "gen_seconds": round(tgen, 1)}
+            "checksum": float(d_out[: 1 << 20].double().sum().item()), "gen_seconds": round(tgen, 1)}
     print(json.dumps(line), flush=True)
 b.shutdown()
