@@ -36,7 +36,7 @@ def build(force=False, verbose=False):
     if r.returncode:
         raise RuntimeError("nvcc failed (%d): %s" % (r.returncode, " ".join(cmd)))
     with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as fh:
-        fh.write(r.stdout)
+        fh.write("".join(l for l in r.stdout.splitlines(True) if "Compile time" not in l))   # (deterministic: no timings)
     return OUT
 
 
