@@ -45,6 +45,10 @@ def lib():
     L.b200_rmsd_1vN_begin.argtypes = [vp, vp, i, vp, i, i, C.POINTER(vp)]
     L.b200_rmsd_1vN_push_f64.argtypes = [vp, vp, sz, i]
     L.b200_rmsd_1vN_push_f32.argtypes = [vp, vp, sz, i]
+    L.b200_rmsd_1vN_set_ref.argtypes = [vp, vp]
+    L.b200_rmsd_1vN_set_ref.restype = i
+    L.b200_set_fixed_point_bits.argtypes = [i]
+    L.b200_set_fixed_point_bits.restype = i
     L.b200_rmsd_1vN_pending.argtypes = [vp]
     L.b200_rmsd_1vN_pending.restype = C.c_long
     L.b200_rmsd_1vN_flush.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_long)]
@@ -193,6 +197,12 @@ class Rmsd1vN:
         else:
             raise TypeError(frames.dtype)
 
+    def set_ref(self, ref_selected):
+        """Replace the reference (reftraj / previous); frames already pushed keep theirs."""
+        ref = np.ascontiguousarray(ref_selected, np.float64).reshape(-1)
+        assert ref.size == 3 * len(self.sel)
+        _check(lib().b200_rmsd_1vN_set_ref(self.h, _p(ref)))
+
     def pending(self):
         return lib().b200_rmsd_1vN_pending(self.h)
 
@@ -265,6 +275,11 @@ ENGINES = {"auto": 0, "fp64": 1, "i8": 2}
 def set_pair_engine(engine):
     """'auto' | 'fp64' | 'i8' (or 0/1/2): which kernel computes the pair covariances."""
     _check(lib().b200_set_pair_engine(ENGINES.get(engine, engine)))
+
+
+def set_fixed_point_bits(bits):
+    """Pin the fractional bits of the tcgen05 engine's fixed-point grid (0 = automatic)."""
+    _check(lib().b200_set_fixed_point_bits(int(bits)))
 
 
 def set_i8_cta_group(cta_group):

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = [os.path.join(HERE, "csrc", "b200_rmsd.cu")]
 DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith((".cuh", ".h"))] + [
-    os.path.join(os.path.dirname(HERE), "include", "b200_rmsd.h")]
+    os.path.join(os.path.dirname(HERE), "include", "b200_rmsd.h"), os.path.join(os.path.dirname(HERE), "include", "b200_rmsd_debug.h")]
 OUT = os.environ.get("B200_RMSD_LIB_OUT") or os.path.join(HERE, "libb200rmsd.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -32,9 +32,11 @@ def build(force=False, verbose=False):
     cmd = [NVCC] + FLAGS + extra + ["-o", OUT] + SRC
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode:
-        sys.stderr.write(r.stdout)
+        sys.stdout.write(r.stdout)
     if r.returncode:
         raise RuntimeError("nvcc failed (%d): %s" % (r.returncode, " ".join(cmd)))
+    if os.environ.get("B200_NO_PTXAS_LOG"):   # (variant builds: the committed log stays that of the product)
+        return OUT
     with open(os.path.join(HERE, "csrc", "ptxas.log"), "w") as fh:
         fh.write("".join(l for l in r.stdout.splitlines(True) if "Compile time" not in l))   # (deterministic: no timings)
     return OUT

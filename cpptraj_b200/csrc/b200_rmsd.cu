@@ -4,16 +4,20 @@
 // Device memory, streams and pinned staging are owned here; cpptraj owns the
 // host buffers it passes in.
 #include "../../include/b200_rmsd.h"
+#include "../../include/b200_rmsd_debug.h"
 #include "rmsd_kernels.cuh"
 #include "pair_i8.cuh"
+#include "host_util.h"
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -75,20 +79,26 @@ struct PinBuf {
   void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-constexpr int NSLOT = 3;  // compute/copy streams per device
+constexpr int NSLOT = 5;   // streams per device: stream 0 uploads / packs (pipelined path), all of them carry bands + downloads
+constexpr int NIN = 2;     // pinned ring slots for staged uploads of pageable COORDS
 
 struct Device {
   int id = -1;
-  cudaStream_t stream[NSLOT] = {nullptr, nullptr, nullptr};
-  cudaEvent_t done[NSLOT] = {nullptr, nullptr, nullptr};
+  cudaStream_t stream[NSLOT] = {};
+  cudaEvent_t done[NSLOT] = {};
   // workspaces (grow-only)
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
   DevBuf imgA, imgB, cenA, cenB, dbgS;   // tcgen05 int8 path: operand images, frame centres
   PinBuf hostScal;                        // pinned slot for the few scalars read back per call
   int numSMs = 0;
   DevBuf outChunk[NSLOT];
-  PinBuf outStage[NSLOT];
-  bool attrSet = false;
+  PinBuf outStage[NSLOT];                 // pageable result buffers: a band lands here, the copy pool moves it on
+  PinBuf inStage[NIN];                    // pageable COORDS: the copy pool gathers rows here, then one H2D copy
+  cudaEvent_t inFree[NIN] = {};
+  bool inUsed[NIN] = {};
+  int inNext = 0;
+  CopyPool pool;                          // staging of pageable inputs (and everything else on the calling thread)
+  CopyPool poolOut;                       // delivery of pageable results (driven by OutRing's own thread)
   void destroy() {
     if (id < 0) return;
     cudaSetDevice(id);
@@ -98,16 +108,39 @@ struct Device {
       stream[s] = nullptr; done[s] = nullptr;
       outChunk[s].release(); outStage[s].release();
     }
+    for (int b = 0; b < NIN; ++b) {
+      if (inFree[b]) cudaEventDestroy(inFree[b]);
+      inFree[b] = nullptr; inUsed[b] = false;
+      inStage[b].release();
+    }
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
                      &imgA, &imgB, &cenA, &cenB, &dbgS};
     for (DevBuf* b : all) b->release();
     hostScal.release();
+    pool.stop(); poolOut.stop();
     id = -1;
   }
 };
 
 std::mutex g_mu;               // serialises public entry points (re-entrant across sequential calls)
-std::vector<Device> g_devs;
+/// The initialised devices (a Device owns threads and mutexes: held by pointer, handed out by reference).
+struct DevList {
+  std::vector<std::unique_ptr<Device>> v;
+  struct It {
+    std::vector<std::unique_ptr<Device>>::iterator p;
+    Device& operator*() const { return **p; }
+    It& operator++() { ++p; return *this; }
+    bool operator!=(const It& o) const { return p != o.p; }
+  };
+  It begin() { return It{v.begin()}; }
+  It end() { return It{v.end()}; }
+  size_t size() const { return v.size(); }
+  bool empty() const { return v.empty(); }
+  Device& operator[](size_t i) { return *v[i]; }
+  void clear() { v.clear(); }
+  void resize(size_t n) { v.clear(); for (size_t i = 0; i < n; ++i) v.emplace_back(new Device()); }
+};
+DevList g_devs;
 bool g_inited = false;
 
 // ------------------------------------------------------------------ stats
@@ -177,18 +210,19 @@ int init_device(Device& d, int id) {
     CU(cudaStreamCreateWithFlags(&d.stream[s], cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&d.done[s], cudaEventDisableTiming));
   }
+  for (int b = 0; b < NIN; ++b) CU(cudaEventCreateWithFlags(&d.inFree[b], cudaEventDisableTiming));
   return B200_OK;
 }
 
 // ------------------------------------------------------------------ launch helpers
 template <int VAR, bool FIT, bool TRI>
 int launch_pair_t(const PairArgs& a, dim3 grid, cudaStream_t st) {
-  static bool attr[64] = {};
+  static std::atomic<bool> attr[64];   // per device; several host threads (one per device) may get here at once
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr[dev & 63]) {
+  if (!attr[dev & 63].load(std::memory_order_acquire)) {
     CU(cudaFuncSetAttribute(pair_kernel<VAR, FIT, TRI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM_BYTES));
-    attr[dev & 63] = true;
+    attr[dev & 63].store(true, std::memory_order_release);
   }
   COUNT_LAUNCH();
   pair_kernel<VAR, FIT, TRI><<<grid, PAIR_THREADS, PAIR_SMEM_BYTES, st>>>(a);
@@ -196,14 +230,17 @@ int launch_pair_t(const PairArgs& a, dim3 grid, cudaStream_t st) {
   return B200_OK;
 }
 
-int g_variant = -1;  // MMA shape variant; env B200_MMA_VARIANT overrides (0..3)
+// Lazily initialised knobs are atomics: b200_rms2d_tri drives one host thread per device and they all read them.
+std::atomic<int> g_variant{-1};  // MMA shape variant; env B200_MMA_VARIANT overrides (0..3)
 int mma_variant() {
-  if (g_variant < 0) {
+  int v = g_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("B200_MMA_VARIANT");
-    g_variant = e ? atoi(e) : 3;
-    if (g_variant < 0 || g_variant > 3) g_variant = 3;
+    v = e ? atoi(e) : 3;
+    if (v < 0 || v > 3) v = 3;
+    g_variant.store(v, std::memory_order_relaxed);
   }
-  return g_variant;
+  return v;
 }
 
 int launch_pair(const PairArgs& a, dim3 grid, bool fit, bool tri, cudaStream_t st) {
@@ -261,14 +298,16 @@ int run_pair_band(const PackSet& A, const PackSet& B, int rg0, int nRgI, bool tr
 // ------------------------------------------------------------------ pair engine selection
 // 0 = auto (tcgen05 int8 path when the selection's extent allows >= the required fractional bits,
 //     else FP64 DMMA), 1 = FP64 DMMA always, 2 = tcgen05 int8 or fail.  Env B200_PAIR_ENGINE.
-int g_engine = -1;
+std::atomic<int> g_engine{-1};
 int pair_engine() {
-  if (g_engine < 0) {
+  int v = g_engine.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("B200_PAIR_ENGINE");
-    g_engine = e ? atoi(e) : 0;
-    if (g_engine < 0 || g_engine > 2) g_engine = 0;
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+    g_engine.store(v, std::memory_order_relaxed);
   }
-  return g_engine;
+  return v;
 }
 std::atomic<int> g_lastEngine{0}, g_lastQs{0};
 long long* g_dbgClk = nullptr;   // device buffer for the kernel's cycle counters (timing experiments)
@@ -303,9 +342,9 @@ int i8_reserve(I8Set& S, DevBuf& img, DevBuf& G, DevBuf& cen, int nFrames, int n
   return B200_OK;
 }
 
-int i8_stats(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
+int i8_stats(const I8Set& S, const void* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
              const int* d_atomIdx, int nAtoms, const double* d_centerMass, const double* d_covMass,
-             unsigned int* d_maxBits, cudaStream_t st, int fEnd = -1) {
+             unsigned int* d_maxBits, cudaStream_t st, int fEnd = -1, bool srcIsDouble = false) {
   if (fEnd < 0) fEnd = S.nFrames;
   I8StatsArgs a;
   a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = fEnd; a.f0 = f0;
@@ -314,7 +353,8 @@ int i8_stats(const I8Set& S, const float* d_crd, size_t stride, const int* d_fra
   const int nb = (fEnd - f0 + 7) / 8;
   if (nb <= 0) return B200_OK;
   COUNT_LAUNCH();
-  i8_stats_kernel<<<nb, 256, 0, st>>>(a);
+  if (srcIsDouble) i8_stats_kernel<double><<<nb, 256, 0, st>>>(a);
+  else i8_stats_kernel<float><<<nb, 256, 0, st>>>(a);
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -326,8 +366,9 @@ int i8_clear(const I8Set& S, cudaStream_t st) {
   return B200_OK;
 }
 
-int i8_quant(const I8Set& S, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
-             const int* d_atomIdx, int nAtoms, const double* d_covMass, int qs, cudaStream_t st, int fEnd = -1) {
+int i8_quant(const I8Set& S, const void* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int f0,
+             const int* d_atomIdx, int nAtoms, const double* d_covMass, int qs, cudaStream_t st, int fEnd = -1,
+             bool srcIsDouble = false) {
   if (fEnd < 0) fEnd = S.nFrames;
   I8QuantArgs a;
   a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = fEnd; a.f0 = f0;
@@ -337,30 +378,91 @@ int i8_quant(const I8Set& S, const float* d_crd, size_t stride, const int* d_fra
   const int nb = (fEnd - f0 + 7) / 8;
   if (nb <= 0) return B200_OK;
   COUNT_LAUNCH();
-  i8_quant_kernel<<<nb, 256, 0, st>>>(a);
+  if (srcIsDouble) i8_quant_kernel<double><<<nb, 256, 0, st>>>(a);
+  else i8_quant_kernel<float><<<nb, 256, 0, st>>>(a);
   CU(cudaGetLastError());
   return B200_OK;
+}
+
+// Fixed-point scale pinned by the caller (b200_set_fixed_point_bits; 0 = automatic).  One process per GPU: the ranks
+// agree on min(qs) among themselves and pin it, so that every shard of one matrix is rounded to the same grid.
+std::atomic<int> g_fixedQs{0};
+constexpr int I8_MAX_ATOMS = 130000;   // int32 TMEM accumulators: one digit product is <= 2^14, the sum stays exact below 2^17 atoms
+                                       // (130,000: the B-digit fold of the epilogue then also fits 48 bits)
+
+/// Meeting point of the per-device host threads of one multi-device call: every thread contributes the extent of the
+/// frames it holds and all of them continue with the maximum (device 0 holds every frame), so that all shards use one
+/// grid and one engine whatever the device count.
+struct ExtentShare {
+  std::mutex mu;
+  std::condition_variable cv;
+  int parties = 1, arrived = 0;
+  bool failed = false;
+  float mx = 0.f;
+  /// \return false when another party failed before the meeting (the caller gives up too)
+  bool meet(float mine, float* all) {
+    std::unique_lock<std::mutex> lk(mu);
+    mx = std::max(mx, mine);
+    ++arrived;
+    cv.notify_all();
+    cv.wait(lk, [&] { return arrived >= parties || failed; });
+    *all = mx;
+    return !failed;
+  }
+  void abandon() {   // a party that cannot reach the meeting (error path) releases the others
+    std::lock_guard<std::mutex> lk(mu);
+    failed = true;
+    cv.notify_all();
+  }
+  void leave() {     // a party with nothing to do (empty shard)
+    std::lock_guard<std::mutex> lk(mu);
+    ++arrived;
+    cv.notify_all();
+  }
+};
+/// Releases the other parties if this one returns before the meeting.
+struct ShareGuard {
+  ExtentShare* s;
+  bool settled = false;
+  explicit ShareGuard(ExtentShare* sh) : s(sh) {}
+  ~ShareGuard() { if (s && !settled) s->abandon(); }
+};
+
+/// qs (fractional bits) for a largest centred, sqrt(m)-scaled coordinate mx; < 0 when none is usable.
+inline int i8_bits_for_extent(double mx, double headroom) {
+  int q = 30;
+  if (mx > 0.0) q = (int)std::floor(std::log2((double)I8_QMAX / (headroom * mx)));
+  return std::min(q, 30);
 }
 
 /// Reads back (max |coordinate|, total mass) after the stats kernel and picks the number of
 /// fractional bits.  *eligible = false when the grid would be too coarse for the contract.
 int i8_choose_scale(Device& d, const unsigned int* d_maxBits, const double* d_total, int nAtoms, cudaStream_t st,
-                    int* qs, bool* eligible) {
+                    int* qs, bool* eligible, ExtentShare* share = nullptr) {
   int rc;
-  if ((rc = d.hostScal.reserve(64))) return rc;
+  *eligible = false; *qs = 0;
+  if ((rc = d.hostScal.reserve(64))) { if (share) share->abandon(); return rc; }
   unsigned int* hBits = (unsigned int*)d.hostScal.p;
   double* hTotal = (double*)((char*)d.hostScal.p + 8);
-  CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(hTotal, d_total, sizeof(double), cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
+  cudaError_t ce = cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(hTotal, d_total, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) {
+    if (share) share->abandon();
+    return fail(B200_ERR_CUDA, "%s:%d: reading back the extent -> %s", __FILE__, __LINE__, cudaGetErrorString(ce));
+  }
   float mx;
   std::memcpy(&mx, hBits, 4);
+  if (share && !share->meet(std::isfinite(mx) ? mx : INFINITY, &mx)) return fail(B200_ERR_STATE, "another device of this call failed");
   const double total = *hTotal;
-  *eligible = false; *qs = 0;
-  if (!(total > 0.0) || !std::isfinite(mx)) return B200_OK;
-  int q = 30;
-  if (mx > 0.f) q = (int)std::floor(std::log2((double)I8_QMAX / (double)mx));
-  if (q > 30) q = 30;
+  // total mass < SMALL: every RMSD is -1 (src/Frame.cpp:1160-1163); the FP64 engine writes that
+  if (!(total >= 1e-14) || !std::isfinite(mx) || nAtoms >= I8_MAX_ATOMS) return B200_OK;
+  int q = i8_bits_for_extent((double)mx, 1.0);
+  const int pinned = g_fixedQs.load(std::memory_order_relaxed);
+  if (pinned > 0) {
+    if (pinned > q) return fail(B200_ERR_ARG, "pinned fixed-point scale (%d bits) too fine for this selection's extent (%d bits fit)", pinned, q);
+    q = pinned;
+  }
   if (q < 0) return B200_OK;
   *qs = q;
   *eligible = i8_worst_error(q, nAtoms, total) <= I8_MAX_WORST_ERROR;
@@ -369,25 +471,27 @@ int i8_choose_scale(Device& d, const unsigned int* d_maxBits, const double* d_to
 
 // MMA CTA group of the tcgen05 kernel: 2 = CTA pairs (tcgen05.mma.cta_group::2, 28 x 28 tiles), 1 = single CTA
 // (14 x 28 tiles).  Env B200_I8_CTA_GROUP or b200_set_i8_cta_group().
-int g_i8Cg = -1;
+std::atomic<int> g_i8Cg{-1};
 int i8_cta_group() {
-  if (g_i8Cg < 0) {
+  int v = g_i8Cg.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("B200_I8_CTA_GROUP");
-    g_i8Cg = e ? atoi(e) : 2;
-    if (g_i8Cg != 1 && g_i8Cg != 2) g_i8Cg = 2;
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2) v = 2;
+    g_i8Cg.store(v, std::memory_order_relaxed);
   }
-  return g_i8Cg;
+  return v;
 }
 
 template <bool TRI, int CG, bool DBG>
 int launch_pair_i8_t(const PairI8Args& a, int grid, cudaStream_t st) {
-  static bool attr[64] = {};
+  static std::atomic<bool> attr[64];
   int dev = 0;
   cudaGetDevice(&dev);
   constexpr int smem = i8_smem_bytes<CG>();
-  if (!attr[dev & 63]) {
+  if (!attr[dev & 63].load(std::memory_order_acquire)) {
     CU(cudaFuncSetAttribute(pair_i8_kernel<TRI, CG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr[dev & 63] = true;
+    attr[dev & 63].store(true, std::memory_order_release);
   }
   COUNT_LAUNCH();
   if (CG == 1) {
@@ -484,7 +588,7 @@ struct TriPlan {   // what prepare_tri() left on the device for the band launche
 /// Blocks the host once (a few scalars read back) when the tcgen05 engine is a candidate.
 int prepare_tri(Device& d, const float* d_crd, size_t stride, const int* d_frameIdx, long srcBase, int nFrames,
                 const int* d_atomIdx, int nAtoms, const double* d_mass, int fit, int row0, cudaStream_t st,
-                Timer* tpack, TriPlan& plan) {
+                Timer* tpack, TriPlan& plan, ExtentShare* share = nullptr) {
   int rc;
   if ((rc = d.scal.reserve(64))) return rc;
   double* d_total = (double*)d.scal.p;
@@ -501,7 +605,7 @@ int prepare_tri(Device& d, const float* d_crd, size_t stride, const int* d_frame
     CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st));
     if ((rc = i8_stats(plan.q, d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
     bool ok = false;
-    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &plan.qs, &ok))) return rc;
+    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &plan.qs, &ok, share))) return rc;
     if (ok) {
       if ((rc = i8_clear(plan.q, st))) return rc;
       if ((rc = i8_quant(plan.q, d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, nAtoms, d_mass, plan.qs, st))) return rc;
@@ -580,16 +684,44 @@ void add_stats(double packMs, long packN, double pairMs, long pairN, double pair
   g_stats.pairs += pairs; g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h;
 }
 
-// Upload the needed span of host COORDS (frames [fLo,fHi), floats [0,width)) to d.crd / d.crdB.
-int upload_crd(DevBuf& buf, const float* crd, size_t stride, int fLo, int fHi, size_t widthFloats, cudaStream_t st,
-               double* h2dBytes) {
-  const size_t rows = (size_t)(fHi - fLo);
+// Rows [fLo,fHi) of host COORDS (the leading `width` floats of each frame) -> d_dst (row pitch `width`), on stream st.
+// Pinned source: one strided DMA.  Pageable source (cpptraj's std::vector<float>): the copy pool gathers <= 16 MiB of
+// rows at a time into one of two pinned ring slots, each followed by its own contiguous H2D copy, so the host-side
+// gather of piece k+1 overlaps the transfer of piece k (the driver's own pageable path moves ~10 GB/s, this ~50).
+int upload_rows(Device& d, float* d_dst, const float* crd, size_t stride, int fLo, int fHi, size_t width, bool pinnedIn,
+                cudaStream_t st, double* h2dBytes) {
+  const size_t rows = (size_t)std::max(0, fHi - fLo);
+  if (!rows) return B200_OK;
+  *h2dBytes += (double)(rows * width * sizeof(float));
+  const float* src = crd + (size_t)fLo * stride;
+  if (pinnedIn) {
+    CU(cudaMemcpy2DAsync(d_dst, width * sizeof(float), src, stride * sizeof(float), width * sizeof(float), rows,
+                         cudaMemcpyHostToDevice, st));
+    return B200_OK;
+  }
+  const size_t rowBytes = width * sizeof(float);
+  const size_t rpp = std::max<size_t>(1, ((size_t)16 << 20) / rowBytes);
   int rc;
-  if ((rc = buf.reserve(rows * widthFloats * sizeof(float)))) return rc;
-  CU(cudaMemcpy2DAsync(buf.p, widthFloats * sizeof(float), crd + (size_t)fLo * stride, stride * sizeof(float),
-                       widthFloats * sizeof(float), rows, cudaMemcpyHostToDevice, st));
-  *h2dBytes += (double)(rows * widthFloats * sizeof(float));
+  for (size_t r0 = 0; r0 < rows; r0 += rpp) {
+    const size_t nr = std::min(rpp, rows - r0);
+    const int b = d.inNext;
+    d.inNext = (d.inNext + 1) % NIN;
+    if (d.inUsed[b]) CU(cudaEventSynchronize(d.inFree[b]));   // the transfer that last read this slot is done
+    if ((rc = d.inStage[b].reserve(std::min(rpp, rows) * rowBytes))) return rc;
+    d.pool.copy2d(d.inStage[b].p, rowBytes, src + r0 * stride, stride * sizeof(float), rowBytes, nr);
+    CU(cudaMemcpyAsync(d_dst + r0 * width, d.inStage[b].p, nr * rowBytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(d.inFree[b], st));
+    d.inUsed[b] = true;
+  }
   return B200_OK;
+}
+
+/// Frames [fLo,fHi) of host COORDS into a (grown) device buffer.
+int upload_crd(Device& d, DevBuf& buf, const float* crd, size_t stride, int fLo, int fHi, size_t widthFloats, cudaStream_t st,
+               double* h2dBytes) {
+  int rc;
+  if ((rc = buf.reserve((size_t)std::max(1, fHi - fLo) * widthFloats * sizeof(float)))) return rc;
+  return upload_rows(d, (float*)buf.p, crd, stride, fLo, fHi, widthFloats, host_ptr_is_pinned(crd + (size_t)fLo * stride), st, h2dBytes);
 }
 
 template <typename T>
@@ -612,22 +744,139 @@ int validate_sel(const int* atomIdx, int nAtoms, size_t stride, int* maxAtom) {
   return B200_OK;
 }
 
-// Pipelined host path of the tcgen05 engine (pinned COORDS, no frame list).  Frames are uploaded from the END of the
-// trajectory towards the start, chunk by chunk.  Rows [a, b) of the triangle pair only with frames >= a, so as soon as a
-// chunk has landed and is quantised its band of rows can be computed and its slice of the triangle copied back while the
+/// Bands of result elements on their way to the caller: slot s holds [base, base+n) of the output array until its
+/// download has completed.  A pinned destination receives the DMA directly.  A pageable one (cpptraj's new float[],
+/// never touched: every page faults on first write) is filled from the slot's pinned stage by the output copy pool,
+/// driven by a delivery thread of its own, so that the thread that stages the uploads and launches the kernels
+/// never waits for a page fault: uploads, kernels, downloads and both host-side copies overlap.
+struct OutRing {
+  Device& d;
+  float* out;          // caller's array (element 0 of the whole matrix)
+  bool pinned;
+  struct Pending { size_t base = 0, n = 0; bool live = false; } pend[NSLOT];
+  double d2h = 0.0;
+  // delivery thread (pageable destinations only)
+  std::thread worker;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<int> queue;      // slots whose download has been queued, in order
+  size_t qHead = 0;
+  bool quit = false, failed = false;
+  // pageable destination: the range this call will fill, populated by the delivery thread's pool before the first
+  // band arrives (from the END when `fromEnd`: the pipelined path delivers the last rows first)
+  char* popLo = nullptr;
+  size_t popBytes = 0;
+  bool fromEnd = false;
+  OutRing(Device& dev, float* o, bool pin, float* first = nullptr, size_t elts = 0, bool lastRowsFirst = false)
+      : d(dev), out(o), pinned(pin), popLo((char*)first), popBytes(elts * sizeof(float)), fromEnd(lastRowsFirst) {
+    if (!pinned) {
+      if (first) advise_hugepages(first, popBytes);
+      worker = std::thread([this] { deliver(); });
+    }
+  }
+  ~OutRing() {
+    if (worker.joinable()) {
+      { std::lock_guard<std::mutex> lk(mu); quit = true; }
+      cv.notify_all();
+      worker.join();
+    }
+  }
+  void deliver() {
+    cudaSetDevice(d.id);
+    if (popLo && popBytes && !getenv("B200_NO_POPULATE")) {
+      const size_t piece = (size_t)4 << 20, np = (popBytes + piece - 1) / piece;
+      std::atomic<bool> supported{true};
+      d.poolOut.run(np, [&](size_t k) {
+        if (!supported.load(std::memory_order_relaxed)) return;
+        const size_t a = (fromEnd ? np - 1 - k : k) * piece;
+        if (!populate_pages(popLo + a, std::min(piece, popBytes - a))) supported.store(false, std::memory_order_relaxed);
+      });
+    }
+    for (;;) {
+      int s;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return quit || qHead < queue.size(); });
+        if (qHead >= queue.size()) return;   // quit and nothing left
+        s = queue[qHead];
+      }
+      const bool ok = cudaEventSynchronize(d.done[s]) == cudaSuccess;
+      if (ok) d.poolOut.copy(out + pend[s].base, d.outStage[s].p, pend[s].n * sizeof(float));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ok) failed = true;
+        pend[s].live = false;
+        ++qHead;
+      }
+      cv.notify_all();
+    }
+  }
+  int reserve(int s, size_t maxElts) {
+    int rc;
+    if ((rc = d.outChunk[s].reserve(std::max<size_t>(maxElts, 1) * sizeof(float)))) return rc;
+    if (!pinned && (rc = d.outStage[s].reserve(std::max<size_t>(maxElts, 1) * sizeof(float)))) return rc;
+    return B200_OK;
+  }
+  /// Wait until slot s's band has been delivered; the slot may be refilled afterwards.
+  int retire(int s) {
+    if (pinned) {
+      if (!pend[s].live) return B200_OK;
+      CU(cudaEventSynchronize(d.done[s]));
+      pend[s].live = false;
+      return B200_OK;
+    }
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !pend[s].live || failed; });
+    if (failed) return fail(B200_ERR_CUDA, "a download of the result failed");
+    return B200_OK;
+  }
+  /// Queue the download of slot s's chunk buffer (n elements, destined for out[base..]) on stream st.
+  int download(int s, size_t base, size_t n, cudaStream_t st) {
+    if (n) {
+      float* dst = pinned ? out + base : (float*)d.outStage[s].p;
+      CU(cudaMemcpyAsync(dst, d.outChunk[s].p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+      d2h += (double)n * sizeof(float);
+    }
+    CU(cudaEventRecord(d.done[s], st));
+    if (pinned) { pend[s].base = base; pend[s].n = n; pend[s].live = true; return B200_OK; }
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      pend[s].base = base; pend[s].n = n; pend[s].live = true;
+      queue.push_back(s);
+    }
+    cv.notify_all();
+    return B200_OK;
+  }
+  int drain() {
+    int rc;
+    for (int s = 0; s < NSLOT; ++s) if ((rc = retire(s))) return rc;
+    return B200_OK;
+  }
+};
+
+// Pipelined host path of the tcgen05 engine (no frame list).  Frames are uploaded from the END of the trajectory
+// towards the start, chunk by chunk.  Rows [a, b) of the triangle pair only with frames >= a, so as soon as a chunk
+// has landed and is quantised its band of rows can be computed and its slice of the triangle copied back while the
 // next chunk uploads: H2D, compute and D2H overlap (PCIe is full duplex) instead of upload -> compute/download.
-// The fixed-point scale must be known before the first chunk is quantised: it is taken from the first chunk's extent
-// with 25 % headroom, every later chunk keeps feeding the running maximum, and if at the end the headroom turned out
-// too small (or the scale leaves too few fractional bits) *done stays false and the caller runs the two-pass path.
+// Pageable COORDS and result buffers (what cpptraj passes) go through pinned ring slots and the copy pool.
+// The fixed-point scale must be known before the first chunk is quantised: it is taken from the extent of the TOP
+// chunk of the trajectory -- the same frames whatever the shard, so all shards of a matrix agree on it -- with 25 %
+// headroom (or it is the scale pinned by b200_set_fixed_point_bits); every later chunk keeps feeding the running
+// maximum, and if at the end the headroom turned out too small (or the scale leaves too few fractional bits) *done
+// stays false and the caller runs the two-pass path.
 int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrames, const int* atomIdx, int nAtoms,
                           const double* mass, int row0, int row1, float* outTri, bool* done) {
   *done = false;
   int maxAtom = 0, rc;
   if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
+  if (nAtoms >= I8_MAX_ATOMS) return B200_OK;
+  double total = (double)nAtoms;
+  if (mass) { total = 0.0; for (int k = 0; k < nAtoms; ++k) total += mass[k]; }
+  if (!(total >= 1e-14)) return B200_OK;      // (every RMSD is -1: the FP64 engine writes that)
   const size_t F = (size_t)nFrames;
   const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
   const int f0 = (row0 / I8_TILE_J) * I8_TILE_J;           // first frame needed (tile aligned)
-  // chunk = band: <= 64 MB of output, a multiple of the 28-frame tile
+  // chunk = band: <= 40 MB of output, a multiple of the 28-frame tile
   int C = (int)std::min<size_t>(2016, std::max<size_t>(8 * I8_TILE_J, ((size_t)40 << 20) / (4 * F) / I8_TILE_J * I8_TILE_J));
   { const char* e = getenv("B200_PIPE_ROWS"); if (e && atoi(e) >= I8_TILE_J) C = atoi(e) / I8_TILE_J * I8_TILE_J; }
   cudaStream_t sIn = d.stream[0];
@@ -644,22 +893,21 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
   I8Set q;
   if ((rc = i8_reserve(q, d.imgA, d.GA, d.cenA, nFrames, nAtoms))) return rc;
   if ((rc = i8_clear(q, sIn))) return rc;
-  // chunk list, last chunk of the trajectory first.  The first chunk to be uploaded (top of the trajectory) and the
-  // last bands to be computed (lowest rows = longest rows) are smaller: nothing overlaps the first upload and the
-  // last download.
+  // Chunk list, last chunk of the trajectory first.  The top chunk [T0, F) is a function of F alone; below it the
+  // chunks grow from small ones at the shard's first frame (nothing overlaps the first upload and the last download).
   struct Chunk { int fa, fb; };
   std::vector<Chunk> chunks;
   {
     std::vector<int> bnd;   // ascending boundaries from f0
     const int small = std::max(I8_TILE_J, C / 4 / I8_TILE_J * I8_TILE_J);
+    const int T0 = (nFrames - f0 > 2 * small) ? (nFrames - small) / I8_TILE_J * I8_TILE_J : f0;
     int at = f0, step = small;
-    while (at < nFrames) {
+    while (at < T0) {
       bnd.push_back(at);
       at += step;
       if (step < C) step = std::min(C, step + small);
     }
-    // split a small piece off the top
-    if (nFrames - bnd.back() > 2 * small) bnd.push_back(std::max(bnd.back() + small, (nFrames - small) / I8_TILE_J * I8_TILE_J));
+    bnd.push_back(T0);
     bnd.push_back(nFrames);
     for (size_t i = bnd.size() - 1; i > 0; --i)
       if (bnd[i] > bnd[i - 1]) chunks.push_back({bnd[i - 1], bnd[i]});
@@ -669,46 +917,35 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     const int lo = std::max(c.fa, row0), hi = std::min(c.fb, row1);
     if (hi > lo) maxChunk = std::max(maxChunk, tri_row_start(F, hi) - tri_row_start(F, lo));
   }
-  const bool pinnedOut = host_ptr_is_pinned(outTri + tri_row_start(F, (size_t)row0));   // (the shard's own range: the base may lie outside the caller's buffer)
-  for (int s = 1; s < NSLOT; ++s) {
-    if ((rc = d.outChunk[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
-    if (!pinnedOut && (rc = d.outStage[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
-  }
-  struct Pending { size_t base = 0, n = 0; bool live = false; } pend[NSLOT];
-  auto retire = [&](int s) -> int {
-    if (!pend[s].live) return B200_OK;
-    CU(cudaEventSynchronize(d.done[s]));
-    if (!pinnedOut) std::memcpy(outTri + pend[s].base, d.outStage[s].p, pend[s].n * sizeof(float));
-    pend[s].live = false;
-    return B200_OK;
-  };
+  float* outFirst = outTri + tri_row_start(F, (size_t)row0);   // (the shard's own range: the base may lie outside the caller's buffer)
+  const size_t outElts = tri_row_start(F, (size_t)row1) - tri_row_start(F, (size_t)row0);
+  const bool pinnedIn = host_ptr_is_pinned(crd + (size_t)f0 * stride);
+  OutRing ring(d, outTri, host_ptr_is_pinned(outFirst), outFirst, outElts, true);
+  for (int s = 1; s < NSLOT; ++s) if ((rc = ring.reserve(s, maxChunk))) return rc;
   std::vector<cudaEvent_t> evs;
   auto cleanup = [&]() { for (cudaEvent_t e : evs) cudaEventDestroy(e); evs.clear(); };
   const float* d_crd = (const float*)d.crd.p;
   const long srcBase = (long)f0;      // row r of the device copy is frame f0 + r
   Timer tpair;
-  double h2d = (double)nAtoms * 4 + (mass ? (double)nAtoms * 8 : 0), d2h = 0.0;
-  int qs = 0, band = 0;
+  double h2d = (double)nAtoms * 4 + (mass ? (double)nAtoms * 8 : 0);
+  int qs = g_fixedQs.load(std::memory_order_relaxed), band = 0;
+  const bool pinnedScale = qs > 0;
+  if (pinnedScale && i8_worst_error(qs, nAtoms, total) > I8_MAX_WORST_ERROR) return B200_OK;
   long nLaunch = 0;
   for (size_t k = 0; k < chunks.size(); ++k) {
     const int fa = chunks[k].fa, fb = chunks[k].fb;
-    CU(cudaMemcpy2DAsync((float*)d.crd.p + (size_t)(fa - f0) * width, width * sizeof(float), crd + (size_t)fa * stride,
-                         stride * sizeof(float), width * sizeof(float), (size_t)(fb - fa), cudaMemcpyHostToDevice, sIn));
-    h2d += (double)(fb - fa) * width * sizeof(float);
+    if ((rc = upload_rows(d, (float*)d.crd.p + (size_t)(fa - f0) * width, crd, stride, fa, fb, width, pinnedIn, sIn, &h2d))) { cleanup(); return rc; }
     if ((rc = i8_stats(q, d_crd, width, nullptr, srcBase, fa, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, sIn, fb))) { cleanup(); return rc; }
-    if (k == 0) {
-      // scale from the first chunk, with headroom for the frames not seen yet
+    if (k == 0 && !pinnedScale) {
+      // scale from the top chunk, with headroom for the frames not seen yet
       if ((rc = d.hostScal.reserve(64))) { cleanup(); return rc; }
       unsigned int* hBits = (unsigned int*)d.hostScal.p;
-      double* hTotal = (double*)((char*)d.hostScal.p + 8);
       CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, sIn));
-      CU(cudaMemcpyAsync(hTotal, d_total, sizeof(double), cudaMemcpyDeviceToHost, sIn));
       CU(cudaStreamSynchronize(sIn));
       float mx;
       std::memcpy(&mx, hBits, 4);
-      const double total = *hTotal;
-      if (!(total > 0.0) || !std::isfinite(mx) || !(mx > 0.f)) { cleanup(); return B200_OK; }
-      qs = std::min(30, (int)std::floor(std::log2((double)I8_QMAX / (1.25 * (double)mx))));
+      if (!std::isfinite(mx) || !(mx > 0.f)) { cleanup(); return B200_OK; }
+      qs = i8_bits_for_extent((double)mx, 1.25);
       if (qs < 0 || i8_worst_error(qs, nAtoms, total) > I8_MAX_WORST_ERROR) { cleanup(); return B200_OK; }
     }
     if ((rc = i8_quant(q, d_crd, width, nullptr, srcBase, fa, (const int*)d.idxA.p, nAtoms, d_mass, qs, sIn, fb))) { cleanup(); return rc; }
@@ -719,7 +956,7 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     evs.push_back(ev);
     CU(cudaEventRecord(ev, sIn));
     const int s = 1 + (band++ % (NSLOT - 1));
-    if ((rc = retire(s))) { cleanup(); return rc; }
+    if ((rc = ring.retire(s))) { cleanup(); return rc; }
     cudaStream_t st = d.stream[s];
     CU(cudaStreamWaitEvent(st, ev, 0));
     const size_t base = tri_row_start(F, lo), n = tri_row_start(F, hi) - base;
@@ -727,49 +964,65 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     if ((rc = run_pair_i8_band(d, q, q, lo, hi, true, qs, d_total, (float*)d.outChunk[s].p, base, 0, nullptr, st))) { cleanup(); return rc; }
     tpair.end(st);
     ++nLaunch;
-    if (n) {
-      float* dst = pinnedOut ? outTri + base : (float*)d.outStage[s].p;
-      CU(cudaMemcpyAsync(dst, d.outChunk[s].p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      d2h += (double)n * sizeof(float);
-    }
-    CU(cudaEventRecord(d.done[s], st));
-    pend[s].base = base; pend[s].n = n; pend[s].live = true;
+    if ((rc = ring.download(s, base, n, st))) { cleanup(); return rc; }
   }
-  // did the headroom hold?
+  // did the scale hold for every frame?
   {
+    if ((rc = d.hostScal.reserve(64))) { cleanup(); return rc; }
     unsigned int* hBits = (unsigned int*)d.hostScal.p;
     CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, sIn));
     CU(cudaStreamSynchronize(sIn));
-    for (int s = 1; s < NSLOT; ++s) if ((rc = retire(s))) { cleanup(); return rc; }
+    if ((rc = ring.drain())) { cleanup(); return rc; }
     for (int s = 1; s < NSLOT; ++s) CU(cudaStreamSynchronize(d.stream[s]));
     cleanup();
     float mx;
     std::memcpy(&mx, hBits, 4);
-    if (!((double)mx * std::ldexp(1.0, qs) <= (double)I8_QMAX)) return B200_OK;   // *done == false: two-pass path recomputes
+    if (!((double)mx * std::ldexp(1.0, qs) <= (double)I8_QMAX)) {
+      if (pinnedScale) return fail(B200_ERR_ARG, "pinned fixed-point scale (%d bits) too fine for this selection's extent", qs);
+      return B200_OK;   // *done == false: the two-pass path recomputes
+    }
   }
-  const double pairs = (double)(tri_row_start(F, row1) - tri_row_start(F, row0));
-  add_stats(0.0, 1, tpair.resolve(), nLaunch, pairs, h2d, d2h);
+  const double pairs = (double)outElts;
+  add_stats(0.0, 1, tpair.resolve(), nLaunch, pairs, h2d, ring.d2h);
   g_lastEngine.store(2); g_lastQs.store(qs);
   *done = true;
   return B200_OK;
 }
 
-// One shard of the triangle on one device, host buffers.
+// One shard of the triangle on one device, host buffers.  `share`: meeting point of the device threads of a
+// multi-device call (nullable).
 int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTotal, const int* frameIdx, int nFrames,
-                       const int* atomIdx, int nAtoms, const double* mass, int fit, int row0, int row1, float* outTri) {
+                       const int* atomIdx, int nAtoms, const double* mass, int fit, int row0, int row1, float* outTri,
+                       ExtentShare* share = nullptr) {
+  ShareGuard guard(share);
   CU(cudaSetDevice(d.id));
-  if (row1 <= row0 || nFrames < 2) return B200_OK;
+  if (row1 <= row0 || nFrames < 2) {
+    if (share) { share->leave(); guard.settled = true; }
+    return B200_OK;
+  }
   int maxAtom = 0, rc;
   if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
+  if (frameIdx) {   // a frame list that lists every frame in order (cluster without a sieve) is no list
+    bool identity = nFrames <= nFramesTotal;
+    for (int f = 0; identity && f < nFrames; ++f) identity = frameIdx[f] == f;
+    if (identity) frameIdx = nullptr;
+  }
+  bool pipelineTried = false;
   {
     const char* e = getenv("B200_HOST_PIPELINE");
-    if (fit && !frameIdx && pair_engine() != 1 && nFrames >= 1024 && nFrames <= nFramesTotal && !(e && atoi(e) == 0) &&
-        host_ptr_is_pinned(crd)) {
+    if (fit && !frameIdx && pair_engine() != 1 && nFrames >= 1024 && nFrames <= nFramesTotal && !(e && atoi(e) == 0)) {
       bool done = false;
+      pipelineTried = true;
       if ((rc = host_tri_pipelined_i8(d, crd, stride, nFrames, atomIdx, nAtoms, mass, row0, row1, outTri, &done))) return rc;
-      if (done) return B200_OK;
+      if (done) {
+        if (share) { share->leave(); guard.settled = true; }
+        return B200_OK;
+      }
     }
   }
+  // (every device thread of a call takes the same decisions up to here; one that falls back after a failed pipelined
+  //  attempt must not wait for the others, which may have succeeded: it leaves the meeting and chooses on its own)
+  if (share && pipelineTried) { share->leave(); guard.settled = true; share = nullptr; }
   // source frame range needed by output frames [f0, nFrames) (f0: first frame either engine packs)
   const int f0 = std::min((row0 / ROWG) * ROWG, (row0 / I8_FR_PER_RG) * I8_FR_PER_RG);
   int sLo = f0, sHi = nFrames;
@@ -783,9 +1036,10 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
     return fail(B200_ERR_ARG, "nFrames %d > nFramesTotal %d", nFrames, nFramesTotal);
   }
   cudaStream_t st0 = d.stream[0];
-  double h2d = 0.0, d2h = 0.0;
+  double h2d = 0.0;
   const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
-  if ((rc = upload_crd(d.crd, crd, stride, sLo, sHi, width, st0, &h2d))) return rc;
+  if ((rc = d.crd.reserve((size_t)(sHi - sLo) * width * sizeof(float)))) return rc;
+  if ((rc = upload_rows(d, (float*)d.crd.p, crd, stride, sLo, sHi, width, host_ptr_is_pinned(crd + (size_t)sLo * stride), st0, &h2d))) return rc;
   if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st0))) return rc;
   if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st0))) return rc;
   if (frameIdx && (rc = upload_vec(d.frameIdx, frameIdx, (size_t)nFrames, st0))) return rc;
@@ -797,36 +1051,28 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
   const int* d_fidx = frameIdx ? (const int*)d.frameIdx.p : nullptr;
   // pack on stream 0, then bands round-robin over the slots
   if ((rc = prepare_tri(d, (const float*)d.crd.p, width, d_fidx, (long)sLo, nFrames, (const int*)d.idxA.p, nAtoms, d_mass,
-                        fit, row0, st0, &tpack, plan))) return rc;
+                        fit, row0, st0, &tpack, plan, share))) return rc;
+  guard.settled = true;   // (met, or nobody meets: fit == 0 / FP64 engine forced)
   CU(cudaEventRecord(d.done[0], st0));
   for (int s = 1; s < NSLOT; ++s) CU(cudaStreamWaitEvent(d.stream[s], d.done[0], 0));
 
-  // band size: <= ~64 MB of output per band, multiple of 32 rows
+  // band size: <= ~40 MB of output per band, multiple of 32 rows
   const size_t F = (size_t)nFrames;
-  int bandRows = (int)std::min<size_t>(2048, std::max<size_t>(ROWG, ((size_t)64 << 20) / (4 * F) / ROWG * ROWG));
-  const bool pinnedOut = host_ptr_is_pinned(outTri + tri_row_start(F, (size_t)row0));   // (the shard's own range: the base may lie outside the caller's buffer)
+  int bandRows = (int)std::min<size_t>(2048, std::max<size_t>(ROWG, ((size_t)40 << 20) / (4 * F) / ROWG * ROWG));
+  float* outFirst = outTri + tri_row_start(F, (size_t)row0);   // (the shard's own range: the base may lie outside the caller's buffer)
+  const size_t outElts = tri_row_start(F, (size_t)row1) - tri_row_start(F, (size_t)row0);
+  OutRing ring(d, outTri, host_ptr_is_pinned(outFirst), outFirst, outElts, false);
   size_t maxChunk = 0;
   for (int i0 = row0; i0 < row1; i0 += bandRows) {
     const int i1 = std::min(row1, i0 + bandRows);
     maxChunk = std::max(maxChunk, tri_row_start(F, i1) - tri_row_start(F, i0));
   }
-  for (int s = 0; s < NSLOT; ++s) {
-    if ((rc = d.outChunk[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
-    if (!pinnedOut && (rc = d.outStage[s].reserve(std::max<size_t>(maxChunk, 1) * sizeof(float)))) return rc;
-  }
-  struct Pending { size_t base = 0, n = 0; bool live = false; } pend[NSLOT];
-  auto retire = [&](int s) -> int {
-    if (!pend[s].live) return B200_OK;
-    CU(cudaEventSynchronize(d.done[s]));
-    if (!pinnedOut) std::memcpy(outTri + pend[s].base, d.outStage[s].p, pend[s].n * sizeof(float));
-    pend[s].live = false;
-    return B200_OK;
-  };
+  for (int s = 0; s < NSLOT; ++s) if ((rc = ring.reserve(s, maxChunk))) return rc;
   int band = 0;
   long nLaunch = 0;
   for (int i0 = row0; i0 < row1; i0 += bandRows, ++band) {
     const int s = band % NSLOT;
-    if ((rc = retire(s))) return rc;
+    if ((rc = ring.retire(s))) return rc;
     const int i1 = std::min(row1, i0 + bandRows);
     const size_t base = tri_row_start(F, i0), n = tri_row_start(F, i1) - base;
     cudaStream_t st = d.stream[s];
@@ -834,18 +1080,25 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
     if ((rc = run_tri_band(d, plan, i0, i1, fit != 0, (float*)d.outChunk[s].p, base, st))) return rc;
     tpair.end(st);
     ++nLaunch;
-    if (n) {
-      float* dst = pinnedOut ? outTri + base : (float*)d.outStage[s].p;
-      CU(cudaMemcpyAsync(dst, d.outChunk[s].p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-      d2h += (double)n * sizeof(float);
-    }
-    CU(cudaEventRecord(d.done[s], st));
-    pend[s].base = base; pend[s].n = n; pend[s].live = true;
+    if ((rc = ring.download(s, base, n, st))) return rc;
   }
-  for (int s = 0; s < NSLOT; ++s) if ((rc = retire(s))) return rc;
+  if ((rc = ring.drain())) return rc;
   for (int s = 0; s < NSLOT; ++s) CU(cudaStreamSynchronize(d.stream[s]));
-  const double pairs = (double)(tri_row_start(F, row1) - tri_row_start(F, row0));
-  add_stats(tpack.resolve(), 1, tpair.resolve(), nLaunch, pairs, h2d, d2h);
+  add_stats(tpack.resolve(), 1, tpair.resolve(), nLaunch, (double)outElts, h2d, ring.d2h);
+  return B200_OK;
+}
+
+/// Runs fn(deviceIndex) on one host thread per initialised device (on the caller's thread when there is one device).
+template <typename F>
+int for_each_device(F&& fn) {
+  const int nd = (int)g_devs.size();
+  if (nd == 1) return fn(0);
+  std::vector<int> rcs(nd, 0);
+  std::vector<std::thread> th;
+  for (int i = 0; i < nd; ++i) th.emplace_back([&, i]() { rcs[i] = fn(i); });
+  for (auto& t : th) t.join();
+  cudaSetDevice(g_devs[0].id);
+  for (int r : rcs) if (r) return r;
   return B200_OK;
 }
 
@@ -867,12 +1120,18 @@ static int init_ids_locked(const int* ids, int want) {
   bool same = g_inited && (int)g_devs.size() == want;
   for (int i = 0; same && i < want; ++i) same = (g_devs[i].id == ids[i]);
   if (same) return B200_OK;
-  for (auto& d : g_devs) d.destroy();
+  for (Device& d : g_devs) d.destroy();
   g_devs.clear();
   g_devs.resize(want);
   for (int i = 0; i < want; ++i) {
     int rc = init_device(g_devs[i], ids[i]);
-    if (rc) { for (auto& d : g_devs) d.destroy(); g_devs.clear(); g_inited = false; return rc; }
+    if (rc) { for (Device& d : g_devs) d.destroy(); g_devs.clear(); g_inited = false; return rc; }
+  }
+  for (Device& d : g_devs) {
+    // fresh pages make the result side the heavier one: it gets the larger share of the host threads
+    const int nt = host_threads_per_device(want);
+    d.pool.ensure(std::max(1, nt * 3 / 8));
+    d.poolOut.ensure(std::max(1, nt - nt * 3 / 8));
   }
   cudaSetDevice(g_devs[0].id);
   g_inited = true;
@@ -914,7 +1173,7 @@ int b200_init_devices(const int* deviceIds, int n) {
 
 void b200_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  for (auto& d : g_devs) d.destroy();
+  for (Device& d : g_devs) d.destroy();
   g_devs.clear();
   g_inited = false;
 }
@@ -930,7 +1189,7 @@ int b200_shard_rows(int nFrames, int shardRank, int shardCount, int* row0, int* 
 }
 
 void b200_set_profiling(int on) { g_profiling = (on != 0); }
-int b200_set_mma_variant(int v) { if (v < 0 || v > 3) return fail(B200_ERR_ARG, "variant must be 0..3"); g_variant = v; return B200_OK; }
+int b200_set_mma_variant(int v) { if (v < 0 || v > 3) return fail(B200_ERR_ARG, "variant must be 0..3"); g_variant.store(v); return B200_OK; }
 void b200_reset_stats(void) { std::lock_guard<std::mutex> lk(g_statMu); g_stats = b200_stats(); g_launches.store(0); }
 void b200_get_stats(b200_stats* out) { if (!out) return; std::lock_guard<std::mutex> lk(g_statMu); *out = g_stats; out->kernel_launches = g_launches.load(); }
 
@@ -957,45 +1216,41 @@ int b200_rms2d_tri(const float* crd, size_t frameStrideFloats, int nFramesTotal,
   int rc;
   if ((rc = ensure_init_locked())) return rc;
   const int nd = (int)g_devs.size();
-  if (nd == 1)
-    return host_tri_on_device(g_devs[0], crd, frameStrideFloats, nFramesTotal, frameIdx, nFrames, atomIdx, nAtoms, mass, fit,
-                              0, nFrames, outTri);
-  // one host thread per device; shards are disjoint contiguous ranges of outTri
-  std::vector<int> rcs(nd, 0);
-  std::vector<std::thread> th;
-  for (int i = 0; i < nd; ++i) {
-    th.emplace_back([&, i]() {
-      int r0 = 0, r1 = 0;
-      int r = shard_rows(nFrames, i, nd, &r0, &r1);
-      if (!r) r = host_tri_on_device(g_devs[i], crd, frameStrideFloats, nFramesTotal, frameIdx, nFrames, atomIdx, nAtoms,
-                                     mass, fit, r0, r1, outTri);
-      rcs[i] = r;
-    });
-  }
-  for (auto& t : th) t.join();
-  cudaSetDevice(g_devs[0].id);
-  for (int r : rcs) if (r) return r;
-  return B200_OK;
+  // one host thread per device; shards are disjoint contiguous ranges of outTri; the threads agree on one
+  // fixed-point grid (and engine) for the whole matrix
+  ExtentShare share;
+  share.parties = nd;
+  return for_each_device([&](int i) -> int {
+    int r0 = 0, r1 = 0;
+    int r = shard_rows(nFrames, i, nd, &r0, &r1);
+    if (r) { if (nd > 1) share.abandon(); return r; }
+    return host_tri_on_device(g_devs[i], crd, frameStrideFloats, nFramesTotal, frameIdx, nFrames, atomIdx, nAtoms, mass, fit,
+                              r0, r1, outTri, nd > 1 ? &share : nullptr);
+  });
 }
 
-int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* atomIdxTgt, const float* crdRef,
-                    size_t strideRef, int nRef, const int* atomIdxRef, int nAtoms, const double* massTgt,
-                    const double* massRefCentering, int fit, float* outFull) {
-  if (!crdTgt || !crdRef || !outFull) return fail(B200_ERR_ARG, "null buffer");
-  if (nTgt <= 0 || nRef <= 0) return B200_OK;
-  std::lock_guard<std::mutex> lk(g_mu);
-  int rc;
-  if ((rc = ensure_init_locked())) return rc;
-  Device& d = g_devs[0];
+}  // extern "C"
+
+namespace {
+/// Target rows [t0,t1) of the full matrix on one device.
+int host_full_on_device(Device& d, const float* crdTgt, size_t strideTgt, int nTgt, const int* atomIdxTgt, const float* crdRef,
+                        size_t strideRef, int nRef, const int* atomIdxRef, int nAtoms, const double* massTgt,
+                        const double* massRefCentering, int fit, int t0, int t1, float* outFull, ExtentShare* share) {
+  ShareGuard guard(share);
   CU(cudaSetDevice(d.id));
-  int maxT = 0, maxR = 0;
+  if (t1 <= t0) {
+    if (share) { share->leave(); guard.settled = true; }
+    return B200_OK;
+  }
+  int maxT = 0, maxR = 0, rc;
   if ((rc = validate_sel(atomIdxTgt, nAtoms, strideTgt, &maxT))) return rc;
   if ((rc = validate_sel(atomIdxRef, nAtoms, strideRef, &maxR))) return rc;
   cudaStream_t st0 = d.stream[0];
-  double h2d = 0.0, d2h = 0.0;
+  double h2d = 0.0;
   const size_t wT = (size_t)3 * (maxT + 1), wR = (size_t)3 * (maxR + 1);
-  if ((rc = upload_crd(d.crd, crdTgt, strideTgt, 0, nTgt, wT, st0, &h2d))) return rc;
-  if ((rc = upload_crd(d.crdB, crdRef, strideRef, 0, nRef, wR, st0, &h2d))) return rc;
+  const int nT = t1 - t0;   // this device's targets: frames t0.. of crdTgt are rows 0.. of the device copy
+  if ((rc = upload_crd(d, d.crd, crdTgt, strideTgt, t0, t1, wT, st0, &h2d))) return rc;
+  if ((rc = upload_crd(d, d.crdB, crdRef, strideRef, 0, nRef, wR, st0, &h2d))) return rc;
   if ((rc = upload_vec(d.idxA, atomIdxTgt, (size_t)nAtoms, st0))) return rc;
   if ((rc = upload_vec(d.idxB, atomIdxRef, (size_t)nAtoms, st0))) return rc;
   if (massTgt && (rc = upload_vec(d.massA, massTgt, (size_t)nAtoms, st0))) return rc;
@@ -1019,24 +1274,25 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
   int qs = 0;
   const int engine = pair_engine();
   if (fit && engine != 1) {
-    if ((rc = i8_reserve(qA, d.imgA, d.GA, d.cenA, nTgt, nAtoms))) return rc;
+    if ((rc = i8_reserve(qA, d.imgA, d.GA, d.cenA, nT, nAtoms))) return rc;
     if ((rc = i8_reserve(qB, d.imgB, d.GB, d.cenB, nRef, nAtoms))) return rc;
     CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st0));
     if ((rc = i8_stats(qA, (const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_maxBits, st0))) return rc;
     if ((rc = i8_stats(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_maxBits, st0))) return rc;
-    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st0, &qs, &useI8))) return rc;
+    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st0, &qs, &useI8, share))) return rc;
     if (useI8) {
       if ((rc = i8_clear(qA, st0)) || (rc = i8_clear(qB, st0))) return rc;
       if ((rc = i8_quant(qA, (const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, nAtoms, dmT, qs, st0))) return rc;
       if ((rc = i8_quant(qB, (const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, nAtoms, dmT, qs, st0))) return rc;
     } else if (engine == 2) {
-      return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but the selection's extent leaves only %d fractional bits", qs);
+      return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but the selection does not qualify (%d fractional bits, %d atoms)", qs, nAtoms);
     }
   } else if (engine == 2) {
     return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but nofit RMSD runs on the FP64 engine only");
   }
+  guard.settled = true;
   if (!useI8) {
-    A.nFrames = nTgt; A.Fpad = round_up(nTgt, ROWG); A.Kpad = round_up(nAtoms, KC);
+    A.nFrames = nT; A.Fpad = round_up(nT, ROWG); A.Kpad = round_up(nAtoms, KC);
     B.nFrames = nRef; B.Fpad = round_up(nRef, ROWG); B.Kpad = A.Kpad;
     if ((rc = d.planesA.reserve(plane_doubles(A.Fpad, A.Kpad) * sizeof(double)))) return rc;
     if ((rc = d.planesB.reserve(plane_doubles(B.Fpad, B.Kpad) * sizeof(double)))) return rc;
@@ -1044,8 +1300,9 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
     if ((rc = d.GB.reserve((size_t)B.Fpad * sizeof(double)))) return rc;
     A.planes = (double*)d.planesA.p; A.G = (double*)d.GA.p;
     B.planes = (double*)d.planesB.p; B.G = (double*)d.GB.p;
-    if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st0>>>((const float*)d.crd.p, wT, nullptr, 0, 0, (const int*)d.idxA.p, d_shift); }
-    if ((rc = run_pack((const float*)d.crd.p, wT, nullptr, 0, nTgt, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_shift, fit, A, st0))) return rc;
+    // nofit: a common origin for both sets (the first selected atom of the first REFERENCE frame: every device has it)
+    if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st0>>>((const float*)d.crdB.p, wR, nullptr, 0, 0, (const int*)d.idxB.p, d_shift); }
+    if ((rc = run_pack((const float*)d.crd.p, wT, nullptr, 0, nT, 0, (const int*)d.idxA.p, nAtoms, dmT, dmT, d_shift, fit, A, st0))) return rc;
     if ((rc = run_pack((const float*)d.crdB.p, wR, nullptr, 0, nRef, 0, (const int*)d.idxB.p, nAtoms, dmR, dmT, d_shift, fit, B, st0))) return rc;
   }
   tpack.end(st0);
@@ -1053,31 +1310,21 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
   // rows (targets) in bands; each band is a contiguous slab of outFull
   const size_t ld = (size_t)nRef;
   int bandRows = (int)std::min<size_t>(1024, std::max<size_t>(ROWG, ((size_t)32 << 20) / (4 * ld) / ROWG * ROWG));
-  const bool pinnedOut = host_ptr_is_pinned(outFull);
-  const size_t maxChunk = (size_t)std::min(bandRows, nTgt) * ld;
+  float* outFirst = outFull + (size_t)t0 * ld;
+  OutRing ring(d, outFull, host_ptr_is_pinned(outFirst), outFirst, (size_t)nT * ld, false);
+  const size_t maxChunk = (size_t)std::min(bandRows, nT) * ld;
   CU(cudaEventRecord(d.done[0], st0));
   for (int s = 1; s < NSLOT; ++s) CU(cudaStreamWaitEvent(d.stream[s], d.done[0], 0));
-  for (int s = 0; s < NSLOT; ++s) {
-    if ((rc = d.outChunk[s].reserve(maxChunk * sizeof(float)))) return rc;
-    if (!pinnedOut && (rc = d.outStage[s].reserve(maxChunk * sizeof(float)))) return rc;
-  }
-  struct Pending { size_t base = 0, n = 0; bool live = false; } pend[NSLOT];
-  auto retire = [&](int s) -> int {
-    if (!pend[s].live) return B200_OK;
-    CU(cudaEventSynchronize(d.done[s]));
-    if (!pinnedOut) std::memcpy(outFull + pend[s].base, d.outStage[s].p, pend[s].n * sizeof(float));
-    pend[s].live = false;
-    return B200_OK;
-  };
+  for (int s = 0; s < NSLOT; ++s) if ((rc = ring.reserve(s, maxChunk))) return rc;
   int band = 0; long nLaunch = 0;
-  for (int i0 = 0; i0 < nTgt; i0 += bandRows, ++band) {
+  for (int i0 = 0; i0 < nT; i0 += bandRows, ++band) {
     const int s = band % NSLOT;
-    if ((rc = retire(s))) return rc;
-    const int i1 = std::min(nTgt, i0 + bandRows);
+    if ((rc = ring.retire(s))) return rc;
+    const int i1 = std::min(nT, i0 + bandRows);
     cudaStream_t st = d.stream[s];
     const size_t base = (size_t)i0 * ld, n = (size_t)(i1 - i0) * ld;
     tpair.begin(st);
-    // kernel indexes out[i*ld + j]; shift the pointer so row i0 lands at the chunk start
+    // kernel indexes out[i*ld + j] with i the device-local target row; shift the pointer so row i0 lands at the chunk start
     if (useI8)
       rc = run_pair_i8_band(d, qA, qB, i0, i1, false, qs, d_total, (float*)d.outChunk[s].p - base, 0, ld, nullptr, st);
     else
@@ -1086,16 +1333,35 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
     if (rc) return rc;
     tpair.end(st);
     ++nLaunch;
-    float* dst = pinnedOut ? outFull + base : (float*)d.outStage[s].p;
-    CU(cudaMemcpyAsync(dst, d.outChunk[s].p, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-    d2h += (double)n * sizeof(float);
-    CU(cudaEventRecord(d.done[s], st));
-    pend[s].base = base; pend[s].n = n; pend[s].live = true;
+    if ((rc = ring.download(s, (size_t)t0 * ld + base, n, st))) return rc;
   }
-  for (int s = 0; s < NSLOT; ++s) if ((rc = retire(s))) return rc;
+  if ((rc = ring.drain())) return rc;
   for (int s = 0; s < NSLOT; ++s) CU(cudaStreamSynchronize(d.stream[s]));
-  add_stats(tpack.resolve(), 2, tpair.resolve(), nLaunch, (double)nTgt * (double)nRef, h2d, d2h);
+  add_stats(tpack.resolve(), 2, tpair.resolve(), nLaunch, (double)nT * (double)nRef, h2d, ring.d2h);
   return B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* atomIdxTgt, const float* crdRef,
+                    size_t strideRef, int nRef, const int* atomIdxRef, int nAtoms, const double* massTgt,
+                    const double* massRefCentering, int fit, float* outFull) {
+  if (!crdTgt || !crdRef || !outFull) return fail(B200_ERR_ARG, "null buffer");
+  if (nTgt <= 0 || nRef <= 0) return B200_OK;
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  // target rows in equal, 32-row aligned shares over the devices (every pair costs the same here)
+  const int nd = (int)g_devs.size();
+  const int per = round_up((nTgt + nd - 1) / nd, ROWG);
+  ExtentShare share;
+  share.parties = nd;
+  return for_each_device([&](int i) -> int {
+    const int t0 = std::min(nTgt, i * per), t1 = std::min(nTgt, (i + 1) * per);
+    return host_full_on_device(g_devs[i], crdTgt, strideTgt, nTgt, atomIdxTgt, crdRef, strideRef, nRef, atomIdxRef, nAtoms,
+                               massTgt, massRefCentering, fit, t0, t1, outFull, nd > 1 ? &share : nullptr);
+  });
 }
 
 int b200_dev_rms2d_tri(const float* d_crd, size_t frameStrideFloats, const int* d_frameIdx, int nFrames,
@@ -1108,7 +1374,7 @@ int b200_dev_rms2d_tri(const float* d_crd, size_t frameStrideFloats, const int* 
   int dev = 0;
   CU(cudaGetDevice(&dev));
   Device* d = nullptr;
-  for (auto& x : g_devs) if (x.id == dev) d = &x;
+  for (Device& x : g_devs) if (x.id == dev) d = &x;
   if (!d) return fail(B200_ERR_STATE, "current device %d was not initialised by b200_init", dev);
   int r0 = 0, r1 = 0;
   if ((rc = shard_rows(nFrames, shardRank, shardCount, &r0, &r1))) return rc;
@@ -1129,42 +1395,75 @@ int b200_dev_rms2d_tri(const float* d_crd, size_t frameStrideFloats, const int* 
 }  // extern "C"
 
 // ------------------------------------------------------------------ one-vs-many
-struct b200_1vN {
+// A streaming handle spreads its chunks round-robin over the initialised devices ("lanes"): every lane has its own
+// stream, input ring and result arrays; a segment list remembers where the results of each pushed chunk live so that
+// flush() returns them in push order (DataSet_double::Add is append-only, src/DataSet_double.cpp:14-20).
+constexpr int ONEVN_NIN = 2;   // input ring slots per lane
+struct OneVNLane {
   Device* dev = nullptr;
-  int nAtoms = 0, fit = 1, wantRot = 0;
-  std::vector<int> atomIdx;
-  DevBuf refw, refsum, idx, in[NSLOT], rms, rot, trans, ws;
-  PinBuf stage[NSLOT];
+  DevBuf refw, refsum, ref, mass, idx, in[ONEVN_NIN], rms, rot, trans, ws;
+  PinBuf stage[ONEVN_NIN];
   cudaStream_t st = nullptr;         // single in-order stream (+ events for slot reuse)
-  cudaEvent_t slotFree[NSLOT] = {nullptr, nullptr, nullptr};
-  long pushed = 0, flushed = 0, cap = 0;
+  cudaEvent_t slotFree[ONEVN_NIN] = {};
+  cudaEvent_t copied = nullptr;      // last H2D copy that read the caller's (pinned) buffer
+  bool touched = false;
   int slot = 0;
-  long bestFrame = -1;
-  double bestVal = 0.0;
+  long cap = 0, used = 0;            // result slots allocated / holding unflushed results
   Timer timer;
-  double h2d = 0.0, d2h = 0.0;
   long launches = 0;
 };
+struct OneVNSegment { int lane; long laneOff, n; };
+struct b200_1vN {
+  int nAtoms = 0, fit = 1, wantRot = 0, maxAtom = 0;
+  bool identity = false, hasMass = false;
+  std::vector<int> atomIdx;
+  std::vector<std::unique_ptr<OneVNLane>> lanes;
+  std::vector<OneVNSegment> segs;    // unflushed chunks in push order
+  int nextLane = 0;
+  long pushed = 0, flushed = 0;
+  long bestFrame = -1;
+  double bestVal = 0.0;
+  double h2d = 0.0, d2h = 0.0;
+};
 
-static int onevn_grow(b200_1vN* h, long need) {
-  if (need <= h->cap) return B200_OK;
-  long ncap = std::max<long>(need, std::max<long>(h->cap * 2, 1 << 16));
+static void onevn_destroy(b200_1vN* h) {
+  if (!h) return;
+  for (auto& lp : h->lanes) {
+    OneVNLane& L = *lp;
+    if (L.dev) cudaSetDevice(L.dev->id);
+    if (L.st) { cudaStreamSynchronize(L.st); cudaStreamDestroy(L.st); }
+    for (int s = 0; s < ONEVN_NIN; ++s) { if (L.slotFree[s]) cudaEventDestroy(L.slotFree[s]); L.in[s].release(); L.stage[s].release(); }
+    if (L.copied) cudaEventDestroy(L.copied);
+    DevBuf* all[] = {&L.refw, &L.refsum, &L.ref, &L.mass, &L.idx, &L.rms, &L.rot, &L.trans, &L.ws};
+    for (DevBuf* b : all) b->release();
+    L.timer.resolve();
+  }
+  if (!g_devs.empty()) cudaSetDevice(g_devs[0].id);
+  delete h;
+}
+
+/// Room for `need` unflushed results on a lane (the live ones are kept).
+static int onevn_grow(b200_1vN* h, OneVNLane& L, long need) {
+  if (need <= L.cap) return B200_OK;
+  long ncap = std::max<long>(need, std::max<long>(L.cap * 2, 1 << 16));
   DevBuf nr, no, nt;
   int rc;
   if ((rc = nr.reserve((size_t)ncap * 8))) return rc;
-  if (h->wantRot) { if ((rc = no.reserve((size_t)ncap * 72))) return rc; if ((rc = nt.reserve((size_t)ncap * 24))) return rc; }
-  const long live0 = h->flushed, live1 = h->pushed;
-  if (live1 > live0) {
-    CU(cudaMemcpyAsync((double*)nr.p + live0, (double*)h->rms.p + live0, (size_t)(live1 - live0) * 8, cudaMemcpyDeviceToDevice, h->st));
+  if (h->wantRot) {
+    if ((rc = no.reserve((size_t)ncap * 72))) { nr.release(); return rc; }
+    if ((rc = nt.reserve((size_t)ncap * 24))) { nr.release(); no.release(); return rc; }
+  }
+  if (L.used > 0) {
+    CU(cudaMemcpyAsync(nr.p, L.rms.p, (size_t)L.used * 8, cudaMemcpyDeviceToDevice, L.st));
     if (h->wantRot) {
-      CU(cudaMemcpyAsync((double*)no.p + 9 * live0, (double*)h->rot.p + 9 * live0, (size_t)(live1 - live0) * 72, cudaMemcpyDeviceToDevice, h->st));
-      CU(cudaMemcpyAsync((double*)nt.p + 3 * live0, (double*)h->trans.p + 3 * live0, (size_t)(live1 - live0) * 24, cudaMemcpyDeviceToDevice, h->st));
+      CU(cudaMemcpyAsync(no.p, L.rot.p, (size_t)L.used * 72, cudaMemcpyDeviceToDevice, L.st));
+      CU(cudaMemcpyAsync(nt.p, L.trans.p, (size_t)L.used * 24, cudaMemcpyDeviceToDevice, L.st));
     }
   }
-  CU(cudaStreamSynchronize(h->st));
-  h->rms.release(); h->rot.release(); h->trans.release();
-  h->rms = nr; h->rot = no; h->trans = nt;
-  h->cap = ncap;
+  CU(cudaStreamSynchronize(L.st));
+  L.rms.release(); L.rot.release(); L.trans.release();
+  L.rms = nr; L.rot = no; L.trans = nt;
+  L.cap = ncap;
   return B200_OK;
 }
 
@@ -1189,12 +1488,12 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
   const char* env = getenv("B200_1VN_STREAM");
   const bool stream = aligned && !(env && atoi(env) == 0);
   if (stream) {
-    static bool attr[64][2] = {};
+    static std::atomic<bool> attr[64][2];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr[dev & 63][sizeof(T) == 8]) {
+    if (!attr[dev & 63][sizeof(T) == 8].load(std::memory_order_acquire)) {
       CU(cudaFuncSetAttribute(onevn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONEVN_S_SMEM_BYTES));
-      attr[dev & 63][sizeof(T) == 8] = true;
+      attr[dev & 63][sizeof(T) == 8].store(true, std::memory_order_release);
     }
     COUNT_LAUNCH();
     onevn_chunks_kernel<<<1, 256, 0, st>>>(d_atomIdx, nAtoms, APC, maxChunks, hdr, kLo);
@@ -1220,17 +1519,34 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
 }
 
 template <typename T>
-static int onevn_launch(b200_1vN* h, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, long outOffset) {
+static int onevn_launch(b200_1vN* h, OneVNLane& L, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, long outOffset) {
   int rc;
-  if ((rc = h->ws.reserve(onevn_ws_bytes(stride, nFrames)))) return rc;
-  h->timer.begin(h->st);
-  rc = onevn_run<T>(h->dev->numSMs, d_crd, stride, nFrames, d_atomIdx, h->nAtoms, (const double*)h->refw.p,
-                    (const double*)h->refsum.p, h->fit, (double*)h->rms.p + outOffset,
-                    h->wantRot ? (double*)h->rot.p + 9 * outOffset : nullptr,
-                    h->wantRot ? (double*)h->trans.p + 3 * outOffset : nullptr, h->ws.p, h->st);
-  h->timer.end(h->st);
+  if ((rc = L.ws.reserve(onevn_ws_bytes(stride, nFrames)))) return rc;
+  L.timer.begin(L.st);
+  rc = onevn_run<T>(L.dev->numSMs, d_crd, stride, nFrames, d_atomIdx, h->nAtoms, (const double*)L.refw.p,
+                    (const double*)L.refsum.p, h->fit, (double*)L.rms.p + outOffset,
+                    h->wantRot ? (double*)L.rot.p + 9 * outOffset : nullptr,
+                    h->wantRot ? (double*)L.trans.p + 3 * outOffset : nullptr, L.ws.p, L.st);
+  L.timer.end(L.st);
   if (rc) return rc;
-  h->launches++;
+  L.launches++;
+  return B200_OK;
+}
+
+/// (Re)loads the reference of every lane: refw = (rx, ry, rz, m) per atom, refsum = its moments.
+static int onevn_load_ref(b200_1vN* h, const double* refSelected) {
+  int rc;
+  for (auto& lp : h->lanes) {
+    OneVNLane& L = *lp;
+    CU(cudaSetDevice(L.dev->id));
+    if ((rc = upload_vec(L.ref, refSelected, (size_t)3 * h->nAtoms, L.st))) return rc;
+    COUNT_LAUNCH();
+    onevn_setup_kernel<<<1, 256, 0, L.st>>>((const double*)L.ref.p, h->hasMass ? (const double*)L.mass.p : nullptr, h->nAtoms,
+                                           (double*)L.refw.p, (double*)L.refsum.p);
+    CU(cudaGetLastError());
+  }
+  // the caller's reference array may change as soon as we return (reftraj / previous): wait for the uploads
+  for (auto& lp : h->lanes) { CU(cudaSetDevice(lp->dev->id)); CU(cudaStreamSynchronize(lp->st)); }
   return B200_OK;
 }
 
@@ -1241,32 +1557,47 @@ int b200_rmsd_1vN_begin(const double* refSelected, const int* atomIdx, int nAtom
   if (!handle) return fail(B200_ERR_ARG, "null handle");
   *handle = nullptr;
   if (!refSelected || !atomIdx || nAtoms <= 0) return fail(B200_ERR_ARG, "bad reference / selection");
+  for (int k = 0; k < nAtoms; ++k) if (atomIdx[k] < 0) return fail(B200_ERR_ARG, "negative atom index");
   std::lock_guard<std::mutex> lk(g_mu);
   int rc;
   if ((rc = ensure_init_locked())) return rc;
   b200_1vN* h = new (std::nothrow) b200_1vN();
   if (!h) return fail(B200_ERR_NOMEM, "out of memory");
-  h->dev = &g_devs[0];
-  CU(cudaSetDevice(h->dev->id));
-  h->nAtoms = nAtoms; h->fit = fit ? 1 : 0; h->wantRot = (wantRot && fit) ? 1 : 0;
+  h->nAtoms = nAtoms; h->fit = fit ? 1 : 0; h->wantRot = (wantRot && fit) ? 1 : 0; h->hasMass = mass != nullptr;
   h->atomIdx.assign(atomIdx, atomIdx + nAtoms);
-  for (int k = 0; k < nAtoms; ++k) if (atomIdx[k] < 0) { delete h; return fail(B200_ERR_ARG, "negative atom index"); }
-  CU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
-  for (int s = 0; s < NSLOT; ++s) CU(cudaEventCreateWithFlags(&h->slotFree[s], cudaEventDisableTiming));
-  DevBuf ref, m;
-  if ((rc = upload_vec(ref, refSelected, (size_t)3 * nAtoms, h->st))) { delete h; return rc; }
-  if (mass && (rc = upload_vec(m, mass, (size_t)nAtoms, h->st))) { delete h; return rc; }
-  if ((rc = upload_vec(h->idx, atomIdx, (size_t)nAtoms, h->st))) { delete h; return rc; }
-  if ((rc = h->refw.reserve((size_t)nAtoms * 32))) { delete h; return rc; }
-  if ((rc = h->refsum.reserve(64))) { delete h; return rc; }
-  COUNT_LAUNCH();
-  onevn_setup_kernel<<<1, 256, 0, h->st>>>((const double*)ref.p, mass ? (const double*)m.p : nullptr, nAtoms, (double*)h->refw.p,
-                                          (double*)h->refsum.p);
-  CU(cudaGetLastError());
-  CU(cudaStreamSynchronize(h->st));
-  ref.release(); m.release();
+  h->identity = true;
+  for (int k = 0; k < nAtoms; ++k) { h->maxAtom = std::max(h->maxAtom, atomIdx[k]); if (atomIdx[k] != k) h->identity = false; }
+  auto setup = [&]() -> int {
+    for (Device& d : g_devs) {
+      h->lanes.emplace_back(new OneVNLane());
+      OneVNLane& L = *h->lanes.back();
+      L.dev = &d;
+      CU(cudaSetDevice(d.id));
+      CU(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+      for (int s = 0; s < ONEVN_NIN; ++s) CU(cudaEventCreateWithFlags(&L.slotFree[s], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&L.copied, cudaEventDisableTiming));
+      int r;
+      if (mass && (r = upload_vec(L.mass, mass, (size_t)nAtoms, L.st))) return r;
+      if ((r = upload_vec(L.idx, atomIdx, (size_t)nAtoms, L.st))) return r;
+      if ((r = L.refw.reserve((size_t)nAtoms * 32))) return r;
+      if ((r = L.refsum.reserve(64))) return r;
+    }
+    return onevn_load_ref(h, refSelected);
+  };
+  rc = setup();
+  cudaSetDevice(g_devs[0].id);
+  if (rc) { onevn_destroy(h); return rc; }
   *handle = h;
   return B200_OK;
+}
+
+int b200_rmsd_1vN_set_ref(b200_1vN* h, const double* refSelected) {
+  if (!h) return fail(B200_ERR_STATE, "null handle");
+  if (!refSelected) return fail(B200_ERR_ARG, "null reference");
+  std::lock_guard<std::mutex> lk(g_mu);
+  const int rc = onevn_load_ref(h, refSelected);   // in stream order: frames pushed so far keep the old reference
+  cudaSetDevice(g_devs[0].id);
+  return rc;
 }
 
 }  // extern "C"
@@ -1277,48 +1608,71 @@ static int onevn_push(b200_1vN* h, const T* src, size_t stride, int nFrames) {
   if (nFrames <= 0) return B200_OK;
   if (!src) return fail(B200_ERR_ARG, "null frames");
   std::lock_guard<std::mutex> lk(g_mu);
-  CU(cudaSetDevice(h->dev->id));
   int rc;
-  int maxAtom = 0;
-  for (int a : h->atomIdx) maxAtom = std::max(maxAtom, a);
-  if ((size_t)3 * ((size_t)maxAtom + 1) > stride) return fail(B200_ERR_ARG, "atom index %d outside frame stride %zu", maxAtom, stride);
-  if ((rc = onevn_grow(h, h->pushed + nFrames))) return rc;
+  if ((size_t)3 * ((size_t)h->maxAtom + 1) > stride)
+    return fail(B200_ERR_ARG, "atom index %d outside frame stride %zu", h->maxAtom, stride);
   const bool pinned = host_ptr_is_pinned(src);
   const int N = h->nAtoms;
-  // chunk so that a slot holds <= 64 MB
-  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  // chunk so that a slot holds <= 64 MB; several lanes: at least one chunk each when there is enough to share
+  const size_t width = (size_t)3 * ((size_t)h->maxAtom + 1);
   const size_t perFrame = pinned ? width * sizeof(T) : (size_t)3 * N * sizeof(T);
-  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nFrames, ((size_t)64 << 20) / perFrame));
+  const int nl = (int)h->lanes.size();
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nFrames, ((size_t)64 << 20) / perFrame));
+  if (nl > 1 && nFrames >= 64 * nl) chunk = std::min(chunk, (nFrames + nl - 1) / nl);
+  for (auto& lp : h->lanes) lp->touched = false;
   for (int f0 = 0; f0 < nFrames; f0 += chunk) {
     const int nf = std::min(chunk, nFrames - f0);
-    const int s = h->slot;
-    h->slot = (h->slot + 1) % NSLOT;
-    CU(cudaEventSynchronize(h->slotFree[s]));  // previous user of this slot is done (no-op when never recorded)
-    if ((rc = h->in[s].reserve((size_t)nf * perFrame))) return rc;
+    const int li = h->nextLane;
+    h->nextLane = (h->nextLane + 1) % nl;
+    OneVNLane& L = *h->lanes[li];
+    CU(cudaSetDevice(L.dev->id));
+    if ((rc = onevn_grow(h, L, L.used + nf))) return rc;
+    const int s = L.slot;
+    L.slot = (L.slot + 1) % ONEVN_NIN;
+    CU(cudaEventSynchronize(L.slotFree[s]));  // previous user of this slot is done (no-op when never recorded)
+    if ((rc = L.in[s].reserve((size_t)nf * perFrame))) return rc;
     if (pinned) {
       // direct DMA of the needed span; gather by atomIdx on the device
-      CU(cudaMemcpy2DAsync(h->in[s].p, width * sizeof(T), src + (size_t)f0 * stride, stride * sizeof(T), width * sizeof(T),
-                           (size_t)nf, cudaMemcpyHostToDevice, h->st));
-      if ((rc = onevn_launch<T>(h, h->in[s].p, width, nf, (const int*)h->idx.p, h->pushed))) return rc;
+      CU(cudaMemcpy2DAsync(L.in[s].p, width * sizeof(T), src + (size_t)f0 * stride, stride * sizeof(T), width * sizeof(T),
+                           (size_t)nf, cudaMemcpyHostToDevice, L.st));
+      CU(cudaEventRecord(L.copied, L.st));
+      L.touched = true;
+      if ((rc = onevn_launch<T>(h, L, L.in[s].p, width, nf, (const int*)L.idx.p, L.used))) return rc;
     } else {
-      // pageable source (e.g. a cpptraj Frame that is reused): gather selected atoms into pinned staging now
-      if ((rc = h->stage[s].reserve((size_t)nf * perFrame))) return rc;
-      T* stg = (T*)h->stage[s].p;
-      for (int f = 0; f < nf; ++f) {
-        const T* fr = src + (size_t)(f0 + f) * stride;
-        T* o = stg + (size_t)f * 3 * N;
-        for (int k = 0; k < N; ++k) {
-          const size_t a3 = (size_t)3 * h->atomIdx[k];
-          o[3 * k] = fr[a3]; o[3 * k + 1] = fr[a3 + 1]; o[3 * k + 2] = fr[a3 + 2];
-        }
+      // pageable source (e.g. cpptraj Frames that are reused): the copy pool packs the selected atoms into pinned staging
+      if ((rc = L.stage[s].reserve((size_t)nf * perFrame))) return rc;
+      T* stg = (T*)L.stage[s].p;
+      const T* base = src + (size_t)f0 * stride;
+      if (h->identity) {
+        L.dev->pool.copy2d(stg, (size_t)3 * N * sizeof(T), base, stride * sizeof(T), (size_t)3 * N * sizeof(T), (size_t)nf);
+      } else {
+        const int* ai = h->atomIdx.data();
+        const int fpp = std::max(1, (int)(((size_t)1 << 20) / ((size_t)3 * N * sizeof(T))));
+        L.dev->pool.run((size_t)(nf + fpp - 1) / fpp, [=](size_t pc) {
+          const int fEnd = std::min(nf, (int)(pc + 1) * fpp);
+          for (int f = (int)pc * fpp; f < fEnd; ++f) {
+            const T* fr = base + (size_t)f * stride;
+            T* o = stg + (size_t)f * 3 * N;
+            for (int k = 0; k < N; ++k) {
+              const size_t a3 = (size_t)3 * ai[k];
+              o[3 * k] = fr[a3]; o[3 * k + 1] = fr[a3 + 1]; o[3 * k + 2] = fr[a3 + 2];
+            }
+          }
+        });
       }
-      CU(cudaMemcpyAsync(h->in[s].p, stg, (size_t)nf * perFrame, cudaMemcpyHostToDevice, h->st));
-      if ((rc = onevn_launch<T>(h, h->in[s].p, (size_t)3 * N, nf, nullptr, h->pushed))) return rc;
+      CU(cudaMemcpyAsync(L.in[s].p, stg, (size_t)nf * perFrame, cudaMemcpyHostToDevice, L.st));
+      if ((rc = onevn_launch<T>(h, L, L.in[s].p, (size_t)3 * N, nf, nullptr, L.used))) return rc;
     }
-    CU(cudaEventRecord(h->slotFree[s], h->st));
+    CU(cudaEventRecord(L.slotFree[s], L.st));
+    h->segs.push_back({li, L.used, (long)nf});
+    L.used += nf;
     h->h2d += (double)nf * perFrame;
     h->pushed += nf;
   }
+  // the call is blocking as far as the caller's buffer is concerned: its last bytes have left for the device
+  for (auto& lp : h->lanes)
+    if (lp->touched) { CU(cudaSetDevice(lp->dev->id)); CU(cudaEventSynchronize(lp->copied)); }
+  cudaSetDevice(g_devs[0].id);
   return B200_OK;
 }
 
@@ -1335,26 +1689,37 @@ long b200_rmsd_1vN_pending(const b200_1vN* h) { return h ? h->pushed - h->flushe
 int b200_rmsd_1vN_flush(b200_1vN* h, double* rmsdOut, double* rotOut, double* transOut, long* argminFrame) {
   if (!h) return fail(B200_ERR_STATE, "null handle");
   std::lock_guard<std::mutex> lk(g_mu);
-  CU(cudaSetDevice(h->dev->id));
   const long n = h->pushed - h->flushed;
-  if (n > 0) {
-    if (!rmsdOut) return fail(B200_ERR_ARG, "null rmsdOut");
-    CU(cudaMemcpyAsync(rmsdOut, (double*)h->rms.p + h->flushed, (size_t)n * 8, cudaMemcpyDeviceToHost, h->st));
-    h->d2h += (double)n * 8;
-    if (rotOut && h->wantRot) { CU(cudaMemcpyAsync(rotOut, (double*)h->rot.p + 9 * h->flushed, (size_t)n * 72, cudaMemcpyDeviceToHost, h->st)); h->d2h += (double)n * 72; }
-    if (transOut && h->wantRot) { CU(cudaMemcpyAsync(transOut, (double*)h->trans.p + 3 * h->flushed, (size_t)n * 24, cudaMemcpyDeviceToHost, h->st)); h->d2h += (double)n * 24; }
+  if (n > 0 && !rmsdOut) return fail(B200_ERR_ARG, "null rmsdOut");
+  long at = 0;
+  for (const OneVNSegment& sg : h->segs) {
+    OneVNLane& L = *h->lanes[sg.lane];
+    CU(cudaSetDevice(L.dev->id));
+    CU(cudaMemcpyAsync(rmsdOut + at, (double*)L.rms.p + sg.laneOff, (size_t)sg.n * 8, cudaMemcpyDeviceToHost, L.st));
+    h->d2h += (double)sg.n * 8;
+    if (rotOut && h->wantRot) { CU(cudaMemcpyAsync(rotOut + 9 * at, (double*)L.rot.p + 9 * sg.laneOff, (size_t)sg.n * 72, cudaMemcpyDeviceToHost, L.st)); h->d2h += (double)sg.n * 72; }
+    if (transOut && h->wantRot) { CU(cudaMemcpyAsync(transOut + 3 * at, (double*)L.trans.p + 3 * sg.laneOff, (size_t)sg.n * 24, cudaMemcpyDeviceToHost, L.st)); h->d2h += (double)sg.n * 24; }
+    at += sg.n;
   }
-  CU(cudaStreamSynchronize(h->st));
+  double ms = 0.0;
+  long launches = 0;
+  for (auto& lp : h->lanes) {
+    CU(cudaSetDevice(lp->dev->id));
+    CU(cudaStreamSynchronize(lp->st));
+    ms += lp->timer.resolve(); launches += lp->launches;
+    lp->launches = 0; lp->used = 0;
+  }
+  cudaSetDevice(g_devs[0].id);
+  h->segs.clear();
   for (long i = 0; i < n; ++i) {
     if (h->bestFrame < 0 || rmsdOut[i] < h->bestVal) { h->bestVal = rmsdOut[i]; h->bestFrame = h->flushed + i; }
   }
   if (argminFrame) *argminFrame = h->bestFrame;
   {
-    const double ms = h->timer.resolve();
     std::lock_guard<std::mutex> sl(g_statMu);
-    g_stats.onevn_ms += ms; g_stats.onevn_launches += h->launches; g_stats.frames_1vN += (double)n;
+    g_stats.onevn_ms += ms; g_stats.onevn_launches += launches; g_stats.frames_1vN += (double)n;
     g_stats.h2d_bytes += h->h2d; g_stats.d2h_bytes += h->d2h;
-    h->launches = 0; h->h2d = 0; h->d2h = 0;
+    h->h2d = 0; h->d2h = 0;
   }
   h->flushed = h->pushed;
   return B200_OK;
@@ -1363,12 +1728,7 @@ int b200_rmsd_1vN_flush(b200_1vN* h, double* rmsdOut, double* rotOut, double* tr
 int b200_rmsd_1vN_end(b200_1vN* h) {
   if (!h) return B200_OK;
   std::lock_guard<std::mutex> lk(g_mu);
-  cudaSetDevice(h->dev->id);
-  if (h->st) { cudaStreamSynchronize(h->st); cudaStreamDestroy(h->st); }
-  for (int s = 0; s < NSLOT; ++s) { if (h->slotFree[s]) cudaEventDestroy(h->slotFree[s]); h->in[s].release(); h->stage[s].release(); }
-  h->refw.release(); h->refsum.release(); h->idx.release(); h->rms.release(); h->rot.release(); h->trans.release(); h->ws.release();
-  h->timer.resolve();
-  delete h;
+  onevn_destroy(h);
   return B200_OK;
 }
 
@@ -1383,7 +1743,7 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   int dev = 0;
   CU(cudaGetDevice(&dev));
   Device* d = nullptr;
-  for (auto& x : g_devs) if (x.id == dev) d = &x;
+  for (Device& x : g_devs) if (x.id == dev) d = &x;
   if (!d) return fail(B200_ERR_STATE, "current device %d was not initialised by b200_init", dev);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
@@ -1408,6 +1768,135 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
 }
 
 
+}  // extern "C"
+
+namespace {
+/// List positions [p0,p1) of the frames against all K centroids on one device.
+/// K >= 3 and a fitted RMSD the tcgen05 engine qualifies for: ONE frames x centroids contraction (the frames are read
+/// once, quantised once; the centroids are the column operand) -- the full-matrix mode of the pair engine.  Otherwise
+/// K streaming one-vs-many passes over the resident frames (K * 12 N bytes per frame; cheaper than quantising for
+/// K <= 2, and the only nofit / FP64 path).
+int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFramesTotal, const int* frameIdx, int p0, int p1,
+                             const int* atomIdx, int nAtoms, const double* mass, int fit, const double* centroids, int K,
+                             double* distOut, int* closestOut, double* closestDistOut, ExtentShare* share) {
+  ShareGuard guard(share);
+  CU(cudaSetDevice(d.id));
+  const int nP = p1 - p0;
+  if (nP <= 0) {
+    if (share) { share->leave(); guard.settled = true; }
+    return B200_OK;
+  }
+  int maxAtom = 0, rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, stride, &maxAtom))) return rc;
+  int sLo = p0, sHi = p1;
+  if (frameIdx) {
+    sLo = nFramesTotal; sHi = 0;
+    for (int f = p0; f < p1; ++f) {
+      if (frameIdx[f] < 0 || frameIdx[f] >= nFramesTotal) return fail(B200_ERR_ARG, "frameIdx[%d]=%d out of range", f, frameIdx[f]);
+      sLo = std::min(sLo, frameIdx[f]); sHi = std::max(sHi, frameIdx[f] + 1);
+    }
+  } else if (p1 > nFramesTotal) {
+    return fail(B200_ERR_ARG, "frame %d > nFramesTotal %d", p1, nFramesTotal);
+  }
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0, d2h = 0.0;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  if ((rc = upload_crd(d, d.crd, crd, stride, sLo, sHi, width, st, &h2d))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
+  if (frameIdx && (rc = upload_vec(d.frameIdx, frameIdx + p0, (size_t)nP, st))) return rc;
+  if ((rc = upload_vec(d.crdB, centroids, (size_t)K * 3 * (size_t)nAtoms, st))) return rc;
+  h2d += (double)K * 24.0 * nAtoms;
+  const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
+  const int* d_fidx = frameIdx ? (const int*)d.frameIdx.p : nullptr;
+  // outputs (device): frame-major table, nearest centroid and its distance
+  const size_t tabBytes = ((size_t)K * (size_t)nP * sizeof(double) + 63) & ~(size_t)63;
+  if ((rc = d.planesB.reserve(tabBytes + (size_t)nP * (sizeof(int) + sizeof(double)) + 128))) return rc;
+  double* dOutT = (double*)d.planesB.p;
+  double* dClosestDist = (double*)((char*)d.planesB.p + tabBytes);
+  int* dClosest = (int*)(dClosestDist + nP);
+  Timer t;
+  bool contracted = false;
+  const int engine = pair_engine();
+  if (fit && K >= 3 && engine != 1) {
+    // ---- one contraction on the tcgen05 engine
+    if ((rc = d.scal.reserve(64))) return rc;
+    double* d_total = (double*)d.scal.p;
+    unsigned int* d_maxBits = (unsigned int*)(d_total + 4);
+    COUNT_LAUNCH();
+    mass_sum_kernel<<<1, 32, 0, st>>>(d_mass, nAtoms, d_total);
+    I8Set qA, qB;
+    if ((rc = i8_reserve(qA, d.imgA, d.GA, d.cenA, nP, nAtoms))) return rc;
+    if ((rc = i8_reserve(qB, d.imgB, d.GB, d.cenB, K, nAtoms))) return rc;
+    CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st));
+    const long baseA = frameIdx ? (long)sLo : 0;   // row of the device copy = frameIdx[f] - sLo, or the list position itself
+    if ((rc = i8_stats(qA, d.crd.p, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
+    // centroids: double rows of 3 N, already gathered; cpptraj keeps them centred (Metric_RMS.cpp:66-81), so the
+    // centring here moves them by rounding noise only
+    if ((rc = i8_stats(qB, d.crdB.p, (size_t)3 * nAtoms, nullptr, 0, 0, nullptr, nAtoms, d_mass, d_mass, d_maxBits, st, -1, true))) return rc;
+    int qs = 0;
+    bool ok = false;
+    if ((rc = i8_choose_scale(d, d_maxBits, d_total, nAtoms, st, &qs, &ok, share))) return rc;
+    guard.settled = true;
+    if (ok) {
+      if ((rc = i8_clear(qA, st)) || (rc = i8_clear(qB, st))) return rc;
+      if ((rc = i8_quant(qA, d.crd.p, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, qs, st))) return rc;
+      if ((rc = i8_quant(qB, d.crdB.p, (size_t)3 * nAtoms, nullptr, 0, 0, nullptr, nAtoms, d_mass, qs, st, -1, true))) return rc;
+      if ((rc = d.outChunk[0].reserve((size_t)nP * K * sizeof(float)))) return rc;
+      t.begin(st);
+      if ((rc = run_pair_i8_band(d, qA, qB, 0, nP, false, qs, d_total, (float*)d.outChunk[0].p, 0, (size_t)K, nullptr, st))) return rc;
+      COUNT_LAUNCH();
+      centroid_argmin_rows_kernel<<<(nP + 255) / 256, 256, 0, st>>>((const float*)d.outChunk[0].p, nP, K, distOut ? dOutT : nullptr,
+                                                                    dClosest, dClosestDist);
+      t.end(st);
+      contracted = true;
+      g_lastEngine.store(2); g_lastQs.store(qs);
+    } else if (engine == 2) {
+      return fail(B200_ERR_ARG, "tcgen05 int8 engine forced but the selection does not qualify (%d fractional bits, %d atoms)", qs, nAtoms);
+    }
+  } else if (share) {
+    share->leave(); guard.settled = true;
+  }
+  if (!contracted) {
+    // ---- K streaming passes
+    const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
+    const size_t wsBytes = (onevn_ws_bytes(width, nP) + 63) & ~(size_t)63;
+    const size_t distBytes = (size_t)K * (size_t)nP * sizeof(double);
+    if ((rc = d.onevnWs.reserve(refBytes + wsBytes + distBytes))) return rc;
+    char* base = (char*)d.onevnWs.p;
+    double* refw = (double*)base;
+    double* refsum = refw + (size_t)4 * nAtoms;
+    void* ws = base + refBytes;
+    double* dist = (double*)(base + refBytes + wsBytes);
+    t.begin(st);
+    for (int k = 0; k < K; ++k) {
+      COUNT_LAUNCH();
+      onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
+      if ((rc = onevn_run<float>(d.numSMs, d.crd.p, width, nP, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
+                                 dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, (long)sLo))) return rc;
+    }
+    COUNT_LAUNCH();
+    centroid_argmin_kernel<<<(nP + 255) / 256, 256, 0, st>>>(dist, nP, K, distOut ? dOutT : nullptr, dClosest, dClosestDist);
+    t.end(st);
+    g_lastEngine.store(1); g_lastQs.store(0);
+  }
+  if (distOut) { CU(cudaMemcpyAsync(distOut + (size_t)p0 * K, dOutT, (size_t)K * nP * sizeof(double), cudaMemcpyDeviceToHost, st)); d2h += 8.0 * K * nP; }
+  if (closestOut) { CU(cudaMemcpyAsync(closestOut + p0, dClosest, (size_t)nP * sizeof(int), cudaMemcpyDeviceToHost, st)); d2h += 4.0 * nP; }
+  if (closestDistOut) { CU(cudaMemcpyAsync(closestDistOut + p0, dClosestDist, (size_t)nP * sizeof(double), cudaMemcpyDeviceToHost, st)); d2h += 8.0 * nP; }
+  CU(cudaStreamSynchronize(st));
+  {
+    const double ms = t.resolve();
+    std::lock_guard<std::mutex> sl(g_statMu);
+    if (contracted) { g_stats.pair_ms += ms; g_stats.pair_launches += 1; g_stats.pairs += (double)nP * K; }
+    else { g_stats.onevn_ms += ms; g_stats.onevn_launches += K; g_stats.frames_1vN += (double)nP * K; }
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h;
+  }
+  return B200_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal, const int* frameIdx, int nFrames,
                                   const int* atomIdx, int nAtoms, const double* mass, int fit, const double* centroids,
                                   int nCentroids, double* distOut, int* closestOut, double* closestDistOut) {
@@ -1416,70 +1905,18 @@ int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, in
   std::lock_guard<std::mutex> lk(g_mu);
   int rc;
   if ((rc = ensure_init_locked())) return rc;
-  Device& d = g_devs[0];
-  CU(cudaSetDevice(d.id));
-  int maxAtom = 0;
-  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
-  int sLo = 0, sHi = nFrames;
-  if (frameIdx) {
-    sLo = nFramesTotal; sHi = 0;
-    for (int f = 0; f < nFrames; ++f) {
-      if (frameIdx[f] < 0 || frameIdx[f] >= nFramesTotal) return fail(B200_ERR_ARG, "frameIdx[%d]=%d out of range", f, frameIdx[f]);
-      sLo = std::min(sLo, frameIdx[f]); sHi = std::max(sHi, frameIdx[f] + 1);
-    }
-  } else if (nFrames > nFramesTotal) {
-    return fail(B200_ERR_ARG, "nFrames %d > nFramesTotal %d", nFrames, nFramesTotal);
-  }
-  cudaStream_t st = d.stream[0];
-  double h2d = 0.0;
-  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
-  if ((rc = upload_crd(d.crd, crd, frameStrideFloats, sLo, sHi, width, st, &h2d))) return rc;
-  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
-  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
-  if (frameIdx && (rc = upload_vec(d.frameIdx, frameIdx, (size_t)nFrames, st))) return rc;
-  DevBuf cen;
-  if ((rc = upload_vec(cen, centroids, (size_t)nCentroids * 3 * (size_t)nAtoms, st))) return rc;
-  // workspace: refw + refsum | one-vs-many workspace | dist [K][nFrames] | outputs
-  const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
-  const size_t wsBytes = (onevn_ws_bytes(width, nFrames) + 63) & ~(size_t)63;
-  const size_t distBytes = (size_t)nCentroids * (size_t)nFrames * sizeof(double);
-  const size_t outBytes = distBytes + (size_t)nFrames * (sizeof(int) + sizeof(double)) + 64;
-  if ((rc = d.onevnWs.reserve(refBytes + wsBytes + distBytes + outBytes))) { cen.release(); return rc; }
-  char* base = (char*)d.onevnWs.p;
-  double* refw = (double*)base;
-  double* refsum = refw + (size_t)4 * nAtoms;
-  void* ws = base + refBytes;
-  double* dist = (double*)(base + refBytes + wsBytes);
-  double* dOutT = (double*)((char*)dist + distBytes);
-  double* dClosestDist = dOutT + (size_t)nCentroids * nFrames;
-  int* dClosest = (int*)(dClosestDist + nFrames);
-  const double* d_mass = mass ? (const double*)d.massA.p : nullptr;
-  Timer t;
-  t.begin(st);
-  for (int k = 0; k < nCentroids; ++k) {
-    COUNT_LAUNCH();
-    onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)cen.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
-    if ((rc = onevn_run<float>(d.numSMs, d.crd.p, width, nFrames, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
-                               dist + (size_t)k * nFrames, nullptr, nullptr, ws, st,
-                               frameIdx ? (const int*)d.frameIdx.p : nullptr, (long)sLo))) { cen.release(); return rc; }
-  }
-  COUNT_LAUNCH();
-  centroid_argmin_kernel<<<(nFrames + 255) / 256, 256, 0, st>>>(dist, nFrames, nCentroids, distOut ? dOutT : nullptr, dClosest,
-                                                                 dClosestDist);
-  t.end(st);
-  double d2h = 0.0;
-  if (distOut) { CU(cudaMemcpyAsync(distOut, dOutT, distBytes, cudaMemcpyDeviceToHost, st)); d2h += (double)distBytes; }
-  if (closestOut) { CU(cudaMemcpyAsync(closestOut, dClosest, (size_t)nFrames * sizeof(int), cudaMemcpyDeviceToHost, st)); d2h += 4.0 * nFrames; }
-  if (closestDistOut) { CU(cudaMemcpyAsync(closestDistOut, dClosestDist, (size_t)nFrames * sizeof(double), cudaMemcpyDeviceToHost, st)); d2h += 8.0 * nFrames; }
-  CU(cudaStreamSynchronize(st));
-  cen.release();
-  {
-    const double ms = t.resolve();
-    std::lock_guard<std::mutex> sl(g_statMu);
-    g_stats.onevn_ms += ms; g_stats.onevn_launches += nCentroids; g_stats.frames_1vN += (double)nFrames * nCentroids;
-    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += d2h;
-  }
-  return B200_OK;
+  // frames in equal contiguous shares over the devices (small jobs stay on one)
+  const int nd = nFrames >= 4096 ? (int)g_devs.size() : 1;
+  const int per = (nFrames + nd - 1) / nd;
+  ExtentShare share;
+  share.parties = nd;
+  auto job = [&](int i) -> int {
+    const int p0 = std::min(nFrames, i * per), p1 = std::min(nFrames, (i + 1) * per);
+    return host_centroids_on_device(g_devs[i], crd, frameStrideFloats, nFramesTotal, frameIdx, p0, p1, atomIdx, nAtoms, mass, fit,
+                                    centroids, nCentroids, distOut, closestOut, closestDistOut, nd > 1 ? &share : nullptr);
+  };
+  if (nd == 1) return job(0);
+  return for_each_device(job);
 }
 
 int b200_debug_i8_clocks(long long* out, int ctas) {
@@ -1501,12 +1938,17 @@ int b200_debug_i8_clocks(long long* out, int ctas) {
 
 int b200_set_pair_engine(int engine) {
   if (engine < 0 || engine > 2) return fail(B200_ERR_ARG, "engine must be 0 (auto), 1 (fp64) or 2 (tcgen05 int8)");
-  g_engine = engine;
+  g_engine.store(engine);
+  return B200_OK;
+}
+int b200_set_fixed_point_bits(int bits) {
+  if (bits < 0 || bits > 30) return fail(B200_ERR_ARG, "fractional bits must be 0 (automatic) or 1..30");
+  g_fixedQs.store(bits);
   return B200_OK;
 }
 int b200_set_i8_cta_group(int ctaGroup) {
   if (ctaGroup != 1 && ctaGroup != 2) return fail(B200_ERR_ARG, "cta group must be 1 or 2");
-  g_i8Cg = ctaGroup;
+  g_i8Cg.store(ctaGroup);
   return B200_OK;
 }
 int b200_get_i8_cta_group(void) { return i8_cta_group(); }
@@ -1528,7 +1970,7 @@ int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames, const
   cudaStream_t st = d.stream[0];
   double h2d = 0.0;
   const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
-  if ((rc = upload_crd(d.crd, crd, frameStrideFloats, 0, nFrames, width, st, &h2d))) return rc;
+  if ((rc = upload_crd(d, d.crd, crd, frameStrideFloats, 0, nFrames, width, st, &h2d))) return rc;
   if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
   if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
   const double* d_mass = mass ? (const double*)d.massA.p : nullptr;

@@ -68,7 +68,8 @@ __host__ __device__ inline size_t i8_image_bytes(int nRowGroups, int nC) {
 // Packing: two passes over the raw COORDS (the second one hits L2).
 // ----------------------------------------------------------------------------
 struct I8StatsArgs {
-  const float* crd; size_t stride; const int* frameIdx; long srcBase;
+  const void* crd;          // float (COORDS) or double (centroid frames) rows, see the kernel's template argument
+  size_t stride; const int* frameIdx; long srcBase;
   int nFrames; int f0;      // frames [f0, nFrames) of the set are processed by this launch
   const int* atomIdx; int nAtoms;
   const double* centerMass; const double* covMass;
@@ -77,12 +78,13 @@ struct I8StatsArgs {
 };
 
 /// One warp per frame: centre (src/Frame.cpp:1043-1055 / :1141-1166) and the extent.
+template <typename T>
 __global__ void __launch_bounds__(256) i8_stats_kernel(I8StatsArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = a.f0 + blockIdx.x * 8 + warp;
   if (f >= a.nFrames) return;
   const long row = (a.frameIdx ? (long)a.frameIdx[f] : (long)f) - a.srcBase;
-  const float* src = a.crd + (size_t)row * a.stride;
+  const T* src = reinterpret_cast<const T*>(a.crd) + (size_t)row * a.stride;
   double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0;
   for (int k = lane; k < a.nAtoms; k += 32) {
     const int at = a.atomIdx ? a.atomIdx[k] : k;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) i8_stats_kernel(I8StatsArgs a) {
 }
 
 struct I8QuantArgs {
-  const float* crd; size_t stride; const int* frameIdx; long srcBase;
+  const void* crd; size_t stride; const int* frameIdx; long srcBase;
   int nFrames; int f0;
   const int* atomIdx; int nAtoms; int nC;
   const double* covMass; const double* centers;
@@ -129,12 +131,13 @@ __device__ __forceinline__ void i8_digits(long long q, int& d0, int& d1, int& d2
 
 /// One warp per frame; a lane handles 4 consecutive atoms per step and writes nine 32-bit words
 /// (plane x digit), each the 4 K-adjacent bytes of one operand row.
+template <typename T>
 __global__ void __launch_bounds__(256) i8_quant_kernel(I8QuantArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int f = a.f0 + blockIdx.x * 8 + warp;
   if (f >= a.nFrames) return;
   const long row = (a.frameIdx ? (long)a.frameIdx[f] : (long)f) - a.srcBase;
-  const float* src = a.crd + (size_t)row * a.stride;
+  const T* src = reinterpret_cast<const T*>(a.crd) + (size_t)row * a.stride;
   const double cx = a.centers[3 * (size_t)f], cy = a.centers[3 * (size_t)f + 1], cz = a.centers[3 * (size_t)f + 2];
   const int g = f / I8_FR_PER_RG, r0 = I8_ROWS_PER_FR * (f % I8_FR_PER_RG);
   uint8_t* gbase = a.image + (size_t)g * a.nC * I8_BLK_BYTES;
@@ -172,9 +175,16 @@ __global__ void __launch_bounds__(256) i8_quant_kernel(I8QuantArgs a) {
       *reinterpret_cast<uint32_t*>(blk + (r >> 3) * 512 + (r & 7) * 16) = word[x];
     }
   }
+  // 3 N q^2 <= 3 N 2^46: the exact int64 sum over the warp holds up to 43,690 atoms; beyond, the lanes' partial sums
+  // (exact) are added in FP64 (relative error 2^-53, the precision G is used at anyway)
+  if (a.nAtoms <= 40000) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
-  if (lane == 0) a.G[f] = (double)gsum * a.invScale2;
+    for (int o = 16; o > 0; o >>= 1) gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+    if (lane == 0) a.G[f] = (double)gsum * a.invScale2;
+  } else {
+    const double gd = warp_sum((double)gsum);
+    if (lane == 0) a.G[f] = gd * a.invScale2;
+  }
 }
 
 // ----------------------------------------------------------------------------
@@ -326,6 +336,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // the same number of tiles (+-1), groups running at the same time work on neighbouring columns
 // (their A rows stay in L2).
 // ----------------------------------------------------------------------------
+#ifndef B200_I8_TPW
+#define B200_I8_TPW 1           // tiles per FP64 window (1 or 2)
+#endif
+constexpr int I8_TPW = B200_I8_TPW;
+static_assert(I8_TPW == 1 || I8_TPW == 2, "tiles per FP64 window");
 #ifndef B200_I8_DRAIN_WARPS
 #define B200_I8_DRAIN_WARPS 4   // measured: 4 (640 threads, 96 registers, no spills) beats 8 (768 threads, 80 registers)
 #endif
@@ -336,10 +351,10 @@ constexpr int I8_SOLVE_WARPS = 14;
 constexpr int I8_WARP_PRODUCER = I8_DRAIN_WARPS + I8_SOLVE_WARPS;   // 18
 constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 19
 constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
-constexpr int I8_XJ_DBL = 128 * 3 + 11;      // int64 per column frame: 3 per operand row + pad; odd => conflict-free LDS.64 / STS.64
+constexpr int I8_XJ_DBL = 128 * 3 + 11;      // entries per column frame: 3 per operand row + pad; odd => conflict-free LDS / STS
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 88480
 constexpr int I8_MAX_STAGES = 8;
-constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 1;
+constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 2;
 template <int CG> __host__ __device__ constexpr int i8_smem_bytes() {
   return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 32 + 256;
 }
@@ -448,25 +463,24 @@ __device__ __forceinline__ double i8_scale2(double v, int e) {
   const int nx = ex + e;
   return (ex == 0 || nx <= 0) ? 0.0 : __hiloint2double((hi & 0x800fffff) | (nx << 20), __double2loint(v));
 }
-/// State of a pair between the FP32 approach to the root (under MMAs) and its FP64 polish (next FP64 window).
-struct I8Pending {
-  double q0, q1, q2, q3;   // quartic in y' = y / 2^k (coefficients O(1)); leading coefficient 1
-  double unit;             // r2 = y' * unit  (unit = 2^k * 2/M in integer units); or the final r2 when `final`
-  double yd, rdq;          // FP32 root estimate and 1/Q'(y), already converted (the conversions stay out of the FP64 window)
-  float dq;
-  bool final;              // the guarded FP64 path already produced r2 (ill-conditioned root)
-};
-/// FP32 part: exponent scaling on the integer pipe, monotone Newton approach from y' = 0 (resolves y' to ~1e-7
-/// RELATIVE whatever its magnitude).  Returns false when the root is ill-conditioned (|Q'| tiny relative to
-/// lambda^3, or E0 not a positive integer-scale value): the caller then takes the guarded FP64 path.
-__device__ __forceinline__ bool i8_root_start(const I8Quartic& c, double unit, I8Pending& pd) {
+/// Smallest non-negative root of the quartic.  Exponent scaling to y' = y / 2^k, 2^k <= E0 < 2^(k+1), through the
+/// exponent field (integer pipe), then the monotone Newton approach from y' = 0 on the FP32 pipe: nothing here touches
+/// the FP64 pipe, so it runs at full speed under the MMAs.  The cancellation happened in the FP64 coefficients; near
+/// the root Q(y') is evaluated in FP32 with an absolute error of ~2e-7 * sum |terms|, i.e. the root carries
+/// ~2e-7 * sum|terms| / |Q'(y')|.  For RMSDs small against the radius of gyration (y' << gap to the next root) that
+/// is 2e-7 RELATIVE, a few 1e-7 A.  An FP64 polish in the next FP64 window used to follow for EVERY pair: it changed
+/// cfg2's RMSDs by < 1e-6 A and cost 250 cycles of every window (profiles/r2_pair_i8_experiments.md).  Now only pairs
+/// whose estimated error exceeds 5e-6 A (RMSD comparable to the size of the molecule, or a small gap) are polished,
+/// in FP64, here -- under the MMAs, where FP64 crawls, but off the tensor pipe's critical path and only when needed.
+/// *r2 = (E0 - lambda_max) * 2/M.  Returns false when the root is ill-conditioned beyond what the polish repairs
+/// (|Q'| tiny relative to lambda^3, or E0 not a positive integer-scale value): the caller takes the guarded FP64 path.
+__device__ __forceinline__ bool i8_root(const I8Quartic& c, double unit, bool wanted, float* r2) {
   const int k = ((__double2hiint(c.e0) >> 20) & 0x7ff) - 1023;
-  pd.q0 = i8_scale2(c.q0, -4 * k); pd.q1 = i8_scale2(c.q1, -3 * k); pd.q2 = i8_scale2(c.q2, -2 * k);
+  const double q0 = i8_scale2(c.q0, -4 * k), q1 = i8_scale2(c.q1, -3 * k), q2 = i8_scale2(c.q2, -2 * k);
   const double x0 = i8_scale2(c.e0, -k);   // E0 / 2^k in [1, 2)
-  pd.q3 = -4.0 * x0;                       // (exact: power-of-two multiple)
-  pd.unit = i8_scale2(unit, k);
-  pd.final = false;
-  const float f0 = (float)pd.q0, f1 = (float)pd.q1, f2 = (float)pd.q2, f3 = (float)pd.q3;
+  const double us = i8_scale2(unit, k);
+  const float f0 = (float)q0, f1 = (float)q1, f2 = (float)q2, xf = (float)x0, unitf = (float)us;
+  const float f3 = -4.f * xf;
   const float g3 = 3.f * f3, g2 = 2.f * f2;
   float y = 0.f, dq = f1, step;
 #pragma unroll
@@ -481,30 +495,29 @@ __device__ __forceinline__ bool i8_root_start(const I8Quartic& c, double unit, I
     dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
     step = __fdividef(qy, dq);
     y -= step;
-    if (!__any_sync(0xffffffffu, fabsf(step) > 4e-7f * fabsf(y))) break;
+    if (!__any_sync(0xffffffffu, fabsf(step) > 2e-7f * fabsf(y))) break;
   }
-  pd.dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
-  pd.yd = (double)y;
-  pd.rdq = (double)__frcp_rn(pd.dq);
-  const float xf = -0.25f * f3;
-  return (fabsf(pd.dq) >= 7e-3f * xf * xf * xf) && (k > 0) && (y < 3.f);
-}
-/// FP64 part (8 instructions): one Newton correction of the FP32 estimate; a few more, in FP64, in the rare case
-/// that the FP32 approach had not converged.  Returns r2 = (E0 - lambda_max) * 2/M.
-__device__ __forceinline__ double i8_root_finish(const I8Pending& pd) {
-  if (pd.final) return pd.unit;
-  double yd = pd.yd;
-  const double Q = fma(fma(fma(yd + pd.q3, yd, pd.q2), yd, pd.q1), yd, pd.q0);
-  double d = Q * pd.rdq;
-  yd -= d;
-#pragma unroll 1
-  for (int it = 0; it < 30 && fabs(d) > 1e-5 * fabs(yd) + 1e-14; ++it) {
-    const double Qn = fma(fma(fma(yd + pd.q3, yd, pd.q2), yd, pd.q1), yd, pd.q0);
-    const double dQ = fma(fma(fma(4.0, yd, 3.0 * pd.q3), yd, 2.0 * pd.q2), yd, pd.q1);
-    d = Qn / dQ;
+  dq = fmaf(fmaf(fmaf(4.f, y, g3), y, g2), y, f1);
+  float r2f = y * unitf;
+  // estimated RMSD error of the FP32 root: rmsd * dy / (2 y), dy = 2e-7 * sum|terms| / |Q'|
+  const float terms = fmaf(fmaf(fmaf(y + fabsf(f3), y, fabsf(f2)), y, fabsf(f1)), y, fabsf(f0));
+  // (`wanted`: lanes without a pair -- tile padding -- hold a quadruple root at E0 and must not crawl through FP64)
+  if (wanted && 1e-7f * terms * unitf > 5e-6f * fabsf(dq) * sqrtf(fmaxf(r2f, 0.f))) {
+    double yd = (double)y;
+    const double q3 = -4.0 * x0;
+    double d = fma(fma(fma(yd + q3, yd, q2), yd, q1), yd, q0) * (double)__frcp_rn(dq);
     yd -= d;
+#pragma unroll 1
+    for (int it = 0; it < 30 && fabs(d) > 1e-9 * fabs(yd) + 1e-14; ++it) {
+      const double Qn = fma(fma(fma(yd + q3, yd, q2), yd, q1), yd, q0);
+      const double dQ = fma(fma(fma(4.0, yd, 3.0 * q3), yd, 2.0 * q2), yd, q1);
+      d = Qn / dQ;
+      yd -= d;
+    }
+    r2f = (float)(yd * us);
   }
-  return yd * pd.unit;
+  *r2 = r2f;
+  return (fabsf(dq) >= 7e-3f * xf * xf * xf) && (k > 0) && (y < 3.f);
 }
 /// Guarded FP64 path (Newton on the unscaled quartic, SVD for double roots); rarely taken.  The covariance
 /// travels BY VALUE: a pointer parameter would force the caller's S into local memory on every pair.
@@ -531,6 +544,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   uint64_t* xFull = bars + 2 * I8_MAX_STAGES + 4;      // [4]  exchange group written
   uint64_t* xEmpty = bars + 2 * I8_MAX_STAGES + 8;     // [4]  exchange group read
   uint64_t* fpDone = bars + 2 * I8_MAX_STAGES + 12;    // [1]  FP64 window of a tile closed (CG 2: by both CTAs; leader's copy)
+  uint64_t* fpLocal = bars + 2 * I8_MAX_STAGES + 13;   // [1]  same, this CTA's solve warps only: the drain warps start on the next tile
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -550,6 +564,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS * CG); }
     for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), 4); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
     mbar_init(smem_u32(fpDone), I8_SOLVE_WARPS * CG);
+    mbar_init(smem_u32(fpLocal), I8_SOLVE_WARPS);
     mbar_fence_init();
   }
   if (warp == I8_WARP_MMA) tmem_alloc<CG>(smem_u32(tmemBaseSlot), 512);
@@ -620,7 +635,10 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       else mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       // FP64 window: the solve warps finished the FP64 part of tile n-2 (they started it when tile n-1's MMAs completed)
       const long long cA = (DBG && dbgClk) ? clock64() : 0;
-      if (n >= 2 && !(DBG && dbgMode >= 2 && dbgMode <= 5)) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1));
+      if (!(DBG && dbgMode >= 2 && dbgMode <= 5)) {
+        if (I8_TPW == 1) { if (n >= 2) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1)); }
+        else if (n >= 2 && (n & 1) == 0) mbar_wait(smem_u32(fpDone), (uint32_t)(((n >> 1) - 1) & 1));   // window k closes before tile 2k+2
+      }
       if (DBG && dbgClk) { const long long c2 = clock64(); cwAcc += c2 - c0; cwFpd += c2 - cA; }
       tc_fence_after();
       const uint32_t dTmem = tmemBase + (uint32_t)(b * 256);
@@ -693,6 +711,14 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       const int b = n & 1;
       long long c0 = (DBG && dbgClk) ? clock64() : 0;
       mbar_wait(smem_u32(&accFull[b]), (uint32_t)((n >> 1) & 1));
+      // The FP64 window of tile n-1 opens at this very moment (the solve warps wait for the same barrier).  The drain
+      // is integer work that would take every other issue slot of the four schedulers while the window's FP64
+      // instructions want them: start it when this CTA's solve warps are through (there is slack: the drain of a tile
+      // takes ~3600 cycles, the MMAs of the next one ~4100).
+      if (!(DBG && dbgMode >= 2 && dbgMode <= 5)) {
+        if (I8_TPW == 1) { if (n >= 1) mbar_wait(smem_u32(fpLocal), (uint32_t)((n - 1) & 1)); }
+        else if (n & 1) mbar_wait(smem_u32(fpLocal), (uint32_t)(((n - 1) >> 1) & 1));   // odd tiles complete as a window opens
+      }
       if (DBG && dbgClk) cwAcc += clock64() - c0;
       tc_fence_after();
       if (DBG && dbgMode >= 2 && dbgMode <= 5) {   // timing experiment: MMA + operand pipeline only
@@ -724,13 +750,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         tmem_ld_wait();
         if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + (size_t)jj * I8_XJ_DBL);
+        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + jj * I8_XJ_DBL);
         if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; c1 = c2; }
         if (!(DBG && dbgMode == 8)) tmem_ld32(tcol + 27, v);                // frames 3..5
         tmem_ld_wait();
         if (DBG && dbgClk) { const long long c2 = clock64(); cwLd += c2 - c1; c1 = c2; }
 #pragma unroll
-        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + (size_t)(3 + jj) * I8_XJ_DBL);
+        for (int jj = 0; jj < 3; ++jj) fold_frame(v + 9 * jj, dst + (3 + jj) * I8_XJ_DBL);
         if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; c1 = c2; }
         if (!(DBG && dbgMode == 8)) tmem_ld16(tcol + 47, v);                // columns 47..62: frame 6 is the last 9 (stays inside the accumulator)
         tmem_ld_wait();
@@ -743,7 +769,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
             else mbar_arrive(smem_u32(&accEmpty[b]));
           }
         }
-        fold_frame(v + 7, dst + (size_t)6 * I8_XJ_DBL);
+        fold_frame(v + 7, dst + 6 * I8_XJ_DBL);
         if (DBG && dbgClk) { const long long c2 = clock64(); cwFold += c2 - c1; }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&xFull[g]));
@@ -771,10 +797,25 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     int n = 0;
     long long cwX = 0, cwWin = 0, cwFp = 0, cwRoot = 0;
     const long long cStart = (DBG && dbgClk) ? clock64() : 0;
-    I8Pending pd;
-    bool pdLive = false, pdValid = false;
-    size_t pdIdx = 0;
-    pd.q0 = pd.q1 = pd.q2 = pd.q3 = pd.unit = pd.yd = pd.rdq = 0.0; pd.dq = 0.f; pd.final = true;
+    const bool plain = !(DBG && (dbgMode == 1 || dbgMode == 6));   // timing experiments 1 / 6: handshakes without the per-pair solve
+    // Output slot of pair (i, j); 0 for pairs this thread does not own (never stored).
+    auto out_index = [&](int i, int j, bool valid) -> size_t {
+      if (TRI) return valid ? tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase : 0;
+      return (size_t)i * a.ldo + (size_t)j;
+    };
+    // FP32 root + store of one pair (under the MMAs; no FP64 instruction unless the root is ill-conditioned).
+    // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the square root is taken in float.
+    auto finish_pair = [&](const I8Quartic& cq, const double* S, bool valid, size_t idx) {
+      float r2;
+      const bool ok = i8_root(cq, outScale, valid, &r2);
+      if (valid && !ok)
+        r2 = (float)(i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale));
+      if (valid) a.out[idx] = (r2 > 0.f) ? sqrtf(r2) : 0.f;
+    };
+    // A tile held back for the next window (I8_TPW == 2): its covariance, 2 E0 and output slot.
+    double Sh[9], gh = 1.0;
+    bool heldLive = false, heldValid = false;
+    size_t heldIdx = 0;
     int itN, jtN;
     bool have = tiles.next(a, it, jt);
     while (have) {
@@ -798,74 +839,62 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
           for (int q = 0; q < 3; ++q)   // fold the A digits: exact int64 (|S| < 2^63 for < 131072 atoms)
             SI[3 * p + q] = src[9 * p + q] + (src[9 * p + 3 + q] << 8) + (src[9 * p + 6 + q] << 16);
 #pragma unroll
-        for (int x = 0; x < 9; ++x) S[x] = __ll2double_rn(SI[x]);   // I2F.F64.S64: XU pipe, not the FP64 pipe
+        for (int x = 0; x < 9; ++x) S[x] = __ll2double_rn(SI[x]);   // I2F.F64.S64: conversion pipe, not the FP64 pipe
       } else {
 #pragma unroll
         for (int x = 0; x < 9; ++x) S[x] = 0.0;
       }
-      // the loads above have completed (their values are consumed): hand the groups back to the drain warps
-      {
-        double keep = S[0];
-#pragma unroll
-        for (int x = 1; x < 9; ++x) keep += S[x];
-        asm volatile("" ::"d"(keep) : "memory");
-      }
+      // All nine are materialised here (the loads have completed, the conversions are done; no FP64-pipe instruction
+      // under the MMAs): hand the exchange groups back to the drain warps.
+      asm volatile("" ::"d"(S[0]), "d"(S[1]), "d"(S[2]), "d"(S[3]), "d"(S[4]), "d"(S[5]), "d"(S[6]), "d"(S[7]), "d"(S[8]) : "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(smem_u32(&xEmpty[2 * h])); mbar_arrive(smem_u32(&xEmpty[2 * h + 1])); }
       if (DBG && a.dbgS && valid) {
 #pragma unroll
         for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
       }
-      // ---- 2. FP64 window: wait until the MMAs of tile n+1 are done (the MMA warp will not issue tile n+2 before
-      //         every solve warp of the CTA (pair) has arrived on fpDone), do all the FP64 work, let the MMAs go on
-      c0 = (DBG && dbgClk) ? clock64() : 0;
-      if (hasNext) mbar_wait(smem_u32(&accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
-      const long long cF = (DBG && dbgClk) ? clock64() : 0;
-      I8Quartic cq;
-      double r2Prev = 0.0;
-      const bool plain = !(DBG && (dbgMode == 6 || dbgMode == 1 || dbgMode == 7 || dbgMode == 8));
-      if (plain) {
-        if (pdLive) r2Prev = i8_root_finish(pd);     // tile n-1: FP64 polish of the root found under the last MMAs
-        cq = i8_coeffs(S, (ga + gb) * halfToInt);    // tile n: everything that must be FP64 (E0 too: outside the
-                                                     // window its two instructions crawl on the solve's critical path)
-        asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2), "d"(r2Prev) : "memory");   // computed before the arrive below
+      const size_t idx = out_index(i, j, valid);
+      // ---- 2. FP64 window, once per I8_TPW tiles.  It opens when the MMAs of tile n+1 have completed and closes when
+      //         every solve warp of the CTA (pair) has arrived on fpDone: the MMA warp issues tile n+2 only then.
+      //         Each window costs ~600 cycles of idle tensor pipe beyond its FP64 work (pipe drain, handshake, refill):
+      //         with two tiles per window -- the odd tile's covariance waits in registers -- half as many are paid.
+      const bool windowTile = I8_TPW == 1 || (n & 1) == 0 || !hasNext;
+      if (!windowTile) {
+#pragma unroll
+        for (int x = 0; x < 9; ++x) Sh[x] = S[x];
+        gh = ga + gb;   // (one FP64 add under the MMAs per held tile)
+        heldLive = true; heldValid = valid; heldIdx = idx;
       } else {
-        cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0;
+        c0 = (DBG && dbgClk) ? clock64() : 0;
+        if (hasNext) mbar_wait(smem_u32(&accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
+        const long long cF = (DBG && dbgClk) ? clock64() : 0;
+        I8Quartic cq, cqh;
+        cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0; cqh = cq;
+        if (plain) {
+          // everything that must be FP64 (E0 too: outside the window its instructions crawl on the critical path)
+          if (I8_TPW == 2 && heldLive) cqh = i8_coeffs(Sh, gh * halfToInt);
+          cq = i8_coeffs(S, (ga + gb) * halfToInt);
+          asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2), "d"(cqh.q0), "d"(cqh.q1), "d"(cqh.q2) : "memory");   // computed before the arrive below
+        }
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr);
+          mbar_arrive(smem_u32(fpLocal));
+        }
+        if (DBG && dbgClk) { const long long c2 = clock64(); cwWin += c2 - c0; cwFp += c2 - cF; }
+        // ---- 3. roots and stores (under the MMAs of the next tiles)
+        const long long cR = (DBG && dbgClk) ? clock64() : 0;
+        if (plain) {
+          if (I8_TPW == 2 && heldLive) finish_pair(cqh, Sh, heldValid, heldIdx);
+          finish_pair(cq, S, valid, idx);
+        } else if (!(DBG && dbgMode == 6)) {
+          if (valid) a.out[idx] = (float)(S[0] + S[4] + S[8]);
+        }
+        heldLive = false;
+        if (DBG && dbgClk) cwRoot += clock64() - cR;
       }
-      __syncwarp();
-      if (lane == 0) { if constexpr (CG == 2) mbar_arrive_cluster(fpDoneAddr); else mbar_arrive(fpDoneAddr); }
-      if (DBG && dbgClk) { const long long c2 = clock64(); cwWin += c2 - c0; cwFp += c2 - cF; }
       ++n;
-      // ---- 3. store tile n-1, FP32 root search for tile n (under the MMAs of tile n+2; no FP64 instructions unless
-      //         the root is ill-conditioned)
-      const long long cR = (DBG && dbgClk) ? clock64() : 0;
-      if (plain) {
-        // clamp: src/Frame.cpp:1264-1268; the result is stored as float (Matrix<float>), so the root is taken in
-        // float: relative error 1.2e-7, i.e. < 4e-7 A for RMSDs of a few A
-        if (pdLive && pdValid) a.out[pdIdx] = (r2Prev > 0.0) ? sqrtf((float)r2Prev) : 0.f;
-        const bool ok = i8_root_start(cq, outScale, pd);
-        if (valid && !ok) {
-          pd.unit = i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale);
-          pd.final = true;
-        }
-        pdLive = true; pdValid = valid;
-        if (TRI)
-          pdIdx = valid ? tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase : 0;
-        else
-          pdIdx = (size_t)i * a.ldo + (size_t)j;
-      } else if (!(DBG && dbgMode == 6)) {
-        if (valid) {
-          const size_t idx = TRI ? tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase
-                                 : (size_t)i * a.ldo + (size_t)j;
-          a.out[idx] = (float)(S[0] + S[4] + S[8]);
-        }
-      }
-      if (DBG && dbgClk) cwRoot += clock64() - cR;
       it = itN; jt = jtN; have = hasNext;
-    }
-    if (pdLive && pdValid) {   // the last tile's pairs (no MMAs in flight any more)
-      const double r2 = i8_root_finish(pd);
-      a.out[pdIdx] = (r2 > 0.0) ? sqrtf((float)r2) : 0.f;
     }
     if (DBG && dbgClk && lane == 0 && u == 0) {
       dbgClk[16 * blockIdx.x + 8] += cwX; dbgClk[16 * blockIdx.x + 9] += clock64() - cStart;

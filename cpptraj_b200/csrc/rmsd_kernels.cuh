@@ -439,7 +439,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2) pair_kernel(PairArgs a) {
   }
 
   // ---- epilogue: per-pair solve, straight into cpptraj's matrix layout ----
-  const double invM = 1.0 / a.totalMass[0];
+  // total mass < Constants::SMALL: the reference reports -1 for every pair (src/Frame.cpp:1160-1163, :1300-1303)
+  const bool massOk = a.totalMass[0] >= 1e-14;
+  const double invM = massOk ? 1.0 / a.totalMass[0] : 0.0;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int nj = 0; nj < 2; ++nj)
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2) pair_kernel(PairArgs a) {
           r = rmsd_nofit_from_trace(acc[0][nj][e + 2 * h] + acc[1][nj][e + 2 * h] + acc[2][nj][e + 2 * h], ga,
                                     gb, invM);
         }
+        if (!massOk) r = -1.0;
         size_t idx;
         if (TRI)
           idx = tri_row_start((size_t)a.nCols, (size_t)i) + (size_t)(j - i - 1) - a.outBase;
@@ -607,7 +610,9 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
         v[x] = s;
       }
       const double M = a.refsum[3];
-      if (!a.fit) {
+      if (M < 1e-14) {   // src/Frame.cpp:1160-1163, :1300-1303
+        a.rmsd[fr] = -1.0;
+      } else if (!a.fit) {
         a.rmsd[fr] = (v[0] < 0.0) ? 0.0 : sqrt(v[0] / M);
       } else {
         // centre relative to the frame origin o
@@ -862,6 +867,7 @@ __global__ void __launch_bounds__(128) onevn_finish_kernel(const double* rec, co
   if (fr >= nFrames) return;
   const double* v = rec + (size_t)fr * ONEVN_REC;
   const double M = refsum[3];
+  if (M < 1e-14) { rmsd[fr] = -1.0; return; }   // src/Frame.cpp:1160-1163, :1300-1303
   if (!fit) { rmsd[fr] = (v[0] < 0.0) ? 0.0 : sqrt(v[0] / M); return; }
   const double cx = v[9] / M, cy = v[10] / M, cz = v[11] / M;
   double S[9];
@@ -899,6 +905,24 @@ __global__ void __launch_bounds__(256) centroid_argmin_kernel(const double* dist
   }
   if (closest) closest[f] = bk;
   if (closestDist) closestDist[f] = best;
+}
+
+/// Same for the frames x centroids table the pair engine wrote (float, frame-major): dist[f * K + k].
+__global__ void __launch_bounds__(256) centroid_argmin_rows_kernel(const float* dist, int nFrames, int K, double* distOut, int* closest,
+                                                                   double* closestDist) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= nFrames) return;
+  const float* row = dist + (size_t)f * K;
+  float best = row[0];
+  int bk = 0;
+  if (distOut) distOut[(size_t)f * K] = (double)best;
+  for (int k = 1; k < K; ++k) {
+    const float d = row[k];
+    if (distOut) distOut[(size_t)f * K + k] = (double)d;
+    if (d < best) { best = d; bk = k; }
+  }
+  if (closest) closest[f] = bk;
+  if (closestDist) closestDist[f] = (double)best;
 }
 
 /// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One block.

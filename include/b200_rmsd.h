@@ -59,7 +59,9 @@ int b200_num_devices(void);
  * frameIdx NULL means frames 0..nFrames-1.  outTri is Matrix<float>::Ptr() of
  * a TRIANGLE matrix of nFrames columns: element (i<j) at
  * nFrames*i - i*(i+1)/2 + j - i - 1 (src/Matrix.h:110-122).
- * Work is split over all initialised devices. */
+ * Work is split over all initialised devices (one host thread each; the shards agree on one fixed-point grid).
+ * Host buffers may be pageable (cpptraj's std::vector<float> / new float[]): they are staged through pinned ring
+ * slots by a pool of host threads (env B200_HOST_THREADS); pinned buffers are read and written by DMA directly. */
 int b200_rms2d_tri(const float* crd, size_t frameStrideFloats, int nFramesTotal,
                    const int* frameIdx, int nFrames,
                    const int* atomIdx, int nAtoms,
@@ -84,7 +86,7 @@ int b200_rms2d_tri_shard(const float* crd, size_t frameStrideFloats, int nFrames
  * covariance and total mass (target frame's Mass_, src/Frame.cpp:1184-1208);
  * massRefCentering is used only to centre each reference frame
  * (SelectedRef.CenterOnOrigin, src/Analysis_Rms2d.cpp:265-266).  Both NULL
- * when the "mass" keyword is absent. */
+ * when the "mass" keyword is absent.  Target rows are split over all initialised devices. */
 int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* atomIdxTgt,
                     const float* crdRef, size_t strideRef, int nRef, const int* atomIdxRef,
                     int nAtoms, const double* massTgt, const double* massRefCentering,
@@ -100,12 +102,18 @@ int b200_rms2d_full(const float* crdTgt, size_t strideTgt, int nTgt, const int* 
  * Results come back in push order (DataSet_double::Add is append-only,
  * src/DataSet_double.cpp:14-20): rmsdOut[n]; rotOut[9n] = the rotation U of
  * RMSD_CenteredRef row-major (NULL if not wanted); transOut[3n] = the
- * target->origin translation "Trans" (NULL if not wanted). */
+ * target->origin translation "Trans" (NULL if not wanted).
+ * A push returns when the caller's buffer may be reused (pageable frames are packed into pinned staging, pinned
+ * ones have left by DMA); the kernels run asynchronously until flush.  Chunks go round-robin to all initialised
+ * devices; total mass < 1e-14 gives -1 for every frame (src/Frame.cpp:1160-1163). */
 typedef struct b200_1vN b200_1vN;
 int b200_rmsd_1vN_begin(const double* refSelected, const int* atomIdx, int nAtoms,
                         const double* mass, int fit, int wantRot, b200_1vN** handle);
 int b200_rmsd_1vN_push_f64(b200_1vN* h, const double* xyz, size_t frameStrideDoubles, int nFrames);
 int b200_rmsd_1vN_push_f32(b200_1vN* h, const float* crd, size_t frameStrideFloats, int nFrames);
+/* Replaces the reference of a live handle (reftraj / previous modes, src/ReferenceAction.h:73-88: the reference
+ * changes from frame to frame).  Frames already pushed keep the reference they were pushed against. */
+int b200_rmsd_1vN_set_ref(b200_1vN* h, const double* refSelected);
 /* Number of frames pushed and not yet flushed. */
 long b200_rmsd_1vN_pending(const b200_1vN* h);
 /* Blocks until all pushed frames are done; argminFrame (nullable) receives the
@@ -122,7 +130,9 @@ int b200_rmsd_1vN_end(b200_1vN* h);
  * doubles, the selected atoms of each Centroid_Coord::Cframe() (already centred on the origin when fitting, as cpptraj
  * keeps them).  frameIdx (nullable) lists the frames, e.g. the sieved-out ones.  Outputs (each nullable):
  * distOut[f*nCentroids + k]; closestOut[f] = nearest centroid, first minimum wins (List.cpp:183-189);
- * closestDistOut[f] its distance.  Runs on device 0. */
+ * closestDistOut[f] its distance.  Three or more centroids with a fitted RMSD run as ONE frames x centroids contraction
+ * on the tcgen05 engine (frames read and quantised once); fewer, or nofit, as one streaming pass per centroid.  Large
+ * frame lists are split over all initialised devices. */
 int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal,
                                   const int* frameIdx, int nFrames,
                                   const int* atomIdx, int nAtoms, const double* mass, int fit,
@@ -179,44 +189,15 @@ void b200_get_stats(b200_stats* out);
  *   0 = automatic (2 when eligible, else 1) -- the default; env B200_PAIR_ENGINE.
  * Forcing 2 on an ineligible call fails with B200_ERR_ARG. */
 int b200_set_pair_engine(int engine);
-/* MMA CTA group of the tcgen05 int8 kernel: 2 (default) = CTA pairs, tcgen05.mma.cta_group::2,
- * 28 x 28 frame-pair tiles; 1 = single-CTA MMAs, 14 x 28 tiles.  Same results; a tuning/test knob. */
-int b200_set_i8_cta_group(int ctaGroup);
-int b200_get_i8_cta_group(void);
+/* Pins the number of fractional bits of engine 2's fixed-point grid for the following calls (0 = automatic: from
+ * the extent of the call's own frames).  One process per GPU: every rank computes a shard of one matrix from the
+ * frames it holds; the ranks agree on min(bits) (b200_last_pair_engine reports what a call used) and pin it, so
+ * that all shards are rounded to the same grid whatever the GPU count.  A single process driving several devices
+ * does this by itself.  A pinned scale too fine for the data fails with B200_ERR_ARG. */
+int b200_set_fixed_point_bits(int bits);
 /* Engine the last rms2d call used (1 or 2; 0 = none yet) and, for 2, the number of
  * fractional bits of its fixed-point grid. */
 int b200_last_pair_engine(int* fractionalBits);
-
-/* Test hook for the tcgen05 path (small inputs, device 0): returns the packed int8
- * operand image, the per-frame G, the raw integer covariances (9 doubles per (i,j),
- * i<j, at (i*nFrames+j)*9) and the triangle.  Any output pointer may be NULL. */
-int b200_debug_i8(const float* crd, size_t frameStrideFloats, int nFrames,
-                  const int* atomIdx, int nAtoms, const double* mass,
-                  unsigned char* imageOut, size_t imageCap, size_t* imageBytes,
-                  double* GOut, double* SOut, float* outTri, int* qsOut);
-
-/* Timing experiments: out == NULL arms per-CTA cycle counters (16 per CTA) that the next
- * tcgen05 pair launches fill in; a later call with out != NULL copies them back and disarms. */
-int b200_debug_i8_clocks(long long* out, int ctas);
-
-/* Tuning knob: PTX shape used for the FP64 MMAs of the pair kernel
- * (0 m8n8k4, 1 m16n8k4, 2 m16n8k8, 3 m16n8k16; all lower to DMMA.8x8x4 SASS). */
-int b200_set_mma_variant(int variant);
-
-/* Measures this device's FP64 tensor (DMMA) issue peak with a register-only
- * mma.sync loop; returns TFLOP/s (<=0 on error).  Used as the roofline
- * denominator for the pair-tile kernel because MEASURED_PEAKS.json holds no
- * FP64 figure. */
-double b200_measure_fp64_mma_peak(int variant);
-/* Same for the tcgen05 kind::i8 pipe (M128 x N256 x K32 MMAs on operands resident in shared
- * memory, one CTA per SM); returns int8 TOP/s.  Roofline denominator of the tcgen05 pair engine. */
-double b200_measure_i8_mma_peak(void);
-/* variant 0 independent accumulators (issue peak), 1 one accumulator (dependent K loop), 2 = 1 + a commit every second MMA */
-double b200_measure_i8_mma_peak_variant(int variant);
-
-/* Latency probe: average cycles for one thread to issue nMma tcgen05 MMAs (M128 N256 K32, one accumulator),
- * commit to an mbarrier and wake up on it; nMma = 0 is the commit round trip alone.  <0 on error. */
-double b200_debug_i8_mma_latency(int nMma, int ctas);
 
 #ifdef __cplusplus
 }

@@ -9,10 +9,22 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    src = open(os.path.join(ROOT, "include", "b200_rmsd.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200_[a-z0-9_A-Z]+)\s*\(", src)))
+HEADERS = ("b200_rmsd.h", "b200_rmsd_debug.h")   # the drop-in boundary; test hooks and probes
+
+
+def declared_symbols(header=None):
+    syms = set()
+    for h in ([header] if header else HEADERS):
+        src = open(os.path.join(ROOT, "include", h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        syms |= set(re.findall(r"\b(b200_[a-z0-9_A-Z]+)\s*\(", src))
+    return sorted(syms)
+
+
+def test_product_header_has_no_debug_exports():
+    prod = declared_symbols("b200_rmsd.h")
+    assert not [s for s in prod if "debug" in s or "measure" in s], prod
+    assert "b200_rmsd_1vN_set_ref" in prod and "b200_set_fixed_point_bits" in prod
 
 
 def test_header_symbols_exported(built):
@@ -25,9 +37,10 @@ def test_header_symbols_exported(built):
 
 
 def test_no_torch_types_in_header():
-    src = open(os.path.join(ROOT, "include", "b200_rmsd.h")).read()
-    code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)     # declarations only, comments stripped
-    assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "&" not in code
+    for h in HEADERS:
+        src = open(os.path.join(ROOT, "include", h)).read()
+        code = re.sub(r"/\*.*?\*/", "", src, flags=re.S)     # declarations only, comments stripped
+        assert "torch" not in code.lower() and "at::" not in code and "std::" not in code and "&" not in code
 
 
 def test_library_does_not_link_oracle(built):
