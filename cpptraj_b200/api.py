@@ -47,6 +47,12 @@ def lib():
     L.b200_rmsd_1vN_push_f32.argtypes = [vp, vp, sz, i]
     L.b200_rmsd_1vN_set_ref.argtypes = [vp, vp]
     L.b200_rmsd_1vN_set_ref.restype = i
+    L.b200_rmsd_build_centroids.argtypes = [vp, sz, i, vp, vp, i, vp, i, vp, i, vp]
+    L.b200_rmsd_build_centroids.restype = i
+    L.b200_coords_resident_begin.argtypes = [vp, sz, i, vp, i]
+    L.b200_coords_resident_begin.restype = i
+    L.b200_coords_resident_end.argtypes = [vp]
+    L.b200_coords_resident_end.restype = i
     L.b200_set_fixed_point_bits.argtypes = [i]
     L.b200_set_fixed_point_bits.restype = i
     L.b200_rmsd_1vN_pending.argtypes = [vp]
@@ -253,6 +259,31 @@ def frames_to_centroids(crd, atom_idx, centroids, mass=None, fit=True, frame_idx
     _check(lib().b200_rmsd_frames_to_centroids(_p(crd), crd.shape[1], crd.shape[0], _p(fidx), nF, _p(sel), len(sel), _p(mass),
                                                int(bool(fit)), _p(cen), cen.shape[0], _p(dist), _p(closest), _p(cdist)))
     return dist, closest, cdist
+
+
+def build_centroids(crd, atom_idx, frame_lists, mass=None, fit=True):
+    """Metric_RMS::CalculateCentroid for several clusters: frame_lists is a sequence of frame-number arrays;
+    returns [K, nAtoms, 3] float64."""
+    crd = _crd2d(crd)
+    sel = _arr(atom_idx, np.int32)
+    mass = _arr(mass, np.float64)
+    frames = np.ascontiguousarray(np.concatenate([np.asarray(f, np.int32) for f in frame_lists]) if len(frame_lists) else np.zeros(0, np.int32), np.int32)
+    offsets = np.zeros(len(frame_lists) + 1, np.int32)
+    offsets[1:] = np.cumsum([len(f) for f in frame_lists])
+    out = np.zeros((len(frame_lists), len(sel), 3), np.float64)
+    _check(lib().b200_rmsd_build_centroids(_p(crd), crd.shape[1], crd.shape[0], _p(frames), _p(offsets), len(frame_lists),
+                                           _p(sel), len(sel), _p(mass), int(bool(fit)), _p(out)))
+    return out
+
+
+def coords_resident_begin(crd, atom_idx):
+    crd = _crd2d(crd)
+    sel = _arr(atom_idx, np.int32)
+    _check(lib().b200_coords_resident_begin(_p(crd), crd.shape[1], crd.shape[0], _p(sel), len(sel)))
+
+
+def coords_resident_end(crd=None):
+    _check(lib().b200_coords_resident_end(None if crd is None else _p(_crd2d(crd))))
 
 
 def set_profiling(on):

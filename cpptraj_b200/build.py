@@ -13,7 +13,7 @@ DEPS = SRC + [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.j
     os.path.join(os.path.dirname(HERE), "include", "b200_rmsd.h"), os.path.join(os.path.dirname(HERE), "include", "b200_rmsd_debug.h")]
 OUT = os.environ.get("B200_RMSD_LIB_OUT") or os.path.join(HERE, "libb200rmsd.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+FLAGS = ["-I", os.path.join(os.path.dirname(HERE), "include"), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-cudart", "static",
          "-Xptxas", "-v"]
 

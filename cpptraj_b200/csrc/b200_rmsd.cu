@@ -3,8 +3,8 @@
 // No torch, no CPU fallback: every compute entry point needs an sm_100 device.
 // Device memory, streams and pinned staging are owned here; cpptraj owns the
 // host buffers it passes in.
-#include "../../include/b200_rmsd.h"
-#include "../../include/b200_rmsd_debug.h"
+#include "b200_rmsd.h"         // (include/ of this repository; src/cuda_b200/ in a cpptraj tree)
+#include "b200_rmsd_debug.h"
 #include "rmsd_kernels.cuh"
 #include "pair_i8.cuh"
 #include "host_util.h"
@@ -97,6 +97,8 @@ struct Device {
   cudaEvent_t inFree[NIN] = {};
   bool inUsed[NIN] = {};
   int inNext = 0;
+  // COORDS kept on the device between calls (b200_coords_resident_begin/end): the leading resWidth floats of all frames
+  const float* resHost = nullptr; size_t resStride = 0, resWidth = 0; int resFrames = 0; DevBuf resBuf;
   CopyPool pool;                          // staging of pageable inputs (and everything else on the calling thread)
   CopyPool poolOut;                       // delivery of pageable results (driven by OutRing's own thread)
   void destroy() {
@@ -116,7 +118,7 @@ struct Device {
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
                      &imgA, &imgB, &cenA, &cenB, &dbgS};
     for (DevBuf* b : all) b->release();
-    hostScal.release();
+    hostScal.release(); resBuf.release(); resHost = nullptr;
     pool.stop(); poolOut.stop();
     id = -1;
   }
@@ -624,7 +626,9 @@ int prepare_tri(Device& d, const float* d_crd, size_t stride, const int* d_frame
     ps.planes = (double*)d.planesA.p; ps.G = (double*)d.GA.p;
     // rows >= row0 only pair with columns > row0: frames below row0's row group are never read
     const int f0 = (row0 / ROWG) * ROWG;
-    if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st>>>(d_crd, stride, d_frameIdx, srcBase, f0, d_atomIdx, d_shift); }
+    // nofit: a common origin, taken from the LAST frame -- the one frame every shard of a matrix holds, so that all
+    // shards (and any device count) subtract the same origin and produce the same bits
+    if (!fit) { COUNT_LAUNCH(); shift_kernel<<<1, 1, 0, st>>>(d_crd, stride, d_frameIdx, srcBase, nFrames - 1, d_atomIdx, d_shift); }
     if ((rc = run_pack(d_crd, stride, d_frameIdx, srcBase, nFrames, f0, d_atomIdx, nAtoms, d_mass, d_mass, d_shift,
                        fit, ps, st))) return rc;
   }
@@ -722,6 +726,21 @@ int upload_crd(Device& d, DevBuf& buf, const float* crd, size_t stride, int fLo,
   int rc;
   if ((rc = buf.reserve((size_t)std::max(1, fHi - fLo) * widthFloats * sizeof(float)))) return rc;
   return upload_rows(d, (float*)buf.p, crd, stride, fLo, fHi, widthFloats, host_ptr_is_pinned(crd + (size_t)fLo * stride), st, h2dBytes);
+}
+
+/// Device copy of frames [fLo,fHi) of host COORDS: the resident copy when the caller announced one
+/// (b200_coords_resident_begin: no transfer, rows indexed by absolute frame number), else an upload into `buf`.
+/// Frame f is row f - *srcBase of *d_ptr, row pitch *pitch floats.
+int get_coords(Device& d, DevBuf& buf, const float* crd, size_t stride, int nFramesTotal, int fLo, int fHi, size_t width,
+               cudaStream_t st, double* h2dBytes, const float** d_ptr, size_t* pitch, long* srcBase) {
+  if (d.resHost == crd && d.resStride == stride && d.resFrames == nFramesTotal && width <= d.resWidth && d.resBuf.p) {
+    *d_ptr = (const float*)d.resBuf.p; *pitch = d.resWidth; *srcBase = 0;
+    return B200_OK;
+  }
+  int rc;
+  if ((rc = upload_crd(d, buf, crd, stride, fLo, fHi, width, st, h2dBytes))) return rc;
+  *d_ptr = (const float*)buf.p; *pitch = width; *srcBase = (long)fLo;
+  return B200_OK;
 }
 
 template <typename T>
@@ -1800,8 +1819,12 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
   }
   cudaStream_t st = d.stream[0];
   double h2d = 0.0, d2h = 0.0;
-  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
-  if ((rc = upload_crd(d, d.crd, crd, stride, sLo, sHi, width, st, &h2d))) return rc;
+  size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  const float* d_frames = nullptr;
+  long rowBase = 0;
+  if ((rc = get_coords(d, d.crd, crd, stride, nFramesTotal, sLo, sHi, width, st, &h2d, &d_frames, &width, &rowBase))) return rc;
+  // list position 0 when there is no frame list: frame p0; with a list: row = frameIdx[.] - rowBase
+  const float* d_list0 = frameIdx ? d_frames : d_frames + (size_t)((long)p0 - rowBase) * width;
   if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
   if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
   if (frameIdx && (rc = upload_vec(d.frameIdx, frameIdx + p0, (size_t)nP, st))) return rc;
@@ -1829,8 +1852,8 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
     if ((rc = i8_reserve(qA, d.imgA, d.GA, d.cenA, nP, nAtoms))) return rc;
     if ((rc = i8_reserve(qB, d.imgB, d.GB, d.cenB, K, nAtoms))) return rc;
     CU(cudaMemsetAsync(d_maxBits, 0, sizeof(unsigned int), st));
-    const long baseA = frameIdx ? (long)sLo : 0;   // row of the device copy = frameIdx[f] - sLo, or the list position itself
-    if ((rc = i8_stats(qA, d.crd.p, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
+    const long baseA = frameIdx ? rowBase : 0;
+    if ((rc = i8_stats(qA, d_list0, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, st))) return rc;
     // centroids: double rows of 3 N, already gathered; cpptraj keeps them centred (Metric_RMS.cpp:66-81), so the
     // centring here moves them by rounding noise only
     if ((rc = i8_stats(qB, d.crdB.p, (size_t)3 * nAtoms, nullptr, 0, 0, nullptr, nAtoms, d_mass, d_mass, d_maxBits, st, -1, true))) return rc;
@@ -1840,7 +1863,7 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
     guard.settled = true;
     if (ok) {
       if ((rc = i8_clear(qA, st)) || (rc = i8_clear(qB, st))) return rc;
-      if ((rc = i8_quant(qA, d.crd.p, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, qs, st))) return rc;
+      if ((rc = i8_quant(qA, d_list0, width, d_fidx, baseA, 0, (const int*)d.idxA.p, nAtoms, d_mass, qs, st))) return rc;
       if ((rc = i8_quant(qB, d.crdB.p, (size_t)3 * nAtoms, nullptr, 0, 0, nullptr, nAtoms, d_mass, qs, st, -1, true))) return rc;
       if ((rc = d.outChunk[0].reserve((size_t)nP * K * sizeof(float)))) return rc;
       t.begin(st);
@@ -1872,8 +1895,8 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
     for (int k = 0; k < K; ++k) {
       COUNT_LAUNCH();
       onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
-      if ((rc = onevn_run<float>(d.numSMs, d.crd.p, width, nP, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
-                                 dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, (long)sLo))) return rc;
+      if ((rc = onevn_run<float>(d.numSMs, d_list0, width, nP, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
+                                 dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, rowBase))) return rc;
     }
     COUNT_LAUNCH();
     centroid_argmin_kernel<<<(nP + 255) / 256, 256, 0, st>>>(dist, nP, K, distOut ? dOutT : nullptr, dClosest, dClosestDist);
@@ -1906,7 +1929,8 @@ int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, in
   int rc;
   if ((rc = ensure_init_locked())) return rc;
   // frames in equal contiguous shares over the devices (small jobs stay on one)
-  const int nd = nFrames >= 4096 ? (int)g_devs.size() : 1;
+  const bool resident = g_devs[0].resHost == crd && g_devs[0].resBuf.p != nullptr;   // (the resident copy lives on device 0)
+  const int nd = (nFrames >= 4096 && !resident) ? (int)g_devs.size() : 1;
   const int per = (nFrames + nd - 1) / nd;
   ExtentShare share;
   share.parties = nd;
@@ -1917,6 +1941,84 @@ int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, in
   };
   if (nd == 1) return job(0);
   return for_each_device(job);
+}
+
+int b200_coords_resident_begin(const float* crd, size_t frameStrideFloats, int nFramesTotal, const int* atomIdx, int nAtoms) {
+  if (!crd || nFramesTotal <= 0) return fail(B200_ERR_ARG, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc, maxAtom = 0;
+  if ((rc = ensure_init_locked())) return rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  d.resHost = nullptr;
+  double h2d = 0.0;
+  if ((rc = upload_crd(d, d.resBuf, crd, frameStrideFloats, 0, nFramesTotal, width, d.stream[0], &h2d))) return rc;
+  CU(cudaStreamSynchronize(d.stream[0]));
+  d.resHost = crd; d.resStride = frameStrideFloats; d.resWidth = width; d.resFrames = nFramesTotal;
+  { std::lock_guard<std::mutex> sl(g_statMu); g_stats.h2d_bytes += h2d; }
+  return B200_OK;
+}
+
+int b200_coords_resident_end(const float* crd) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return B200_OK;
+  Device& d = g_devs[0];
+  if (crd == nullptr || d.resHost == crd) {
+    cudaSetDevice(d.id);
+    d.resBuf.release();
+    d.resHost = nullptr; d.resWidth = 0; d.resFrames = 0;
+  }
+  return B200_OK;
+}
+
+int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal, const int* frames, const int* offsets,
+                              int nClusters, const int* atomIdx, int nAtoms, const double* mass, int fit, double* centroidsOut) {
+  if (!crd || !frames || !offsets || !centroidsOut || nClusters <= 0) return fail(B200_ERR_ARG, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc, maxAtom = 0;
+  if ((rc = ensure_init_locked())) return rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  const int nList = offsets[nClusters];
+  if (offsets[0] != 0 || nList < 0) return fail(B200_ERR_ARG, "bad offsets");
+  if (nList == 0) return B200_OK;
+  int sLo = nFramesTotal, sHi = 0;
+  for (int k = 0; k < nClusters; ++k) if (offsets[k + 1] < offsets[k]) return fail(B200_ERR_ARG, "offsets not ascending");
+  for (int p = 0; p < nList; ++p) {
+    if (frames[p] < 0 || frames[p] >= nFramesTotal) return fail(B200_ERR_ARG, "frames[%d]=%d out of range", p, frames[p]);
+    sLo = std::min(sLo, frames[p]); sHi = std::max(sHi, frames[p] + 1);
+  }
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  const float* d_frames = nullptr;
+  size_t pitch = width;
+  long rowBase = 0;
+  if ((rc = get_coords(d, d.crd, crd, frameStrideFloats, nFramesTotal, sLo, sHi, width, st, &h2d, &d_frames, &pitch, &rowBase))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
+  if ((rc = upload_vec(d.frameIdx, frames, (size_t)nList, st))) return rc;
+  if ((rc = upload_vec(d.idxB, offsets, (size_t)nClusters + 1, st))) return rc;
+  const size_t outBytes = (size_t)nClusters * 3 * (size_t)nAtoms * sizeof(double);
+  if ((rc = d.planesB.reserve(outBytes))) return rc;
+  CU(cudaMemsetAsync(d.planesB.p, 0, outBytes, st));
+  CentroidArgs a;
+  a.crd = d_frames; a.stride = pitch; a.srcBase = rowBase; a.frames = (const int*)d.frameIdx.p;
+  a.offsets = (const int*)d.idxB.p; a.atomIdx = (const int*)d.idxA.p; a.nAtoms = nAtoms;
+  a.mass = mass ? (const double*)d.massA.p : nullptr; a.fit = fit ? 1 : 0; a.out = (double*)d.planesB.p;
+  COUNT_LAUNCH();
+  centroid_build_kernel<<<nClusters, CENT_THREADS, 0, st>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(centroidsOut, d.planesB.p, outBytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  {
+    std::lock_guard<std::mutex> sl(g_statMu);
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)outBytes;
+  }
+  return B200_OK;
 }
 
 int b200_debug_i8_clocks(long long* out, int ctas) {

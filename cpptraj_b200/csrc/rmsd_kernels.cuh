@@ -947,6 +947,113 @@ __global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, con
 }
 
 // ----------------------------------------------------------------------------
+// centroid_build_kernel: Metric_RMS::CalculateCentroid (src/Cluster/Metric_RMS.cpp:86-113) for many clusters at once.
+// The reference fits every frame of a cluster, in order, to the running SUM of the frames before it and adds the
+// rotated frame -- a scan: frame j cannot start before frame j-1 has been added.  One CTA per cluster walks its frame
+// list; within a frame the atoms are spread over the threads: pass A accumulates the covariance with the running sum
+// (17 FP64 sums, block reduction), one thread solves for the rotation (same quartic / adjugate code as the one-vs-many
+// path), pass B rotates the centred frame and adds it.  The running sum lives in the output array (L2-resident).
+// ----------------------------------------------------------------------------
+constexpr int CENT_THREADS = 512;
+struct CentroidArgs {
+  const float* crd; size_t stride; long srcBase;   // frame f is row f - srcBase
+  const int* frames;      // concatenated frame lists
+  const int* offsets;     // [K + 1]
+  const int* atomIdx; int nAtoms;
+  const double* mass;     // nullable
+  int fit;
+  double* out;            // K x 3 nAtoms: running sum, finally the centroid
+};
+__global__ void __launch_bounds__(CENT_THREADS) centroid_build_kernel(CentroidArgs a) {
+  __shared__ double red[CENT_THREADS / 32][17];
+  __shared__ double bc[16];   // broadcast: U (9), centre (3), [12] total mass
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.x;
+  const int j0 = a.offsets[k], m = a.offsets[k + 1] - j0;
+  if (m <= 0) return;
+  double* cent = a.out + (size_t)k * 3 * a.nAtoms;
+  auto block_sum = [&](double* v, int n) {   // v[0..n) summed over the block into bc-independent `red`, result in v on all threads
+    for (int x = 0; x < n; ++x) { const double s = warp_sum(v[x]); if (lane == 0) red[warp][x] = s; }
+    __syncthreads();
+    for (int x = 0; x < n; ++x) { double s = 0.0; for (int w = 0; w < CENT_THREADS / 32; ++w) s += red[w][x]; v[x] = s; }
+    __syncthreads();
+  };
+  // ---- first frame: the start of the sum, centred when fitting (:94-97)
+  {
+    const float* src = a.crd + (size_t)((long)a.frames[j0] - a.srcBase) * a.stride;
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = tid; i < a.nAtoms; i += CENT_THREADS) {
+      const size_t at = (size_t)(a.atomIdx ? a.atomIdx[i] : i);
+      const double w = a.mass ? a.mass[i] : 1.0;
+      const double x = (double)src[3 * at], y = (double)src[3 * at + 1], z = (double)src[3 * at + 2];
+      cent[3 * i] = x; cent[3 * i + 1] = y; cent[3 * i + 2] = z;
+      v[0] += w * x; v[1] += w * y; v[2] += w * z; v[3] += w;
+    }
+    block_sum(v, 4);
+    if (tid == 0) bc[12] = v[3];
+    if (a.fit && v[3] != 0.0) {
+      const double cx = v[0] / v[3], cy = v[1] / v[3], cz = v[2] / v[3];
+      for (int i = tid; i < a.nAtoms; i += CENT_THREADS) { cent[3 * i] -= cx; cent[3 * i + 1] -= cy; cent[3 * i + 2] -= cz; }
+    }
+    __syncthreads();
+  }
+  const double M = bc[12];
+  for (int j = 1; j < m; ++j) {
+    const float* src = a.crd + (size_t)((long)a.frames[j0 + j] - a.srcBase) * a.stride;
+    if (a.fit) {
+      const size_t at0 = (size_t)(a.atomIdx ? a.atomIdx[0] : 0);
+      const double ox = (double)src[3 * at0], oy = (double)src[3 * at0 + 1], oz = (double)src[3 * at0 + 2];
+      // pass A: v[0..8] = sum m x' r^T, [9..11] = sum m x', [12] = sum m |x'|^2, [13..15] = sum m r, [16] = sum m |r|^2
+      double v[17];
+#pragma unroll
+      for (int x = 0; x < 17; ++x) v[x] = 0.0;
+      for (int i = tid; i < a.nAtoms; i += CENT_THREADS) {
+        const size_t at = (size_t)(a.atomIdx ? a.atomIdx[i] : i);
+        const double w = a.mass ? a.mass[i] : 1.0;
+        const double x = (double)src[3 * at] - ox, y = (double)src[3 * at + 1] - oy, z = (double)src[3 * at + 2] - oz;
+        const double rx = cent[3 * i], ry = cent[3 * i + 1], rz = cent[3 * i + 2];
+        const double mx = w * x, my = w * y, mz = w * z;
+        v[0] += mx * rx; v[1] += mx * ry; v[2] += mx * rz;
+        v[3] += my * rx; v[4] += my * ry; v[5] += my * rz;
+        v[6] += mz * rx; v[7] += mz * ry; v[8] += mz * rz;
+        v[9] += mx; v[10] += my; v[11] += mz;
+        v[12] += mx * x + my * y + mz * z;
+        v[13] += w * rx; v[14] += w * ry; v[15] += w * rz;
+        v[16] += w * (rx * rx + ry * ry + rz * rz);
+      }
+      block_sum(v, 17);
+      if (tid == 0) {
+        const double cx = v[9] / M, cy = v[10] / M, cz = v[11] / M;   // centre of the frame relative to o
+        double S[9];
+        S[0] = v[0] - cx * v[13]; S[1] = v[1] - cx * v[14]; S[2] = v[2] - cx * v[15];
+        S[3] = v[3] - cy * v[13]; S[4] = v[4] - cy * v[14]; S[5] = v[5] - cy * v[15];
+        S[6] = v[6] - cz * v[13]; S[7] = v[7] - cz * v[14]; S[8] = v[8] - cz * v[15];
+        const double gt = v[12] - M * (cx * cx + cy * cy + cz * cz);
+        const double e0 = 0.5 * (gt + v[16]);
+        const double lam = largest_root(quartic_of(S), e0, S);
+        rotation_from_cov(S, lam, bc);
+        bc[9] = cx + ox; bc[10] = cy + oy; bc[11] = cz + oz;
+      }
+      __syncthreads();
+    }
+    // pass B: rotate the centred frame (Frame::Rotate, src/Frame.h:508-517) and add it (:102-104)
+    for (int i = tid; i < a.nAtoms; i += CENT_THREADS) {
+      const size_t at = (size_t)(a.atomIdx ? a.atomIdx[i] : i);
+      double x = (double)src[3 * at], y = (double)src[3 * at + 1], z = (double)src[3 * at + 2];
+      if (a.fit) {
+        x -= bc[9]; y -= bc[10]; z -= bc[11];
+        const double X = x * bc[0] + y * bc[1] + z * bc[2], Y = x * bc[3] + y * bc[4] + z * bc[5],
+                     Z = x * bc[6] + y * bc[7] + z * bc[8];
+        x = X; y = Y; z = Z;
+      }
+      cent[3 * i] += x; cent[3 * i + 1] += y; cent[3 * i + 2] += z;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < 3 * a.nAtoms; i += CENT_THREADS) cent[i] /= (double)m;   // (:108)
+}
+
+// ----------------------------------------------------------------------------
 // FP64 MMA issue-peak probe (register-only): roofline denominator for pair_kernel.
 // ----------------------------------------------------------------------------
 template <int VAR>

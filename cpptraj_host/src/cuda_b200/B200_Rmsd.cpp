@@ -94,50 +94,119 @@ int Cpptraj::B200::ClosestCentroids(DataSet_Coords_CRD const& crd, AtomMask cons
   return 0;
 }
 
-// -----------------------------------------------------------------------------
-Cpptraj::B200::Rmsd1vN::~Rmsd1vN() { if (handle_ != 0) b200_rmsd_1vN_end(handle_); }
-
-int Cpptraj::B200::Rmsd1vN::Begin(Frame const& selectedRef, Frame const& massFrame, bool fit, bool useMass) {
+int Cpptraj::B200::CentroidDists(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+                                 bool fit, Cluster::Cframes const& frames, Frame const& centroidFrame,
+                                 std::vector<double>& dist)
+{
   if (Init()) return 1;
-  if (handle_ != 0) { b200_rmsd_1vN_end(handle_); handle_ = 0; }
+  dist.assign(frames.size(), 0.0);
+  if (frames.size() < 1) return 0;
+  if (centroidFrame.Natom() != mask.Nselected()) {
+    mprinterr("Error: B200 RMSD: centroid has %i atoms, mask selects %i\n", centroidFrame.Natom(), mask.Nselected());
+    return 1;
+  }
+  if (b200_rmsd_frames_to_centroids(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &(*frames.begin()), (int)frames.size(),
+                                    &mask.Selected()[0], mask.Nselected(), ptr_or_null(mass), fit ? 1 : 0,
+                                    centroidFrame.xAddress(), 1, &dist[0], 0, 0))
+    return b200_err("frame-centroid distances");
+  return 0;
+}
+
+int Cpptraj::B200::BuildCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+                                  bool fit, std::vector<Cluster::Cframes const*> const& clusterFrames,
+                                  std::vector<Frame*> const& centroids)
+{
+  if (Init()) return 1;
+  if (clusterFrames.size() != centroids.size()) {
+    mprinterr("Internal Error: B200 RMSD: %zu frame lists, %zu centroids\n", clusterFrames.size(), centroids.size());
+    return 1;
+  }
+  if (clusterFrames.empty()) return 0;
+  const size_t n3 = (size_t)3 * (size_t)mask.Nselected();
+  std::vector<int> offsets(1, 0), frames;
+  for (size_t k = 0; k != clusterFrames.size(); k++) {
+    frames.insert(frames.end(), clusterFrames[k]->begin(), clusterFrames[k]->end());
+    offsets.push_back( (int)frames.size() );
+  }
+  if (frames.empty()) return 0;
+  std::vector<double> out( clusterFrames.size() * n3 );
+  if (b200_rmsd_build_centroids(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &frames[0], &offsets[0],
+                                (int)clusterFrames.size(), &mask.Selected()[0], mask.Nselected(), ptr_or_null(mass),
+                                fit ? 1 : 0, &out[0]))
+    return b200_err("centroids");
+  for (size_t k = 0; k != centroids.size(); k++) {
+    if (clusterFrames[k]->empty()) continue;
+    if (centroids[k]->Natom() != mask.Nselected()) {
+      mprinterr("Internal Error: B200 RMSD: centroid frame %zu has %i atoms, mask selects %i\n", k, centroids[k]->Natom(), mask.Nselected());
+      return 1;
+    }
+    std::copy(out.begin() + k * n3, out.begin() + (k + 1) * n3, centroids[k]->xAddress());
+  }
+  return 0;
+}
+
+// -----------------------------------------------------------------------------
+Cpptraj::B200::ResidentCoords::~ResidentCoords() { if (crd_ != 0) b200_coords_resident_end(crd_); }
+
+int Cpptraj::B200::ResidentCoords::Begin(DataSet_Coords_CRD const& crd, AtomMask const& mask) {
+  if (Init()) return 1;
+  if (crd.Size() < 1 || mask.None()) return 0;
+  if (b200_coords_resident_begin(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &mask.Selected()[0], mask.Nselected())) {
+    mprintf("Warning: B200 RMSD: coordinates not kept on the device (%s).\n", b200_last_error());
+    return 1;
+  }
+  crd_ = crd.RawFrames();
+  return 0;
+}
+
+// -----------------------------------------------------------------------------
+Cpptraj::B200::Rmsd1vN::~Rmsd1vN() { End(); }
+
+void Cpptraj::B200::Rmsd1vN::End() { if (handle_ != 0) { b200_rmsd_1vN_end(handle_); handle_ = 0; } }
+
+int Cpptraj::B200::Rmsd1vN::Begin(Frame const& selectedRef, Frame const& massFrame, const int* atomIdx,
+                                  bool fit, bool useMass, bool wantRot)
+{
+  if (Init()) return 1;
+  End();
   nAtoms_ = selectedRef.Natom();
-  nBuffered_ = 0; best_ = -1;
   if (nAtoms_ < 1) { mprinterr("Error: B200 RMSD: empty reference selection.\n"); return 1; }
-  buffer_.resize( (size_t)BATCH * 3 * (size_t)nAtoms_ );
-  std::vector<int> identity( nAtoms_ );           // frames arrive already gathered (tgtFrame_.SetCoordinates)
-  for (int i = 0; i < nAtoms_; i++) identity[i] = i;
+  std::vector<int> identity;
+  if (atomIdx == 0) {                              // frames arrive already gathered (tgtFrame_.SetCoordinates)
+    identity.resize( nAtoms_ );
+    for (int i = 0; i < nAtoms_; i++) identity[i] = i;
+    atomIdx = &identity[0];
+  }
   std::vector<double> mass;
   if (useMass) mass = MassesOf(massFrame);
-  if (b200_rmsd_1vN_begin(selectedRef.xAddress(), &identity[0], nAtoms_, ptr_or_null(mass), fit ? 1 : 0, 0, &handle_))
+  if (b200_rmsd_1vN_begin(selectedRef.xAddress(), atomIdx, nAtoms_, ptr_or_null(mass), fit ? 1 : 0, wantRot ? 1 : 0, &handle_))
     return b200_err("rmsd setup");
   return 0;
 }
 
-int Cpptraj::B200::Rmsd1vN::pushBuffer() {
-  if (nBuffered_ == 0) return 0;
-  if (b200_rmsd_1vN_push_f64(handle_, &buffer_[0], (size_t)3 * (size_t)nAtoms_, (int)nBuffered_)) return b200_err("rmsd push");
-  nBuffered_ = 0;
+int Cpptraj::B200::Rmsd1vN::SetRef(Frame const& selectedRef) {
+  if (handle_ == 0 || selectedRef.Natom() != nAtoms_) {
+    mprinterr("Error: B200 RMSD: reference has %i selected atoms, handle %i\n", selectedRef.Natom(), nAtoms_);
+    return 1;
+  }
+  if (b200_rmsd_1vN_set_ref(handle_, selectedRef.xAddress())) return b200_err("rmsd reference");
   return 0;
 }
 
-int Cpptraj::B200::Rmsd1vN::Push(Frame const& selectedTgt) {
-  if (selectedTgt.Natom() != nAtoms_) {
+int Cpptraj::B200::Rmsd1vN::One(Frame const& selectedTgt, double& rmsd, double* rot, double* trans) {
+  if (handle_ == 0 || selectedTgt.Natom() != nAtoms_) {
     mprinterr("Error: B200 RMSD: frame has %i selected atoms, reference %i\n", selectedTgt.Natom(), nAtoms_);
     return 1;
   }
-  const double* x = selectedTgt.xAddress();
-  std::copy(x, x + (size_t)3 * (size_t)nAtoms_, buffer_.begin() + (size_t)nBuffered_ * 3 * (size_t)nAtoms_);
-  if (++nBuffered_ == BATCH) return pushBuffer();
+  if (b200_rmsd_1vN_push_f64(handle_, selectedTgt.xAddress(), (size_t)3 * (size_t)nAtoms_, 1)) return b200_err("rmsd push");
+  if (b200_rmsd_1vN_flush(handle_, &rmsd, rot, trans, 0)) return b200_err("rmsd flush");
   return 0;
 }
 
-int Cpptraj::B200::Rmsd1vN::Flush(DataSet_double& rmsd) {
-  if (handle_ == 0) return 0;
-  if (pushBuffer()) return 1;
-  const long n = b200_rmsd_1vN_pending(handle_);
-  if (n < 1) return 0;
-  std::vector<double> r( (size_t)n );
-  if (b200_rmsd_1vN_flush(handle_, &r[0], 0, 0, &best_)) return b200_err("rmsd flush");
-  for (long i = 0; i != n; i++) rmsd.AddElement( r[i] );   // append-only, frame order (DataSet_double.cpp:14-20)
+int Cpptraj::B200::Rmsd1vN::Coords(const float* base, size_t strideFloats, int nFrames, double* rmsd, double* rot, double* trans) {
+  if (handle_ == 0) { mprinterr("Internal Error: B200 RMSD: Coords() before Begin().\n"); return 1; }
+  if (nFrames < 1) return 0;
+  if (b200_rmsd_1vN_push_f32(handle_, base, strideFloats, nFrames)) return b200_err("rmsd push");
+  if (b200_rmsd_1vN_flush(handle_, rmsd, rot, trans, 0)) return b200_err("rmsd flush");
   return 0;
 }

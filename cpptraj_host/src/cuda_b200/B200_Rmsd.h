@@ -41,34 +41,63 @@ int CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<d
 int ClosestCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
                      Cluster::Cframes const& frames, std::vector<Frame const*> const& centroidFrames,
                      std::vector<int>& closest, std::vector<double>& closestDist);
-/** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417) when coordinates are not modified (nomod / nofit):
-  * the selected atoms of every frame (Action_Rmsd::tgtFrame_ after SetCoordinates) are buffered on the host and
-  * pushed to the device in batches; results are appended to the DataSet in frame order at Flush().
+/** Frame-to-centroid RMSDs of many frames against ONE centroid (Metric_RMS::FrameCentroidDist, Cluster/Metric_RMS.cpp:75-81):
+  * the loops of BestReps::FindBestRepFrames_Centroid (Cluster/BestReps.cpp:310-316), Node::CalcAvgToCentroid
+  * (Cluster/Node.cpp:89-101) and Algorithm_Kmeans::FindSeedsFromClusters (Cluster/Algorithm_Kmeans.cpp:296-303).
+  * \a dist receives one value per frame of \a frames, in order.
+  */
+int CentroidDists(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
+                  Cluster::Cframes const& frames, Frame const& centroidFrame, std::vector<double>& dist);
+/** Centroid building (Metric_RMS::CalculateCentroid, Cluster/Metric_RMS.cpp:86-113) for many clusters at once: every
+  * cluster's frames are fitted, in order, to the running sum of the frames before them and averaged -- one CTA per
+  * cluster on the device.  \a clusterFrames: the frame lists, \a centroids: the Centroid_Coord::Cframe() to fill
+  * (set up for mask.Nselected() atoms), same order.
+  */
+int BuildCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
+                   std::vector<Cluster::Cframes const*> const& clusterFrames, std::vector<Frame*> const& centroids);
+/** Keeps the selected span of a COORDS set on the device while it exists (Cluster::Control::Run, Cluster/Control.cpp:690-830):
+  * the centroid / frame-to-centroid calls of a clustering run then skip the upload.  The frames must not change meanwhile.
+  */
+class ResidentCoords {
+  public:
+    ResidentCoords() : crd_(0) {}
+    ~ResidentCoords();
+    /// \return 0 if OK; on failure the calls simply upload what they need.
+    int Begin(DataSet_Coords_CRD const&, AtomMask const&);
+  private:
+    ResidentCoords(ResidentCoords const&);
+    ResidentCoords& operator=(ResidentCoords const&);
+    const float* crd_;
+};
+/** One-vs-many RMSD for Action_Rmsd (Action_Rmsd.cpp:321-417).  Two uses:
+  *  - frame by frame (One): the selected atoms of the current frame (Action_Rmsd::tgtFrame_ after SetCoordinates) are
+  *    pushed and the result is read back at once -- RMSD, rotation matrix, target-to-origin translation -- so that
+  *    DoAction() continues exactly as with Frame::RMSD_CenteredRef (savematrices, savevectors, coordinate
+  *    modification, DataSet::Add by frame number);
+  *  - a whole in-memory COORDS set (Coords): raw float frames, gathered by the mask on the device, one pass
+  *    ('crdaction <set> rms ...', Exec_CrdAction.cpp:78-98).
   */
 class Rmsd1vN {
   public:
-    Rmsd1vN() : handle_(0), nAtoms_(0), nBuffered_(0), best_(-1) {}
+    Rmsd1vN() : handle_(0), nAtoms_(0) {}
     ~Rmsd1vN();
     /// \param selectedRef REF_.SelectedRef(): selected atoms, already centred when fitting (ReferenceAction.cpp:155-169)
     /// \param massFrame Frame whose per-atom masses weight the fit (the TARGET frame's, Frame.cpp:1184-1208)
-    int Begin(Frame const& selectedRef, Frame const& massFrame, bool fit, bool useMass);
+    /// \param atomIdx Selected atom numbers when raw COORDS frames will be pushed (Coords); 0 when frames arrive gathered (One)
+    int Begin(Frame const& selectedRef, Frame const& massFrame, const int* atomIdx, bool fit, bool useMass, bool wantRot);
     bool Active() const { return handle_ != 0; }
-    /// Buffer the selected atoms of one frame (Frame set up from the target mask).
-    int Push(Frame const& selectedTgt);
-    /// Push what is buffered, wait, append all pending RMSDs to \a rmsd in push order. \return 0 if OK.
-    int Flush(DataSet_double& rmsd);
-    /// Index (over all frames pushed) of the smallest RMSD so far.
-    long BestFrame() const { return best_; }
+    void End();
+    /// Replace the reference (reftraj / previous).
+    int SetRef(Frame const& selectedRef);
+    /// Fit one frame (set up from the target mask). \a rot (9, row-major U) and \a trans (3) are set when fitting with wantRot.
+    int One(Frame const& selectedTgt, double& rmsd, double* rot, double* trans);
+    /// Fit \a nFrames raw COORDS frames (frame i at base + i*strideFloats). Outputs sized nFrames, 9*nFrames, 3*nFrames (rot/trans may be 0).
+    int Coords(const float* base, size_t strideFloats, int nFrames, double* rmsd, double* rot, double* trans);
   private:
     Rmsd1vN(Rmsd1vN const&);
     Rmsd1vN& operator=(Rmsd1vN const&);
-    int pushBuffer();
-    static const unsigned int BATCH = 512;   ///< frames per device push
     b200_1vN* handle_;
     int nAtoms_;
-    unsigned int nBuffered_;
-    long best_;
-    std::vector<double> buffer_;             ///< BATCH x 3*nAtoms_ selected coordinates
 };
 }
 }

@@ -139,6 +139,27 @@ int b200_rmsd_frames_to_centroids(const float* crd, size_t frameStrideFloats, in
                                   const double* centroids, int nCentroids,
                                   double* distOut, int* closestOut, double* closestDistOut);
 
+/* ---- cluster: COORDS resident on the device -----------------------------------------------
+ * A clustering run calls the two functions above (and the one below) many times on the same, unchanging COORDS set
+ * (Cluster::Control::Run, src/Cluster/Control.cpp:690-830).  Between begin and end the leading 3*(max atomIdx + 1)
+ * floats of every frame stay on device 0 and calls that pass the same `crd` (same stride and frame count, atoms
+ * within that span) skip the upload.  The caller must not modify the frames in between.  end(NULL) drops any. */
+int b200_coords_resident_begin(const float* crd, size_t frameStrideFloats, int nFramesTotal,
+                               const int* atomIdx, int nAtoms);
+int b200_coords_resident_end(const float* crd);
+
+/* ---- cluster: centroid building with fit ----------------------------------------------
+ * Metric_RMS::CalculateCentroid (src/Cluster/Metric_RMS.cpp:86-113) for nClusters clusters at once: cluster k owns
+ * frames[offsets[k] .. offsets[k+1]); its first frame starts a running sum (centred when fit != 0), every further
+ * frame is fitted to that sum, rotated and added, and the sum is divided by the frame count.  centroidsOut:
+ * nClusters x 3*nAtoms doubles (the selected atoms of each Centroid_Coord::Cframe()); clusters without frames are
+ * left as zeros.  The scan over a cluster's frames is sequential by definition; clusters run side by side (one CTA
+ * each).  Runs on device 0. */
+int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nFramesTotal,
+                              const int* frames, const int* offsets, int nClusters,
+                              const int* atomIdx, int nAtoms, const double* mass, int fit,
+                              double* centroidsOut);
+
 /* ---- device-resident variants (benchmarks, pipelines that keep COORDS in HBM)
  * All pointers are DEVICE pointers on the current device; `stream` is a
  * cudaStream_t (NULL = default stream); asynchronous w.r.t. the host.

@@ -68,6 +68,22 @@ class Oracle(_Base):
         L.orc_rmsd_1vN.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+        L.orc_build_centroid.restype = C.c_int
+        L.orc_build_centroid.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_int, C.c_void_p]
+
+    def build_centroid(self, crd, sel, frames, mass=None, fit=True):
+        """Metric_RMS::CalculateCentroid (src/Cluster/Metric_RMS.cpp:86-113): [len(sel), 3] float64."""
+        crd = np.ascontiguousarray(crd, np.float32)
+        sel = np.ascontiguousarray(sel, np.int32)
+        frames = np.ascontiguousarray(frames, np.int32)
+        mass = _opt(mass, np.float64)
+        out = np.zeros((len(sel), 3), np.float64)
+        rc = self.lib.orc_build_centroid(_ptr(crd), crd.shape[1], _ptr(frames), len(frames), _ptr(sel), len(sel),
+                                         _ptr(mass), int(bool(fit)), _ptr(out))
+        if rc:
+            raise RuntimeError("oracle failed rc=%d" % rc)
+        return out
 
     def threads(self):
         return self.lib.orc_num_threads()
@@ -201,6 +217,22 @@ class Reference(_Base):
                                      _ptr(crdR), crdR.shape[1], crdR.shape[0],
                                      natomR or self._natom_total(crdR, selR), _ptr(selR),
                                      len(selT), _ptr(massTgt), _ptr(massRef), int(bool(fit)), _ptr(out))
+        if rc:
+            raise RuntimeError("reference driver failed rc=%d" % rc)
+        return out
+
+    def build_centroid(self, crd, sel, frames, mass=None, fit=True, natom_total=None):
+        crd = np.ascontiguousarray(crd, np.float32)
+        sel = np.ascontiguousarray(sel, np.int32)
+        frames = np.ascontiguousarray(frames, np.int32)
+        mass = _opt(mass, np.float64)
+        out = np.zeros((len(sel), 3), np.float64)
+        f = self.lib.ref_build_centroid
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                      C.c_void_p, C.c_int, C.c_void_p]
+        rc = f(_ptr(crd), crd.shape[1], crd.shape[0], natom_total or self._natom_total(crd, sel), _ptr(frames), len(frames),
+               _ptr(sel), len(sel), _ptr(mass), int(bool(fit)), _ptr(out))
         if rc:
             raise RuntimeError("reference driver failed rc=%d" % rc)
         return out

@@ -243,4 +243,34 @@ int ref_rmsd_1vN(const float* crd, size_t stride, int nF, int natomTotal, const 
   return 0;
 }
 
+// Metric_RMS::CalculateCentroid (src/Cluster/Metric_RMS.cpp:86-113) with the reference's own Frame arithmetic.
+int ref_build_centroid(const float* crd, size_t stride, int nTotalFrames, int natomTotal, const int* frames, int nIn,
+                       const int* sel, int n, const double* mass, int fit, double* cent)
+{
+  Coords C;
+  if (fill(C, crd, stride, nTotalFrames, natomTotal, sel, n, mass)) return 1;
+  bool useMass = (mass != 0);
+  Frame frm1, cframe;
+  frm1.SetupFrameFromMask(C.mask, C.atoms);
+  Matrix_3x3 Rot; Vec3 Trans;
+  for (int j = 0; j < nIn; j++) {
+    getFrame(C, frames[j], frm1);
+    if (cframe.empty()) {
+      cframe = frm1;
+      if (fit) cframe.CenterOnOrigin(useMass);
+    } else {
+      if (fit) {
+        frm1.RMSD_CenteredRef(cframe, Rot, Trans, useMass);
+        frm1.Rotate(Rot);
+      }
+      cframe += frm1;
+    }
+  }
+  if (nIn > 0) {
+    cframe.Divide((double)nIn);
+    std::memcpy(cent, cframe.xAddress(), sizeof(double) * 3 * (size_t)n);
+  }
+  return 0;
+}
+
 } // extern "C"

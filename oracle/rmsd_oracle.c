@@ -424,6 +424,44 @@ int orc_rmsd_1vN(const float *crd, size_t stride, int nF, const int *sel, int n,
     return err;
 }
 
+/* ---- f2: centroid building with fit ------------------------------------------
+ * src/Cluster/Metric_RMS.cpp:86-113 (Metric_RMS::CalculateCentroid): the first
+ * frame of the cluster is the start of a running SUM (centred when fitting);
+ * every further frame is fitted to that sum (RMSD_CenteredRef translates the
+ * frame to the origin and returns the rotation, :101), rotated (Frame::Rotate,
+ * src/Frame.h:508-517: x' = U x) and added; finally divided by the frame count.
+ * frames[nIn]: frame numbers of the cluster; cent: 3n doubles out. */
+int orc_build_centroid(const float *crd, size_t stride, const int *frames, int nIn,
+                       const int *sel, int n, const double *mass, int fit, double *cent)
+{
+    int useMass = (mass != NULL);
+    if (nIn < 1) return 0;
+    double *T = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+    if (!T) return 1;
+    for (int j = 0; j < nIn; j++) {
+        orc_gather(crd, stride, frames[j], sel, n, T);
+        if (j == 0) {
+            memcpy(cent, T, sizeof(double) * 3 * (size_t)n);
+            if (fit) { double c[3]; orc_center_on_origin(cent, n, mass, useMass, c); }   /* :96-97 */
+        } else {
+            if (fit) {
+                double U[9], tr[3];
+                orc_rmsd_centered_ref(T, cent, n, mass, useMass, U, tr);                   /* :100 */
+                for (int i = 0; i < n; i++) {                                              /* :102, Frame.h:508-517 */
+                    double x = T[3 * i], y = T[3 * i + 1], z = T[3 * i + 2];
+                    T[3 * i]     = x * U[0] + y * U[1] + z * U[2];
+                    T[3 * i + 1] = x * U[3] + y * U[4] + z * U[5];
+                    T[3 * i + 2] = x * U[6] + y * U[7] + z * U[8];
+                }
+            }
+            for (int i = 0; i < 3 * n; i++) cent[i] += T[i];                               /* :104 */
+        }
+    }
+    for (int i = 0; i < 3 * n; i++) cent[i] /= (double)nIn;                                /* :108 */
+    free(T);
+    return 0;
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

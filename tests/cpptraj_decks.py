@@ -1,0 +1,84 @@
+"""cpptraj input decks run both by the UNMODIFIED reference (goldens, tools/make_golden_cpptraj.py, here in the build
+container) and by cpptraj.B200 (tests/test_gpu_cpptraj_e2e.py, on the GPU box).  They restate the reference's own
+test decks (file:line below) with the ASCII trajectories tz2.crd / tz2.truncoct.crd in place of the NetCDF ones
+(this build has no NetCDF).  {D} = directory holding tz2.parm7, tz2.crd, tz2.truncoct.parm7,
+tz2.truncoct.crd.  Each deck: name -> (input text, [(output file, kind)]); kind 'table' = numeric columns compared
+with a tolerance, 'crd' = Amber ASCII coordinates compared number by number, 'text' = compared after numeric parsing of
+every token that is a number."""
+
+DECKS = {
+    # test/Test_RMSD/RunTest.sh:14-42 "Basic RMSD tests": first, mass + savevectors combined, reftraj from file and from COORDS
+    "rmsd_basic": ("""noprogress
+parm {D}/tz2.truncoct.parm7
+trajin {D}/tz2.truncoct.crd
+rms Res2-11 first :2-11 out rmsd.dat
+rms Res2-11_mass first :2-11 out rmsd.mass.dat mass savevectors combined vecsout vecs.dat
+rms Res2_11_traj reftraj {D}/tz2.truncoct.crd :2-11 out rmsd.reftraj.dat
+run
+removedata Res2_11_traj
+loadtraj {D}/tz2.truncoct.crd name TZ2
+rms Res2_11_traj reftraj TZ2 :2-11 out rmsd.refcoords.dat
+""", [("rmsd.dat", "table"), ("rmsd.mass.dat", "table"), ("vecs.dat", "table"), ("rmsd.reftraj.dat", "table"),
+      ("rmsd.refcoords.dat", "table")]),
+    # test/Test_RMSD/RunTest.sh:44-62 "RMS coordinate rotation/rotation matrices test": norotate, rotate + savematrices, outtraj
+    "rmsd_rotate": ("""noprogress
+parm {D}/tz2.parm7 [NOWAT]
+reference {D}/tz2.crd parm [NOWAT] 1 [first]
+parm {D}/tz2.truncoct.parm7 [WAT]
+trajin {D}/tz2.truncoct.crd parm [WAT]
+strip :WAT
+rms NOROT ref [first] norotate @CA
+outtraj tz2.norotate.crd parm [WAT]
+rms ROT ref [first] out rms.dat @CA savematrices matricesout rmatrices.dat
+outtraj tz2.rotate.crd parm [WAT]
+""", [("rms.dat", "table"), ("rmatrices.dat", "table"), ("tz2.norotate.crd", "crd"), ("tz2.rotate.crd", "crd")]),
+    # test/Test_RMSD/RunTest.sh:64-76 "RMS nomod"
+    "rmsd_nomod": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+rms First_CA :2-12@CA out NoMod.dat nomod
+trajout NoMod.crd
+""", [("NoMod.dat", "table"), ("NoMod.crd", "crd")]),
+    # test/Test_RMSD/RunTest.sh:78-91 "RMS fit to previous"
+    "rmsd_previous": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+rms ToPrevious :2-12@CA previous out Previous.dat
+""", [("Previous.dat", "table")]),
+    # src/Exec_CrdAction.cpp:78-98: the rms action on an in-memory COORDS set (fit + coordinate modification), a
+    # data set that reads the RMSD set while it is being filled (filter), and the modified coordinates written out
+    "crdaction_rms": ("""noprogress
+parm {D}/tz2.parm7
+loadcrd {D}/tz2.crd name CRD
+crdaction CRD rms R1 first @CA,C,N out crd_rms.dat savematrices matricesout crd_rmat.dat
+crdaction CRD rms R2 first :2-12@CA nofit mass out crd_rms_nofit.dat crdframes 3,90,4
+crdout CRD fitted.crd
+""", [("crd_rms.dat", "table"), ("crd_rmat.dat", "table"), ("crd_rms_nofit.dat", "table"), ("fitted.crd", "crd")]),
+    # an action that reads the RMSD data set during trajectory processing: filter on the running set
+    "rmsd_filter": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+rms R1 first :2-12@CA out filt_rms.dat nomod
+filter R1 min 0.0 max 2.0 out filt.dat
+""", [("filt_rms.dat", "table"), ("filt.dat", "table")]),
+    # src/Analysis_Rms2d.cpp:289-293: rms2d with the pseudo-autocorrelation tail
+    "rms2d_corr": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd 1 40
+2drms crd1 :3-7 rmsout rms2d.dat corr corr.dat
+""", [("rms2d.dat", "table"), ("corr.dat", "table")]),
+    # test/Test_Cluster_Kmeans/RunTest.sh:26-34: k-means (centroid updates Metric_RMS::FrameOpCentroid on the CPU, seed
+    # search, final centroids, best representatives and the cluster summary through the B200 path)
+    "cluster_kmeans": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+cluster means clusters 5 rms @CA summary summary.dat info info.dat out cnumvtime.dat
+""", [("summary.dat", "text"), ("info.dat", "text"), ("cnumvtime.dat", "table")]),
+    # hierarchical agglomerative, fitted, with sieve restore by epsilon (second List::AddFramesByCentroid overload,
+    # src/Cluster/List.cpp:215-298) and centroid best representatives
+    "cluster_hier_sieve_eps": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+cluster crd1 @CA hieragglo epsilon 2.5 averagelinkage rms out hs.out summary hs.summary.dat sieve 4 sievetoframe repsilon 2.0 bestrep centroid savenreps 2
+""", [("hs.out", "table"), ("hs.summary.dat", "text")]),
+}

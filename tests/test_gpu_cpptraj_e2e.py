@@ -74,8 +74,8 @@ def test_cpptraj_cluster_pairwise_cache_on_b200(tmp_path):
 
 
 def test_cpptraj_rms_nomod_on_b200(tmp_path):
-    """test/Test_RMSD/RunTest.sh "RMS nomod": the rmsd action, coordinates not modified, batched through the one-vs-many
-    path by Action_Rmsd and appended in Print()."""
+    """test/Test_RMSD/RunTest.sh "RMS nomod" against the reference's own NoMod.dat.save: the rmsd action, every frame
+    fitted on the device (Action_Rmsd::B200_Fit) and added to the data set by frame number as on the CPU."""
     if not os.path.exists(BIN) or not os.path.exists(os.path.join(STAGE, "NoMod.dat.save")):
         pytest.skip("cpptraj.B200 (with the Action_Rmsd branch) not staged")
     deck = "parm %s\ntrajin %s\nrms First_CA :2-12@CA out NoMod.dat nomod\n" % (
@@ -115,3 +115,67 @@ def test_cpptraj_cluster_sieve_restore_on_b200(tmp_path):
     for g, w in zip(gs, ws):
         assert g[0] == w[0] and g[1] == w[1] and g[5] == w[5]
         assert abs(float(g[3]) - float(w[3])) <= 2e-3 and abs(float(g[6]) - float(w[6])) <= 2e-3
+
+
+# ---------------------------------------------------------------- decks against the unmodified reference
+import sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from cpptraj_decks import DECKS as REF_DECKS   # noqa: E402
+
+
+def _numbers(path):
+    """Every token of a text file: floats where it parses, the string otherwise (comment lines included)."""
+    out = []
+    for line in open(path):
+        for tok in line.split():
+            try:
+                out.append(float(tok))
+            except ValueError:
+                out.append(tok)
+    return out
+
+
+def _amber_crd(path):
+    """Amber ASCII trajectory: title line, then 8.3f fields."""
+    vals = []
+    for line in open(path).readlines()[1:]:
+        vals.extend(float(line[i:i + 8]) for i in range(0, len(line.rstrip("\n")), 8))
+    return np.array(vals)
+
+
+@pytest.mark.parametrize("name", sorted(REF_DECKS))
+def test_cpptraj_deck_matches_unmodified_reference(tmp_path, name):
+    """The reference's Test_RMSD decks 1-4 (first / mass / savevectors / reftraj; norotate / rotate / savematrices /
+    outtraj; nomod; previous -- test/Test_RMSD/RunTest.sh:14-91), `crdaction ... rms` with coordinate modification, an
+    action that reads the RMSD set while it is being filled, `rms2d ... corr`, k-means and hierarchical clustering with the
+    epsilon sieve restore: cpptraj.B200 (every RMSD, rotation, translation, centroid and frame-to-centroid distance from the
+    B200 path) against the UNMODIFIED reference run on the CPU (tools/make_golden_cpptraj.py -> tests/golden/cpptraj/)."""
+    gold = os.path.join(ROOT, "tests", "golden", "cpptraj", name)
+    if not os.path.exists(BIN) or not os.path.isdir(gold):
+        pytest.skip("cpptraj.B200 not staged or goldens missing")
+    text, outs = REF_DECKS[name]
+    if "tz2.truncoct" in text and not os.path.exists(os.path.join(STAGE, "tz2.truncoct.crd")):
+        pytest.skip("tz2.truncoct.* not staged")
+    (tmp_path / "in").write_text(text.replace("{D}", STAGE))
+    r = subprocess.run([BIN, "-i", "in"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path))
+    assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-3000:]
+    assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    for fname, kind in outs:
+        got_p, want_p = str(tmp_path / fname), os.path.join(gold, fname)
+        if kind == "table":
+            got, want = table(got_p), table(want_p)
+            assert got.shape == want.shape, (fname, got.shape, want.shape)
+            # values are printed with 4 decimals: the contract (1e-4 A) plus one unit of the last printed digit
+            assert np.abs(got - want).max() <= 2.01e-4, (fname, np.abs(got - want).max())
+        elif kind == "crd":
+            got, want = _amber_crd(got_p), _amber_crd(want_p)
+            assert got.shape == want.shape, (fname, got.shape, want.shape)
+            assert np.abs(got - want).max() <= 1.01e-3, (fname, np.abs(got - want).max())   # 8.3f fields: one unit of the last digit
+        else:
+            got, want = _numbers(got_p), _numbers(want_p)
+            assert len(got) == len(want), fname
+            for g, w in zip(got, want):
+                if isinstance(w, float):
+                    assert isinstance(g, float) and abs(g - w) <= 2e-3 + 1e-6 * abs(w), (fname, g, w)
+                else:
+                    assert g == w, (fname, g, w)

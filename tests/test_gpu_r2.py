@@ -224,6 +224,46 @@ def test_frames_to_centroids_one_contraction(b200, oracle, K, use_mass):
         assert np.array_equal(closest, dist.argmin(1))
 
 
+# ---------------------------------------------------------------- centroid building with fit
+@pytest.mark.parametrize("fit,use_mass", [(True, False), (True, True), (False, False)])
+def test_build_centroids(b200, oracle, fit, use_mass):
+    """Metric_RMS::CalculateCentroid (src/Cluster/Metric_RMS.cpp:86-113): frames fitted in order to the running sum.
+    The oracle's restatement is bit-identical to the reference's own Frame arithmetic (tests/test_oracle.py)."""
+    c, m, sel = synth_case(4711, 400, 260, 300, 5)
+    mass = m[sel] if use_mass else None
+    rng = np.random.default_rng(1)
+    lists = [np.array([7], np.int32), np.arange(0, 400, 4, dtype=np.int32), rng.permutation(400)[:150].astype(np.int32),
+             np.zeros(0, np.int32), np.array([64, 63, 399, 5, 5], np.int32)]      # bit-identical neighbours, a repeated frame, an empty cluster
+    got = b200.build_centroids(c, sel, lists, mass=mass, fit=fit)
+    assert got.shape == (len(lists), len(sel), 3)
+    for k, fr in enumerate(lists):
+        if len(fr) == 0:
+            assert np.all(got[k] == 0.0)
+            continue
+        want = oracle.build_centroid(c, sel, fr, mass=mass, fit=fit)
+        assert maxdiff(got[k], want) <= 1e-8, (k, maxdiff(got[k], want))
+    # COORDS resident on the device (a clustering run): same bits, no frame upload
+    b200.coords_resident_begin(c, sel)
+    try:
+        b200.reset_stats()
+        assert np.array_equal(b200.build_centroids(c, sel, lists, mass=mass, fit=fit), got)
+        assert b200.get_stats()["h2d_bytes"] < 0.05 * c.nbytes
+        if fit:
+            d1 = b200.frames_to_centroids(c, sel, got[[1, 2, 4]].reshape(3, -1), mass=mass)[0]
+    finally:
+        b200.coords_resident_end()
+    if fit:
+        assert np.array_equal(b200.frames_to_centroids(c, sel, got[[1, 2, 4]].reshape(3, -1), mass=mass)[0], d1)
+    # the centroids feed the frame-to-centroid distances: same nearest centroid as with the oracle's centroids
+    if fit:
+        cen = got[[0, 1, 2, 4]]
+        _, closest, _ = b200.frames_to_centroids(c, sel, cen.reshape(4, -1), mass=mass)
+        wantc = np.stack([oracle.rmsd_1vN(c, sel, oracle.build_centroid(c, sel, lists[k], mass=mass), mass=mass) for k in (0, 1, 2, 4)], axis=1)
+        srt = np.sort(wantc, axis=1)
+        clear = (srt[:, 1] - srt[:, 0]) > 2 * TOL
+        assert np.array_equal(closest[clear], wantc.argmin(1)[clear])
+
+
 # ---------------------------------------------------------------- several devices, one process (what CPPTRAJ_B200_NGPU drives)
 def test_single_process_multi_device(oracle):
     import torch

@@ -108,3 +108,16 @@ def test_edge_cases(oracle):
     assert out.shape == (1,) and out[0] < 1e-5
     z = oracle.rms2d_tri(c, sel, mass=np.zeros(4))          # total mass < SMALL: reference returns -1
     assert np.all(z == -1.0)
+
+
+def test_centroid_builder_vs_compiled_reference(oracle, reference):
+    """SURVEY 8(f) rank 2: Metric_RMS::CalculateCentroid restated (oracle/rmsd_oracle.c: orc_build_centroid) against the
+    reference's own Frame::RMSD_CenteredRef / Rotate / += / Divide (oracle/ref_driver.cpp: ref_build_centroid)."""
+    from helpers import synth_case
+    c, m, sel = synth_case(9, 60, 40, 50, 2)
+    for frames in (np.array([3, 17, 4, 55, 20, 21, 0], np.int32), np.array([8], np.int32), np.arange(60, dtype=np.int32)):
+        for mass in (None, m[sel]):
+            for fit in (True, False):
+                a = oracle.build_centroid(c, sel, frames, mass, fit)
+                b = reference.build_centroid(c, sel, frames, mass, fit, natom_total=50)
+                assert np.array_equal(a, b)
