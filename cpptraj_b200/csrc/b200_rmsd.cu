@@ -940,7 +940,7 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
   const size_t outElts = tri_row_start(F, (size_t)row1) - tri_row_start(F, (size_t)row0);
   const bool pinnedIn = host_ptr_is_pinned(crd + (size_t)f0 * stride);
   OutRing ring(d, outTri, host_ptr_is_pinned(outFirst), outFirst, outElts, true);
-  for (int s = 1; s < NSLOT; ++s) if ((rc = ring.reserve(s, maxChunk))) return rc;
+  // (ring slots are reserved at first use: in a fresh process pinning slot k+1 overlaps the work queued for slot k)
   std::vector<cudaEvent_t> evs;
   auto cleanup = [&]() { for (cudaEvent_t e : evs) cudaEventDestroy(e); evs.clear(); };
   const float* d_crd = (const float*)d.crd.p;
@@ -975,7 +975,7 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     evs.push_back(ev);
     CU(cudaEventRecord(ev, sIn));
     const int s = 1 + (band++ % (NSLOT - 1));
-    if ((rc = ring.retire(s))) { cleanup(); return rc; }
+    if ((rc = ring.retire(s)) || (rc = ring.reserve(s, maxChunk))) { cleanup(); return rc; }
     cudaStream_t st = d.stream[s];
     CU(cudaStreamWaitEvent(st, ev, 0));
     const size_t base = tri_row_start(F, lo), n = tri_row_start(F, hi) - base;
@@ -1086,12 +1086,11 @@ int host_tri_on_device(Device& d, const float* crd, size_t stride, int nFramesTo
     const int i1 = std::min(row1, i0 + bandRows);
     maxChunk = std::max(maxChunk, tri_row_start(F, i1) - tri_row_start(F, i0));
   }
-  for (int s = 0; s < NSLOT; ++s) if ((rc = ring.reserve(s, maxChunk))) return rc;
   int band = 0;
   long nLaunch = 0;
   for (int i0 = row0; i0 < row1; i0 += bandRows, ++band) {
     const int s = band % NSLOT;
-    if ((rc = ring.retire(s))) return rc;
+    if ((rc = ring.retire(s)) || (rc = ring.reserve(s, maxChunk))) return rc;
     const int i1 = std::min(row1, i0 + bandRows);
     const size_t base = tri_row_start(F, i0), n = tri_row_start(F, i1) - base;
     cudaStream_t st = d.stream[s];

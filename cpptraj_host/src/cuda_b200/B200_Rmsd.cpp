@@ -2,6 +2,8 @@
 #include "b200_rmsd.h"
 #include <cstdlib>
 #include <algorithm>
+#include <thread>
+#include "../Timer.h"
 #include "../AtomMask.h"
 #include "../CpptrajStdio.h"
 #include "../DataSet_Coords_CRD.h"
@@ -15,15 +17,40 @@ static int b200_err(const char* what) {
   return 1;
 }
 
-int Cpptraj::B200::Init() {
-  static bool initialised = false;
-  if (initialised) return 0;
-  int want = 0, used = 0;
+// Device set-up (CUDA context, streams, host copy pools: ~1 s in a fresh process) may be started early, on a thread of
+// its own, by the Setup()/Init() of the commands that will use the path: it then overlaps trajectory reading.
+static bool b200_initialised = false, b200_async_started = false;
+static int b200_init_rc = 0, b200_init_used = 0;
+static double b200_init_seconds = 0.0;
+static std::thread b200_init_thread;
+
+static void b200_do_init() {
+  int want = 0;
   const char* env = getenv("CPPTRAJ_B200_NGPU");
   if (env != 0) want = atoi(env);
-  if (b200_init(want, &used)) return b200_err("device probe");
-  mprintf("\tB200 RMSD path: %i device(s).\n", used);
-  initialised = true;
+  Timer t_init;
+  t_init.Start();
+  b200_init_rc = b200_init(want, &b200_init_used);
+  t_init.Stop();
+  b200_init_seconds = t_init.Total();
+}
+
+void Cpptraj::B200::InitAsync() {
+  if (b200_initialised || b200_async_started) return;
+  b200_async_started = true;
+  b200_init_thread = std::thread( b200_do_init );
+}
+
+int Cpptraj::B200::Init() {
+  if (b200_initialised) return 0;
+  if (b200_async_started) {
+    if (b200_init_thread.joinable()) b200_init_thread.join();
+  } else
+    b200_do_init();
+  if (b200_init_rc) { b200_async_started = false; return b200_err("device probe"); }
+  mprintf("\tB200 RMSD path: %i device(s) (set-up %.4f s%s).\n", b200_init_used, b200_init_seconds,
+          b200_async_started ? ", started in the background at command set-up" : "");
+  b200_initialised = true;
   return 0;
 }
 
@@ -47,6 +74,8 @@ int Cpptraj::B200::Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask,
   if (tgt.Size() < 1 || tgtMask.Nselected() < 1) return 0;
   float* mat = static_cast<float*>( out.MatrixPtr() );
   int err;
+  Timer t_call;
+  t_call.Start();
   if (!fullMatrix)
     err = b200_rms2d_tri(tgt.RawFrames(), tgt.FrameStride(), (int)tgt.Size(), 0, (int)tgt.Size(),
                          &tgtMask.Selected()[0], tgtMask.Nselected(), ptr_or_null(tgtMass), fit ? 1 : 0, mat);
@@ -54,6 +83,9 @@ int Cpptraj::B200::Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask,
     err = b200_rms2d_full(tgt.RawFrames(), tgt.FrameStride(), (int)tgt.Size(), &tgtMask.Selected()[0],
                           ref.RawFrames(), ref.FrameStride(), (int)ref.Size(), &refMask.Selected()[0],
                           tgtMask.Nselected(), ptr_or_null(tgtMass), ptr_or_null(refMass), fit ? 1 : 0, mat);
+  t_call.Stop();
+  if (!err) mprintf("\tB200 RMSD path: %zu x %zu frames, %i atoms: %.4f s in the library.\n", tgt.Size(), ref.Size(),
+                    tgtMask.Nselected(), t_call.Total());
   return err ? b200_err("rms2d") : 0;
 }
 

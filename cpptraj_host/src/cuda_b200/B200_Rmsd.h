@@ -19,6 +19,8 @@ namespace Cluster { class Cframes; }
 namespace B200 {
 /// One-time device probe (pattern of Cpptraj.cpp:120-135). CPPTRAJ_B200_NGPU limits the device count. \return 0 if OK.
 int Init();
+/// Start the device probe on a background thread (from a command's Setup()/Init(), before trajectory processing); Init() joins it.
+void InitAsync();
 /// Per-selected-atom masses of a Frame set up with SetupFrameFromMask (Frame.cpp:502-512).
 std::vector<double> MassesOf(Frame const&);
 /** rms2d (Analysis_Rms2d::Calculate_2D, Analysis_Rms2d.cpp:196-295). \a out must already be allocated by the caller
