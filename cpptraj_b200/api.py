@@ -19,7 +19,8 @@ class Stats(C.Structure):
     _fields_ = [("pack_ms", C.c_double), ("pair_ms", C.c_double), ("onevn_ms", C.c_double),
                 ("pack_launches", C.c_long), ("pair_launches", C.c_long), ("onevn_launches", C.c_long),
                 ("pairs", C.c_double), ("frames_1vN", C.c_double), ("h2d_bytes", C.c_double),
-                ("d2h_bytes", C.c_double), ("kernel_launches", C.c_long)]
+                ("d2h_bytes", C.c_double), ("kernel_launches", C.c_long),
+                ("onevn_stream_ms", C.c_double), ("onevn_stream_launches", C.c_long)]
 
 
 _lib = None

@@ -150,6 +150,8 @@ std::mutex g_statMu;
 b200_stats g_stats = {};
 bool g_profiling = false;
 std::atomic<long> g_launches{0};
+struct Timer;
+
 #define COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
 
 struct EventPair {
@@ -180,6 +182,12 @@ struct Timer {  // collects (start,stop) events; resolved after a sync
     return ms;
   }
 };
+
+// CUDA events around the streaming kernel of the one-vs-many path alone (the dominant kernel of that path); resolved by
+// b200_get_stats after a device synchronisation.
+std::mutex g_streamMu;
+Timer g_streamTimer;
+long g_streamLaunches = 0;
 
 bool host_ptr_is_pinned(const void* p) {
   cudaPointerAttributes at;
@@ -1208,8 +1216,28 @@ int b200_shard_rows(int nFrames, int shardRank, int shardCount, int* row0, int* 
 
 void b200_set_profiling(int on) { g_profiling = (on != 0); }
 int b200_set_mma_variant(int v) { if (v < 0 || v > 3) return fail(B200_ERR_ARG, "variant must be 0..3"); g_variant.store(v); return B200_OK; }
-void b200_reset_stats(void) { std::lock_guard<std::mutex> lk(g_statMu); g_stats = b200_stats(); g_launches.store(0); }
-void b200_get_stats(b200_stats* out) { if (!out) return; std::lock_guard<std::mutex> lk(g_statMu); *out = g_stats; out->kernel_launches = g_launches.load(); }
+void b200_reset_stats(void) {
+  { std::lock_guard<std::mutex> tl(g_streamMu); if (!g_streamTimer.ev.empty()) { cudaDeviceSynchronize(); g_streamTimer.resolve(); } g_streamLaunches = 0; }
+  std::lock_guard<std::mutex> lk(g_statMu);
+  g_stats = b200_stats();
+  g_launches.store(0);
+}
+void b200_get_stats(b200_stats* out) {
+  if (!out) return;
+  {
+    std::lock_guard<std::mutex> tl(g_streamMu);
+    if (!g_streamTimer.ev.empty()) {
+      cudaDeviceSynchronize();   // (the one-vs-many kernels run on the current device's streams)
+      const double ms = g_streamTimer.resolve();
+      std::lock_guard<std::mutex> lk(g_statMu);
+      g_stats.onevn_stream_ms += ms; g_stats.onevn_stream_launches += g_streamLaunches;
+      g_streamLaunches = 0;
+    }
+  }
+  std::lock_guard<std::mutex> lk(g_statMu);
+  *out = g_stats;
+  out->kernel_launches = g_launches.load();
+}
 
 int b200_rms2d_tri_shard(const float* crd, size_t frameStrideFloats, int nFramesTotal, const int* frameIdx, int nFrames,
                          const int* atomIdx, int nAtoms, const double* mass, int fit, int shardRank, int shardCount,
@@ -1485,45 +1513,80 @@ static int onevn_grow(b200_1vN* h, OneVNLane& L, long need) {
   return B200_OK;
 }
 
-/// Launches the one-vs-many kernels for `nFrames` frames at d_crd on stream st: chunk table, TMA streaming kernel +
+/// Launches the one-vs-many kernels for `nFrames` frames at d_crd on stream st: chunk table, a TMA streaming kernel +
 /// per-frame finish (sorted selections, 16-byte aligned base), then the general gather kernel, which returns at once
-/// when the streaming variant did the work (the choice is made on the device: no host round trip).
+/// when a streaming variant did the work (the choice is made on the device: no host round trip).
+/// Fitted RMSD of a dense enough selection: streaming variant 2 (chunk-major, partial records per frame and part);
+/// no-fit, or selections so sparse that the partial records would rival the frame data: variant 1.
+/// refw: 4 N doubles (rx, ry, rz, m) followed by 4 N doubles (m rx, m ry, m rz, m), as onevn_setup_kernel writes them.
 /// ws: workspace of at least onevn_ws_bytes() bytes.
+static size_t onevn_max_chunks(size_t stride, int chunkAtoms) { return std::min<size_t>(stride / 3 / (size_t)chunkAtoms + 2, 1u << 20); }
+template <typename T>
+static bool onevn_use_v2(size_t stride, int nAtoms, int fit) {
+  if (!fit) return false;
+  if (const char* e = getenv("B200_1VN_V2")) return atoi(e) != 0;
+  const size_t parts = 2 * onevn_max_chunks(stride, ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T)));
+  return parts * 128 <= (size_t)nAtoms * 3 * sizeof(T) / 2 && parts <= 256;   // partial records (128 B each) <= half the bytes read per frame
+}
 static size_t onevn_ws_bytes(size_t stride, int nFrames) {
-  const size_t maxChunks = stride / 3 / (ONEVN_S_CHUNK_BYTES / 24) + 2;   // (double frames: the smaller chunk)
-  return 64 + (maxChunks + 1) * sizeof(int) + 64 + (size_t)nFrames * ONEVN_REC * sizeof(double);
+  const size_t maxChunks = onevn_max_chunks(stride, ONEVN2_CHUNK_BYTES / 24);   // (double frames: the smaller chunk)
+  const size_t head = 64 + (maxChunks + 1) * sizeof(int) + 64 + 8 * maxChunks * sizeof(double) + 64;
+  // variant 2 is only chosen when its 2 * maxChunks records per frame stay small (onevn_use_v2): bound them by 256 parts
+  const size_t parts = std::min<size_t>(2 * maxChunks, 256);
+  return head + (size_t)nFrames * std::max<size_t>(ONEVN_REC, parts * 16) * sizeof(double);
 }
 template <typename T>
 static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, int nAtoms,
                      const double* refw, const double* refsum, int fit, double* rmsd, double* rot, double* trans,
                      void* ws, cudaStream_t st, const int* d_frameIdx = nullptr, long srcBase = 0) {
-  constexpr int APC = ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));
-  const int maxChunks = (int)std::min<size_t>(stride / 3 / APC + 2, 1u << 20);
+  const bool v2 = onevn_use_v2<T>(stride, nAtoms, fit);
+  const int APC = v2 ? ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T)) : ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));
+  const int maxChunks = (int)onevn_max_chunks(stride, APC);
   int* hdr = (int*)ws;
   int* kLo = hdr + 16;
-  double* rec = (double*)((char*)ws + ((64 + (size_t)(maxChunks + 1) * sizeof(int) + 63) & ~(size_t)63));
+  double* partSum = (double*)((char*)ws + ((64 + (size_t)(maxChunks + 1) * sizeof(int) + 63) & ~(size_t)63));
+  double* rec = partSum + 8 * (size_t)maxChunks + 8;
   const bool aligned = (((uintptr_t)d_crd) & 15) == 0;
   const char* env = getenv("B200_1VN_STREAM");
   const bool stream = aligned && !(env && atoi(env) == 0);
   if (stream) {
-    static std::atomic<bool> attr[64][2];
+    static std::atomic<bool> attr[64][4];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (!attr[dev & 63][sizeof(T) == 8].load(std::memory_order_acquire)) {
-      CU(cudaFuncSetAttribute(onevn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONEVN_S_SMEM_BYTES));
-      attr[dev & 63][sizeof(T) == 8].store(true, std::memory_order_release);
+    const int slot = (sizeof(T) == 8 ? 1 : 0) + (v2 ? 2 : 0);
+    if (!attr[dev & 63][slot].load(std::memory_order_acquire)) {
+      if (v2) CU(cudaFuncSetAttribute(onevn_stream2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONEVN2_SMEM_BYTES));
+      else CU(cudaFuncSetAttribute(onevn_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, ONEVN_S_SMEM_BYTES));
+      attr[dev & 63][slot].store(true, std::memory_order_release);
     }
     COUNT_LAUNCH();
     onevn_chunks_kernel<<<1, 256, 0, st>>>(d_atomIdx, nAtoms, APC, maxChunks, hdr, kLo);
-    OneVNStreamArgs sa;
-    sa.crd = d_crd; sa.stride = stride; sa.frameIdx = d_frameIdx; sa.srcBase = srcBase; sa.nFrames = nFrames;
-    sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms;
-    sa.refw = refw; sa.hdr = hdr; sa.kLo = kLo; sa.fit = fit; sa.rec = rec;
-    const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
-    COUNT_LAUNCH();
-    onevn_stream_kernel<T><<<std::min(nGroups, numSMs > 0 ? numSMs : 148), ONEVN_S_THREADS, ONEVN_S_SMEM_BYTES, st>>>(sa);
-    COUNT_LAUNCH();
-    onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
+    const int sms = numSMs > 0 ? numSMs : 148;
+    if (v2) {
+      COUNT_LAUNCH();
+      onevn_parts_kernel<<<1, 256, 0, st>>>(refw + (size_t)4 * nAtoms, hdr, kLo, partSum);
+      OneVN2Args sa;
+      sa.crd = d_crd; sa.stride = stride; sa.frameIdx = d_frameIdx; sa.srcBase = srcBase; sa.nFrames = nFrames;
+      sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms; sa.refmw = refw + (size_t)4 * nAtoms; sa.hdr = hdr; sa.kLo = kLo; sa.rec = rec;
+      COUNT_LAUNCH();
+      { std::lock_guard<std::mutex> tl(g_streamMu); if (g_streamTimer.begin(st)) ++g_streamLaunches; }
+      onevn_stream2_kernel<T><<<std::max(sms, maxChunks), ONEVN2_THREADS, ONEVN2_SMEM_BYTES, st>>>(sa);
+      { std::lock_guard<std::mutex> tl(g_streamMu); g_streamTimer.end(st); }
+      COUNT_LAUNCH();
+      onevn_finish2_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, kLo, partSum, nFrames, refsum, rmsd, rot, trans);
+    } else {
+      OneVNStreamArgs sa;
+      sa.crd = d_crd; sa.stride = stride; sa.frameIdx = d_frameIdx; sa.srcBase = srcBase; sa.nFrames = nFrames;
+      sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms;
+      sa.refw = refw; sa.hdr = hdr; sa.kLo = kLo; sa.fit = fit; sa.rec = rec;
+      const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
+      COUNT_LAUNCH();
+      { std::lock_guard<std::mutex> tl(g_streamMu); if (g_streamTimer.begin(st)) ++g_streamLaunches; }
+      onevn_stream_kernel<T><<<std::min(nGroups, sms), ONEVN_S_THREADS, ONEVN_S_SMEM_BYTES, st>>>(sa);
+      { std::lock_guard<std::mutex> tl(g_streamMu); g_streamTimer.end(st); }
+      COUNT_LAUNCH();
+      onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
+    }
   }
   OneVNArgs a;
   a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = nFrames;
@@ -1560,7 +1623,7 @@ static int onevn_load_ref(b200_1vN* h, const double* refSelected) {
     if ((rc = upload_vec(L.ref, refSelected, (size_t)3 * h->nAtoms, L.st))) return rc;
     COUNT_LAUNCH();
     onevn_setup_kernel<<<1, 256, 0, L.st>>>((const double*)L.ref.p, h->hasMass ? (const double*)L.mass.p : nullptr, h->nAtoms,
-                                           (double*)L.refw.p, (double*)L.refsum.p);
+                                           (double*)L.refw.p, (double*)L.refsum.p, (double*)L.refw.p + (size_t)4 * h->nAtoms);
     CU(cudaGetLastError());
   }
   // the caller's reference array may change as soon as we return (reftraj / previous): wait for the uploads
@@ -1597,7 +1660,7 @@ int b200_rmsd_1vN_begin(const double* refSelected, const int* atomIdx, int nAtom
       int r;
       if (mass && (r = upload_vec(L.mass, mass, (size_t)nAtoms, L.st))) return r;
       if ((r = upload_vec(L.idx, atomIdx, (size_t)nAtoms, L.st))) return r;
-      if ((r = L.refw.reserve((size_t)nAtoms * 32))) return r;
+      if ((r = L.refw.reserve((size_t)nAtoms * 64))) return r;   // (rx, ry, rz, m) and (m rx, m ry, m rz, m)
       if ((r = L.refsum.reserve(64))) return r;
     }
     return onevn_load_ref(h, refSelected);
@@ -1764,12 +1827,12 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   for (Device& x : g_devs) if (x.id == dev) d = &x;
   if (!d) return fail(B200_ERR_STATE, "current device %d was not initialised by b200_init", dev);
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
+  const size_t refBytes = ((size_t)nAtoms * 64 + 64 + 63) & ~(size_t)63;
   if ((rc = d->onevnWs.reserve(refBytes + onevn_ws_bytes(frameStrideFloats, nFrames)))) return rc;
   double* refw = (double*)d->onevnWs.p;
-  double* refsum = refw + (size_t)4 * nAtoms;
+  double* refsum = refw + (size_t)8 * nAtoms;
   COUNT_LAUNCH();
-  onevn_setup_kernel<<<1, 256, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum);
+  onevn_setup_kernel<<<1, 256, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum, refw + (size_t)4 * nAtoms);
   Timer t;
   if (g_profiling) t.begin(st);
   rc = onevn_run<float>(d->numSMs, d_crd, frameStrideFloats, nFrames, d_atomIdx, nAtoms, refw, refsum, fit ? 1 : 0, d_rmsdOut,
@@ -1881,19 +1944,20 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
   }
   if (!contracted) {
     // ---- K streaming passes
-    const size_t refBytes = ((size_t)nAtoms * 32 + 64 + 63) & ~(size_t)63;
+    const size_t refBytes = ((size_t)nAtoms * 64 + 64 + 63) & ~(size_t)63;
     const size_t wsBytes = (onevn_ws_bytes(width, nP) + 63) & ~(size_t)63;
     const size_t distBytes = (size_t)K * (size_t)nP * sizeof(double);
     if ((rc = d.onevnWs.reserve(refBytes + wsBytes + distBytes))) return rc;
     char* base = (char*)d.onevnWs.p;
     double* refw = (double*)base;
-    double* refsum = refw + (size_t)4 * nAtoms;
+    double* refsum = refw + (size_t)8 * nAtoms;
     void* ws = base + refBytes;
     double* dist = (double*)(base + refBytes + wsBytes);
     t.begin(st);
     for (int k = 0; k < K; ++k) {
       COUNT_LAUNCH();
-      onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum);
+      onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum,
+                                            refw + (size_t)4 * nAtoms);
       if ((rc = onevn_run<float>(d.numSMs, d_list0, width, nP, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
                                  dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, rowBase))) return rc;
     }

@@ -190,9 +190,6 @@ __global__ void __launch_bounds__(256) i8_quant_kernel(I8QuantArgs a) {
 // ----------------------------------------------------------------------------
 // tcgen05 / TMEM helpers
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 template <int CG>

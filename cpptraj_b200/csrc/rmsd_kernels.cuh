@@ -68,6 +68,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 /// Blocks until the phase with the given parity has completed.  The suspend-time hint lets the hardware park the
 /// thread until the phase completes instead of returning early: without it the retry loop of ~700 waiting threads
 /// took ~40 % of the issue slots of the tcgen05 pair kernel (ncu: SYNCS + BRA + YIELD).
@@ -888,6 +891,268 @@ __global__ void __launch_bounds__(128) onevn_finish_kernel(const double* rec, co
   }
 }
 
+// ----------------------------------------------------------------------------
+// One-vs-many, streaming variant 2 ("chunk-major"), fitted RMSD only.
+// What bounded variant 1 (ncu, profiles/r1e_onevn_stream_kernel_ncu_details.csv: 0.41 of HBM, issue 47 %, nothing
+// saturated): every (4 frames x 1024 atoms) step re-staged the chunk's reference atoms and atom numbers (36 KB next to
+// 48 KB of frame data, six bulk copies of ~225 TMA-issue cycles each), ran a 512-thread reduction with two CTA-wide
+// barriers, and only one of its two 84 KB stages was ever in flight.
+// Here a CTA owns ONE 1024-atom chunk of the selection for its whole life: the chunk's reference (pre-multiplied by
+// the masses) and atom numbers are loaded into shared memory once; what streams through a 6-deep mbarrier ring is
+// frame data only: one stage = the chunk's span of two frames (2 x 12 KB, two bulk copies issued by a producer warp).
+// Two consumer warps per stage (one per half of the chunk's selected atoms) accumulate 13 FP64 sums for both frames
+// relative to a local origin (the chunk's first atom of each frame, read from the stage itself), reduce them inside
+// the warp and write one 16-double partial record per (frame, part); no CTA-wide barrier in the steady state.
+// onevn_finish2_kernel (one thread per frame) shifts the partial sums to a common origin, adds them up and solves.
+// Grid: nChunks x floor(SMs / nChunks) CTAs; CTA (c, k) takes frame pairs k, k + P, k + 2P, ...
+// ----------------------------------------------------------------------------
+constexpr int ONEVN2_CHUNK_BYTES = 12288;                        // per frame and stage: 1024 float atoms / 512 double atoms
+constexpr int ONEVN2_MAX_APC = ONEVN2_CHUNK_BYTES / 12;          // 1024
+constexpr int ONEVN2_FR = 2;                                     // frames per stage
+constexpr int ONEVN2_BUF_BYTES = ONEVN2_CHUNK_BYTES + 32;        // + alignment slack at both ends
+#ifndef B200_ONEVN2_STAGES
+#define B200_ONEVN2_STAGES 6
+#endif
+#ifndef B200_ONEVN2_UNROLL
+#define B200_ONEVN2_UNROLL 2   // (+3 % over 1; 7 stages and an integer-pipe float->double conversion measured no better / worse)
+#endif
+#ifndef B200_ONEVN2_ICVT
+#define B200_ONEVN2_ICVT 0
+#endif
+constexpr int ONEVN2_STAGES = B200_ONEVN2_STAGES;
+constexpr int ONEVN2_UNROLL = B200_ONEVN2_UNROLL;
+constexpr int ONEVN2_STAGE_BYTES = ONEVN2_FR * ONEVN2_BUF_BYTES;
+constexpr int ONEVN2_REF_BYTES = ONEVN2_MAX_APC * 32;            // (m rx, m ry, m rz, m) of the chunk's selected atoms
+constexpr int ONEVN2_IDX_BYTES = ONEVN2_MAX_APC * 4 + 32;
+constexpr int ONEVN2_SMEM_BYTES = ONEVN2_REF_BYTES + ONEVN2_IDX_BYTES + ONEVN2_STAGES * ONEVN2_STAGE_BYTES + 128;
+constexpr int ONEVN2_CONSUMERS = 2 * ONEVN2_STAGES;             // warps: two per stage
+constexpr int ONEVN2_THREADS = 32 * (ONEVN2_CONSUMERS + 1);     // + the producer warp
+
+struct OneVN2Args {
+  const void* crd;
+  size_t stride;            // elements per frame
+  const int* frameIdx;      // nullable: frame n is row frameIdx[n] - srcBase of crd
+  long srcBase;
+  int nFrames;
+  const int* atomIdx;       // nullable (identity)
+  int nAtoms;
+  const double* refmw;      // 4 doubles per selected atom: m rx, m ry, m rz, m
+  const int* hdr;           // [0] first atom of the span, [1] chunks per frame, [2] 1 = selection sorted (usable)
+  const int* kLo;           // [chunks + 1]: first selected-atom index of every chunk
+  double* rec;              // 16 doubles per (frame, part): 13 sums + the local origin; part = 2 * chunk + half
+};
+
+/// float -> double on the integer pipe (exponent rebias, mantissa shift): the conversion pipe moves 16 lanes/clk/SM, a
+/// third of what the streaming kernel needs at HBM speed.  Exact for zero and normal numbers; denormal floats
+/// (|x| < 1.2e-38, never a coordinate) are flushed to zero.
+__device__ __forceinline__ double onevn2_cvt(float v) {
+#if B200_ONEVN2_ICVT
+  const unsigned int u = __float_as_uint(v);
+  const unsigned int ex = (u >> 23) & 0xffu;
+  const unsigned int hi = (u & 0x80000000u) | (((ex + 896u) << 20) | ((u & 0x007fffffu) >> 3));
+  return ex == 0u ? __hiloint2double((int)(u & 0x80000000u), 0) : __hiloint2double((int)hi, (int)(u << 29));
+#else
+  return (double)v;
+#endif
+}
+__device__ __forceinline__ double onevn2_cvt(double v) { return v; }
+
+template <typename T>
+__global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2Args a) {
+  if (a.hdr[2] == 0) return;   // selection not sorted: onevn_kernel (launched later) does the work
+  constexpr int APC = ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T));
+  extern __shared__ __align__(128) unsigned char smem_o2[];
+  double4* sref = reinterpret_cast<double4*>(smem_o2);
+  unsigned char* sidxRaw = smem_o2 + ONEVN2_REF_BYTES;
+  unsigned char* ring = sidxRaw + ONEVN2_IDX_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + ONEVN2_STAGES * ONEVN2_STAGE_BYTES);
+  uint64_t* empty = full + ONEVN2_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int a0 = a.hdr[0], nCh = a.hdr[1];
+  const int P = (int)gridDim.x / nCh;                    // CTAs per chunk (the host sizes the grid as nCh * P)
+  if ((int)blockIdx.x >= nCh * P) return;
+  const int c = (int)blockIdx.x % nCh, k = (int)blockIdx.x / nCh;
+  const int nPairs = (a.nFrames + ONEVN2_FR - 1) / ONEVN2_FR;
+  const int myPairs = k < nPairs ? (nPairs - 1 - k) / P + 1 : 0;
+  const int kA = a.kLo[c], nSel = a.kLo[c + 1] - kA;
+  const int chunkA0 = a0 + c * APC;
+  const int lastAtom = a.atomIdx ? a.atomIdx[a.nAtoms - 1] : a.nAtoms - 1;
+  const int nAt = min(APC, lastAtom - chunkA0 + 1);      // atoms of the span covered by this chunk
+  if (tid == 0) {
+    for (int s = 0; s < ONEVN2_STAGES; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 2); }
+    mbar_fence_init();
+  }
+  // the chunk's reference atoms and atom numbers: resident for the life of the CTA
+  for (int i = tid; i < nSel; i += ONEVN2_THREADS) {
+    sref[i] = reinterpret_cast<const double4*>(a.refmw)[kA + i];
+    if (a.atomIdx) reinterpret_cast<int*>(sidxRaw)[i] = a.atomIdx[kA + i] - chunkA0;
+  }
+  __syncthreads();
+  if (nSel <= 0 || myPairs <= 0) return;
+  const int* sidx = reinterpret_cast<const int*>(sidxRaw);
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(a.crd);
+
+  if (warp == ONEVN2_CONSUMERS) {
+    // ===================== producer: lanes 0 and 1 copy one frame's chunk each =====================
+    for (int n = 0; n < myPairs; ++n) {
+      const int st = n % ONEVN2_STAGES;
+      mbar_wait(smem_u32(&empty[st]), (uint32_t)(((n / ONEVN2_STAGES) & 1) ^ 1));
+      unsigned char* sbuf = ring + st * ONEVN2_STAGE_BYTES;
+      uint32_t bytes = 0, len = 0;
+      const unsigned char* src = nullptr;
+      if (lane < ONEVN2_FR) {
+        const int fr = min((k + n * P) * ONEVN2_FR + lane, a.nFrames - 1);
+        const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+        const size_t off = (row * a.stride + (size_t)3 * (size_t)chunkA0) * sizeof(T);
+        const size_t s0 = off & ~(size_t)15;
+        len = (uint32_t)(off - s0) + (uint32_t)nAt * 3u * (uint32_t)sizeof(T);
+        src = base + s0;
+        bytes = len & ~15u;
+        unsigned char* dst = sbuf + lane * ONEVN2_BUF_BYTES;
+        for (uint32_t t = bytes; t < len; t += 4)   // tail below a 16-byte boundary: whole 4-byte words, ordinary loads
+          *reinterpret_cast<uint32_t*>(dst + t) = *reinterpret_cast<const uint32_t*>(src + t);
+      }
+      uint32_t tot = bytes + __shfl_xor_sync(0xffffffffu, bytes, 1);
+      const uint32_t bar = smem_u32(&full[st]);
+      __syncwarp();                                  // (the tail stores precede the arrive that publishes the stage)
+      if (lane == 0) mbar_expect_tx(bar, tot);
+      __syncwarp();
+      if (lane < ONEVN2_FR && bytes) bulk_g2s(smem_u32(sbuf + lane * ONEVN2_BUF_BYTES), src, bytes, bar);
+      __syncwarp();
+    }
+    return;
+  }
+  // ===================== consumers: warp w works on stage w / 2, half w % 2 of the chunk's selected atoms =====================
+  const int h = warp & 1, myStage = warp >> 1;
+  const int half0 = (nSel + 1) / 2;
+  const int kBeg = h ? half0 : 0, kEnd = h ? nSel : half0;
+  const int part = 2 * c + h;
+  const int nParts = 2 * nCh;
+  for (int n = myStage; n < myPairs; n += ONEVN2_STAGES) {
+    const int st = myStage;   // (n % STAGES == myStage by construction)
+    mbar_wait(smem_u32(&full[st]), (uint32_t)((n / ONEVN2_STAGES) & 1));
+    const unsigned char* sbuf = ring + st * ONEVN2_STAGE_BYTES;
+    const int f0 = (k + n * P) * ONEVN2_FR;
+    const T* fp[ONEVN2_FR];
+    double o[ONEVN2_FR][3];
+#pragma unroll
+    for (int f = 0; f < ONEVN2_FR; ++f) {
+      const int fr = min(f0 + f, a.nFrames - 1);
+      const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
+      const size_t off = (row * a.stride + (size_t)3 * (size_t)chunkA0) * sizeof(T);
+      fp[f] = reinterpret_cast<const T*>(sbuf + f * ONEVN2_BUF_BYTES + (off & 15));
+      // local origin: the first selected atom of this part (keeps the sums small, costs no global read)
+      const int at0 = a.atomIdx ? sidx[kBeg < kEnd ? kBeg : 0] : (kA + kBeg - chunkA0);
+      o[f][0] = onevn2_cvt(fp[f][3 * at0]); o[f][1] = onevn2_cvt(fp[f][3 * at0 + 1]); o[f][2] = onevn2_cvt(fp[f][3 * at0 + 2]);
+    }
+    double acc[ONEVN2_FR][13];
+#pragma unroll
+    for (int f = 0; f < ONEVN2_FR; ++f)
+#pragma unroll
+      for (int x = 0; x < 13; ++x) acc[f][x] = 0.0;
+#pragma unroll ONEVN2_UNROLL
+    for (int kk = kBeg + lane; kk < kEnd; kk += 32) {
+      const int at = a.atomIdx ? sidx[kk] : (kA + kk - chunkA0);
+      const double4 rw = sref[kk];
+#pragma unroll
+      for (int f = 0; f < ONEVN2_FR; ++f) {
+        const T* p = fp[f] + 3 * at;
+        const double x = onevn2_cvt(p[0]) - o[f][0], y = onevn2_cvt(p[1]) - o[f][1], z = onevn2_cvt(p[2]) - o[f][2];
+        acc[f][0] = fma(x, rw.x, acc[f][0]); acc[f][1] = fma(x, rw.y, acc[f][1]); acc[f][2] = fma(x, rw.z, acc[f][2]);
+        acc[f][3] = fma(y, rw.x, acc[f][3]); acc[f][4] = fma(y, rw.y, acc[f][4]); acc[f][5] = fma(y, rw.z, acc[f][5]);
+        acc[f][6] = fma(z, rw.x, acc[f][6]); acc[f][7] = fma(z, rw.y, acc[f][7]); acc[f][8] = fma(z, rw.z, acc[f][8]);
+        acc[f][9] = fma(x, rw.w, acc[f][9]); acc[f][10] = fma(y, rw.w, acc[f][10]); acc[f][11] = fma(z, rw.w, acc[f][11]);
+        acc[f][12] = fma(rw.w, fma(x, x, fma(y, y, z * z)), acc[f][12]);
+      }
+    }
+    // the stage's bytes have been consumed: hand it back before the reduction
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty[st]));
+#pragma unroll
+    for (int f = 0; f < ONEVN2_FR; ++f) {
+      const int fr = f0 + f;
+      double mine = 0.0;      // lane x keeps sum x (x < 13), lanes 13..15 the origin
+#pragma unroll
+      for (int x = 0; x < 13; ++x) {
+        const double v = warp_sum(acc[f][x]);
+        if (lane == x) mine = v;
+      }
+      if (lane >= 13 && lane < 16) mine = o[f][lane - 13];
+      if (fr < a.nFrames && lane < 16) a.rec[((size_t)fr * nParts + part) * 16 + lane] = mine;
+    }
+  }
+}
+
+/// Per-part constants of the reference for onevn_finish2_kernel: partSum[p] = (sum m rx, sum m ry, sum m rz, sum m)
+/// over the selected atoms of part p = 2 * chunk + half.  One block.
+__global__ void __launch_bounds__(256) onevn_parts_kernel(const double* refmw, const int* hdr, const int* kLo, double* partSum) {
+  if (hdr[2] == 0) return;
+  const int nParts = 2 * hdr[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int p = warp; p < nParts; p += nw) {
+    const int c = p >> 1, h = p & 1;
+    const int kA = kLo[c], nSel = kLo[c + 1] - kA, half0 = (nSel + 1) / 2;
+    const int kb = kA + (h ? half0 : 0), ke = kA + (h ? nSel : half0);
+    double s0 = 0, s1 = 0, s2 = 0, sm = 0;
+    for (int k = kb + lane; k < ke; k += 32) {
+      const double4 r = reinterpret_cast<const double4*>(refmw)[k];
+      s0 += r.x; s1 += r.y; s2 += r.z; sm += r.w;
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sm = warp_sum(sm);
+    if (lane == 0) { partSum[4 * p] = s0; partSum[4 * p + 1] = s1; partSum[4 * p + 2] = s2; partSum[4 * p + 3] = sm; }
+  }
+}
+
+/// One thread per frame: the partial records of its parts, shifted to the origin of the first non-empty part and
+/// added up, then the same solve as onevn_finish_kernel.
+__global__ void __launch_bounds__(128) onevn_finish2_kernel(const double* rec, const int* hdr, const int* kLo, const double* partSum,
+                                                            int nFrames, const double* refsum, double* rmsd, double* rot, double* trans) {
+  if (hdr[2] == 0) return;
+  const int fr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (fr >= nFrames) return;
+  const int nParts = 2 * hdr[1];
+  const double M = refsum[3];
+  if (M < 1e-14) { rmsd[fr] = -1.0; return; }   // src/Frame.cpp:1160-1163
+  double v[13];
+#pragma unroll
+  for (int x = 0; x < 13; ++x) v[x] = 0.0;
+  double ox = 0.0, oy = 0.0, oz = 0.0;
+  bool have = false;
+  for (int p = 0; p < nParts; ++p) {
+    {   // parts without selected atoms wrote no (or an empty) record
+      const int nSel = kLo[(p >> 1) + 1] - kLo[p >> 1], half0 = (nSel + 1) / 2;
+      if (((p & 1) ? nSel - half0 : half0) <= 0) continue;
+    }
+    const double mp = partSum[4 * p + 3];
+    const double* r = rec + ((size_t)fr * nParts + p) * 16;
+    if (!have) { ox = r[13]; oy = r[14]; oz = r[15]; have = true; }
+    const double dx = r[13] - ox, dy = r[14] - oy, dz = r[15] - oz;   // x - o* = (x - o_p) + d
+    const double sx = partSum[4 * p], sy = partSum[4 * p + 1], sz = partSum[4 * p + 2];
+    v[0] += r[0] + dx * sx; v[1] += r[1] + dx * sy; v[2] += r[2] + dx * sz;
+    v[3] += r[3] + dy * sx; v[4] += r[4] + dy * sy; v[5] += r[5] + dy * sz;
+    v[6] += r[6] + dz * sx; v[7] += r[7] + dz * sy; v[8] += r[8] + dz * sz;
+    v[9] += r[9] + mp * dx; v[10] += r[10] + mp * dy; v[11] += r[11] + mp * dz;
+    v[12] += r[12] + 2.0 * (dx * r[9] + dy * r[10] + dz * r[11]) + mp * (dx * dx + dy * dy + dz * dz);
+  }
+  const double cx = v[9] / M, cy = v[10] / M, cz = v[11] / M;
+  double S[9];
+  S[0] = v[0] - cx * refsum[0]; S[1] = v[1] - cx * refsum[1]; S[2] = v[2] - cx * refsum[2];
+  S[3] = v[3] - cy * refsum[0]; S[4] = v[4] - cy * refsum[1]; S[5] = v[5] - cy * refsum[2];
+  S[6] = v[6] - cz * refsum[0]; S[7] = v[7] - cz * refsum[1]; S[8] = v[8] - cz * refsum[2];
+  const double gt = v[12] - M * (cx * cx + cy * cy + cz * cz);
+  const double e0 = 0.5 * (gt + refsum[4]);
+  const Quartic q = quartic_of(S);
+  const double lam = largest_root(q, e0, S);
+  const double e = e0 - lam;
+  rmsd[fr] = (e < 0.0) ? 0.0 : sqrt(2.0 * e / M);
+  if (rot) rotation_from_cov(S, lam, rot + 9 * (size_t)fr);
+  if (trans) {
+    trans[3 * (size_t)fr] = -(cx + ox);
+    trans[3 * (size_t)fr + 1] = -(cy + oy);
+    trans[3 * (size_t)fr + 2] = -(cz + oz);
+  }
+}
+
 /// Frame-to-centroid distances: dist[k * nFrames + f] (one column per centroid, as the one-vs-many passes wrote them)
 /// -> nearest centroid per frame (first minimum wins, as List::AddFramesByCentroid's `dist < mindist`,
 /// src/Cluster/List.cpp:183-189) and, optionally, the frame-major table distOut[f * K + k].
@@ -926,13 +1191,15 @@ __global__ void __launch_bounds__(256) centroid_argmin_rows_kernel(const float* 
 }
 
 /// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One block.
-__global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum) {
+__global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum,
+                                                          double* refmw = nullptr) {
   __shared__ double part[8][5];
   double s0 = 0, s1 = 0, s2 = 0, sm = 0, sg = 0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const double m = mass ? mass[k] : 1.0;
     const double x = ref[3 * k], y = ref[3 * k + 1], z = ref[3 * k + 2];
     refw[4 * k] = x; refw[4 * k + 1] = y; refw[4 * k + 2] = z; refw[4 * k + 3] = m;
+    if (refmw) { refmw[4 * k] = m * x; refmw[4 * k + 1] = m * y; refmw[4 * k + 2] = m * z; refmw[4 * k + 3] = m; }   // (streaming variant 2)
     s0 += m * x; s1 += m * y; s2 += m * z; sm += m; sg += m * (x * x + y * y + z * z);
   }
   s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); sm = warp_sum(sm); sg = warp_sum(sg);

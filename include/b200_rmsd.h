@@ -195,6 +195,8 @@ typedef struct b200_stats {
   double h2d_bytes;
   double d2h_bytes;
   long   kernel_launches; /* every kernel this library launched (all kinds)     */
+  double onevn_stream_ms; /* the streaming kernel of the one-vs-many path alone  */
+  long   onevn_stream_launches;
 } b200_stats;
 void b200_set_profiling(int on);
 void b200_reset_stats(void);

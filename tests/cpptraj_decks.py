@@ -54,6 +54,20 @@ crdaction CRD rms R1 first @CA,C,N out crd_rms.dat savematrices matricesout crd_
 crdaction CRD rms R2 first :2-12@CA nofit mass out crd_rms_nofit.dat crdframes 3,90,4
 crdout CRD fitted.crd
 """, [("crd_rms.dat", "table"), ("crd_rmat.dat", "table"), ("crd_rms_nofit.dat", "table"), ("fitted.crd", "crd")]),
+    # src/Action_Align.cpp:96: align (fit + move, no RMSD output) with a move mask and mass weighting
+    "align": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+align :2-12@CA first mass move :1-13
+trajout aligned.crd
+""", [("aligned.crd", "crd")]),
+    # src/Exec_CrdTransform.cpp:75-134: iterative RMS refinement (every iteration fits all frames to a new average)
+    "crdtransform_rmsrefine": ("""noprogress
+parm {D}/tz2.parm7
+loadcrd {D}/tz2.crd name CRD
+crdtransform CRD name REFINED rmsrefine mask @CA rmstol 0.0005
+crdout REFINED refined.crd
+""", [("refined.crd", "crd")]),
     # an action that reads the RMSD data set during trajectory processing (ADVICE r1): filter on the running set
     "rmsd_filter": ("""noprogress
 parm {D}/tz2.parm7
