@@ -50,6 +50,8 @@ def lib():
     L.b200_rmsd_1vN_set_ref.restype = i
     L.b200_rmsd_build_centroids.argtypes = [vp, sz, i, vp, vp, i, vp, i, vp, i, vp]
     L.b200_rmsd_build_centroids.restype = i
+    L.b200_hieragglo.argtypes = [vp, i, i, i, dbl, vp, vp, vp, C.POINTER(i), C.POINTER(i)]
+    L.b200_hieragglo.restype = i
     L.b200_coords_resident_begin.argtypes = [vp, sz, i, vp, i]
     L.b200_coords_resident_begin.restype = i
     L.b200_coords_resident_end.argtypes = [vp]
@@ -275,6 +277,21 @@ def build_centroids(crd, atom_idx, frame_lists, mass=None, fit=True):
     _check(lib().b200_rmsd_build_centroids(_p(crd), crd.shape[1], crd.shape[0], _p(frames), _p(offsets), len(frame_lists),
                                            _p(sel), len(sel), _p(mass), int(bool(fit)), _p(out)))
     return out
+
+
+def hieragglo(tri, nframes, linkage=1, target_clusters=None, epsilon=None):
+    """Algorithm_HierAgglo::DoClustering on a cache triangle: (mergeInto, mergeFrom, findMin[nCalls]).
+    linkage 0 single / 1 average / 2 complete; None = the reference's defaults (1 cluster, no epsilon)."""
+    tri = _arr(tri, np.float32)
+    assert tri.size == tri_size(nframes)
+    into = np.zeros(max(nframes, 1), np.int32)
+    frm = np.zeros(max(nframes, 1), np.int32)
+    fmin = np.zeros(max(nframes, 1), np.float32)
+    nc, nm = C.c_int(0), C.c_int(0)
+    _check(lib().b200_hieragglo(_p(tri), nframes, linkage, 1 if target_clusters is None else target_clusters,
+                                np.finfo(np.float64).max if epsilon is None else epsilon, _p(into), _p(frm), _p(fmin),
+                                C.byref(nc), C.byref(nm)))
+    return into[:nm.value].copy(), frm[:nm.value].copy(), fmin[:nc.value].copy()
 
 
 def coords_resident_begin(crd, atom_idx):

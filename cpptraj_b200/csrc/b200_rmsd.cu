@@ -7,6 +7,7 @@
 #include "b200_rmsd_debug.h"
 #include "rmsd_kernels.cuh"
 #include "pair_i8.cuh"
+#include "hieragglo.cuh"
 #include "host_util.h"
 
 #include <algorithm>
@@ -89,6 +90,7 @@ struct Device {
   // workspaces (grow-only)
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
   DevBuf imgA, imgB, cenA, cenB, dbgS;   // tcgen05 int8 path: operand images, frame centres
+  DevBuf haD, haS, haMisc;                // hierarchical clustering: cluster-distance triangle, linkage sums, per-cluster state
   PinBuf hostScal;                        // pinned slot for the few scalars read back per call
   int numSMs = 0;
   DevBuf outChunk[NSLOT];
@@ -116,7 +118,7 @@ struct Device {
       inStage[b].release();
     }
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
-                     &imgA, &imgB, &cenA, &cenB, &dbgS};
+                     &imgA, &imgB, &cenA, &cenB, &dbgS, &haD, &haS, &haMisc};
     for (DevBuf* b : all) b->release();
     hostScal.release(); resBuf.release(); resHost = nullptr;
     pool.stop(); poolOut.stop();
@@ -2080,6 +2082,93 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
   {
     std::lock_guard<std::mutex> sl(g_statMu);
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)outBytes;
+  }
+  return B200_OK;
+}
+
+// ---- cluster: hierarchical agglomerative clustering on the cache triangle (hieragglo.cuh)
+int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetClusters, double epsilon,
+                   int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges) {
+  if (!tri || !mergeInto || !mergeFrom || !findMin || !nCalls || !nMerges) return fail(B200_ERR_ARG, "null argument");
+  if (linkage < 0 || linkage > 2) return fail(B200_ERR_ARG, "linkage must be 0 (single), 1 (average) or 2 (complete)");
+  if (nFrames < 0) return fail(B200_ERR_ARG, "nFrames < 0");
+  *nCalls = 0; *nMerges = 0;
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  if (nFrames < 2) return B200_OK;   // nothing to merge
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  const size_t n = (size_t)nFrames, nElt = n * (n - 1) / 2;
+  double h2d = 0.0;
+  if ((rc = d.haD.reserve(nElt * sizeof(float)))) return rc;
+  {   // the triangle as rows of 1 Mi floats (+ a remainder row): pinned -> DMA, pageable -> staged by the copy pool
+    const size_t W = (size_t)1 << 20, rows = nElt / W, rem = nElt - rows * W;
+    const bool pinned = host_ptr_is_pinned(tri);
+    if (rows && (rc = upload_rows(d, (float*)d.haD.p, tri, W, 0, (int)rows, W, pinned, st, &h2d))) return rc;
+    if (rem && (rc = upload_rows(d, (float*)d.haD.p + rows * W, tri + rows * W, rem, 0, 1, rem, pinned, st, &h2d))) return rc;
+  }
+  if (linkage == 1 && (rc = d.haS.reserve(nElt * sizeof(double)))) return rc;
+  // per-cluster state, 256-byte aligned pieces of one allocation
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t off = 0;
+  const size_t oKeys = off;    off += up(n * sizeof(ha_u64));
+  const size_t oClosest = off; off += up(n * sizeof(int));
+  const size_t oCmin = off;    off += up(n * sizeof(float));
+  const size_t oNfr = off;     off += up(n * sizeof(int));
+  const size_t oVnew = off;    off += up(n * sizeof(float));
+  const size_t oOold = off;    off += up(n * sizeof(float));
+  const size_t oSnew = off;    off += up(n * sizeof(double));
+  const size_t oListA = off;   off += up(n * sizeof(int));
+  const size_t oListB = off;   off += up(n * sizeof(int));
+  const size_t oInto = off;    off += up(n * sizeof(int));
+  const size_t oFrom = off;    off += up(n * sizeof(int));
+  const size_t oFind = off;    off += up(n * sizeof(float));
+  const size_t oIgn = off;     off += up(n);
+  const size_t oCtl = off;     off += up(sizeof(HaCtl));
+  if ((rc = d.haMisc.reserve(off))) return rc;
+  char* base = (char*)d.haMisc.p;
+  HaArgs a;
+  a.D = (float*)d.haD.p; a.S = linkage == 1 ? (double*)d.haS.p : nullptr;
+  a.n = nFrames; a.linkage = linkage; a.target = std::max(1, targetClusters); a.eps = epsilon;
+  a.closest = (int*)(base + oClosest); a.cmin = (float*)(base + oCmin); a.ign = (unsigned char*)(base + oIgn);
+  a.nfr = (int*)(base + oNfr); a.vnew = (float*)(base + oVnew); a.snew = (double*)(base + oSnew); a.oold = (float*)(base + oOold);
+  a.listA = (int*)(base + oListA); a.listB = (int*)(base + oListB); a.ctl = (HaCtl*)(base + oCtl);
+  a.mergeInto = (int*)(base + oInto); a.mergeFrom = (int*)(base + oFrom); a.findMin = (float*)(base + oFind);
+  ha_u64* keys = (ha_u64*)(base + oKeys);
+  CU(cudaMemsetAsync(keys, 0xff, n * sizeof(ha_u64), st));
+  const int initGrid = std::min<int>(nFrames - 1, d.numSMs * 8);
+  COUNT_LAUNCH();
+  hieragglo_init_kernel<<<initGrid, 256, 0, st>>>(a.D, nFrames, keys);
+  CU(cudaGetLastError());
+  COUNT_LAUNCH();
+  hieragglo_init2_kernel<<<d.numSMs * 4, 256, 0, st>>>(a, keys, nElt);
+  CU(cudaGetLastError());
+  // one thread-block cluster runs every merge: CTAs per cluster from the cluster count (env B200_HA_TEAM overrides)
+  int team = nFrames < 2048 ? 1 : nFrames < 8192 ? 4 : 8;
+  if (const char* e = getenv("B200_HA_TEAM")) team = std::max(1, std::min(16, atoi(e)));
+  if (team > 8) CU(cudaFuncSetAttribute(hieragglo_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(team); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  COUNT_LAUNCH();
+  CU(cudaLaunchKernelEx(&cfg, hieragglo_kernel, a));
+  HaCtl ctl;
+  CU(cudaMemcpyAsync(&ctl, a.ctl, sizeof(HaCtl), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  *nCalls = ctl.nCalls; *nMerges = ctl.nMerges;
+  if (ctl.nMerges > 0) {
+    CU(cudaMemcpy(mergeInto, a.mergeInto, (size_t)ctl.nMerges * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(mergeFrom, a.mergeFrom, (size_t)ctl.nMerges * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (ctl.nCalls > 0) CU(cudaMemcpy(findMin, a.findMin, (size_t)ctl.nCalls * sizeof(float), cudaMemcpyDeviceToHost));
+  {
+    std::lock_guard<std::mutex> sl(g_statMu);
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)(ctl.nMerges * 8 + ctl.nCalls * 4);
   }
   return B200_OK;
 }

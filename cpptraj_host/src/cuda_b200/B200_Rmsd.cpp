@@ -242,3 +242,24 @@ int Cpptraj::B200::Rmsd1vN::Coords(const float* base, size_t strideFloats, int n
   if (b200_rmsd_1vN_flush(handle_, rmsd, rot, trans, 0)) return b200_err("rmsd flush");
   return 0;
 }
+
+int Cpptraj::B200::HierAgglo(const float* triangle, int nCached, int linkage, int targetClusters, double epsilon,
+                             std::vector<int>& mergeInto, std::vector<int>& mergeFrom, std::vector<float>& findMin)
+{
+  if (Init()) return 1;
+  mergeInto.assign( (size_t)std::max(nCached, 1), 0 );
+  mergeFrom.assign( (size_t)std::max(nCached, 1), 0 );
+  findMin.assign( (size_t)std::max(nCached, 1), 0.0f );
+  int nCalls = 0, nMerges = 0;
+  Timer t_call;
+  t_call.Start();
+  int err = b200_hieragglo(triangle, nCached, linkage, targetClusters, epsilon, &mergeInto[0], &mergeFrom[0], &findMin[0],
+                           &nCalls, &nMerges);
+  t_call.Stop();
+  if (err) return b200_err("hieragglo");
+  mergeInto.resize( (size_t)nMerges );
+  mergeFrom.resize( (size_t)nMerges );
+  findMin.resize( (size_t)nCalls );
+  mprintf("\tB200: %i merges of %i initial clusters on the device in %.4f s.\n", nMerges, nCached, t_call.Total());
+  return 0;
+}

@@ -57,6 +57,14 @@ int CentroidDists(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vect
   */
 int BuildCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
                    std::vector<Cluster::Cframes const*> const& clusterFrames, std::vector<Frame*> const& centroids);
+/** Hierarchical agglomerative clustering on an in-memory pairwise cache (Algorithm_HierAgglo::DoClustering /
+  * MergeClosest, Cluster/Algorithm_HierAgglo.cpp:97-245, with the DynamicMatrix bookkeeping): all merges run on the
+  * device in one launch.  \a triangle: DataSet_PairwiseCache_MEM::Ptr() for \a nCached frames; \a linkage in
+  * Algorithm_HierAgglo::LINKAGETYPE order.  Per MergeClosest call m: \a findMin[m]; for the calls that merged,
+  * \a mergeInto[m] (C1, kept) and \a mergeFrom[m] (C2, removed) as initial-cluster numbers.
+  */
+int HierAgglo(const float* triangle, int nCached, int linkage, int targetClusters, double epsilon,
+              std::vector<int>& mergeInto, std::vector<int>& mergeFrom, std::vector<float>& findMin);
 /** Keeps the selected span of a COORDS set on the device while it exists (Cluster::Control::Run, Cluster/Control.cpp:690-830):
   * the centroid / frame-to-centroid calls of a clustering run then skip the upload.  The frames must not change meanwhile.
   */

@@ -160,6 +160,23 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
                               const int* atomIdx, int nAtoms, const double* mass, int fit,
                               double* centroidsOut);
 
+/* ---- cluster: hierarchical agglomerative clustering on the pairwise cache ---------------------------
+ * The merge loop of Algorithm_HierAgglo::DoClustering / MergeClosest (src/Cluster/Algorithm_HierAgglo.cpp:97-245) with
+ * the Cluster::DynamicMatrix bookkeeping (src/Cluster/DynamicMatrix.h:43-126, DynamicMatrix.cpp:7-33), run on the
+ * device by one thread-block cluster.  tri: the pairwise cache, DataSet_PairwiseCache_MEM::Ptr() (triangle of nFrames
+ * columns, layout above; pageable or pinned); one initial cluster per cached frame, Num() = cache index
+ * (buildInitialClusters, :86-95).  linkage: 0 single, 1 average, 2 complete (LINKAGETYPE,
+ * src/Cluster/Algorithm_HierAgglo.h:35); targetClusters / epsilon: nclusters_ / epsilon_ after DoClustering's defaults
+ * (-1 -> 1, -1.0 -> DBL_MAX).  Outputs (caller-allocated, nFrames entries each): for MergeClosest call m the value
+ * FindMin returned, findMin[m] (what `epsilonplot` prints), and -- for the calls that merged -- the cluster kept,
+ * mergeInto[m] (the lower Num), and the cluster merged into it, mergeFrom[m].  *nCalls = MergeClosest calls made,
+ * *nMerges = merges (nCalls - 1 when the last call stopped on epsilon).  The caller replays the merges on its cluster
+ * list (Node::MergeFrames, List::RemoveCluster).  Which pair merges, ties included, is the reference's choice exactly;
+ * single and complete linkage distances are exact, average-linkage sums are kept in double (see hieragglo.cuh).
+ * Device memory: 4 bytes per pair, 12 for average linkage.  Runs on device 0. */
+int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetClusters, double epsilon,
+                   int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges);
+
 /* ---- device-resident variants (benchmarks, pipelines that keep COORDS in HBM)
  * All pointers are DEVICE pointers on the current device; `stream` is a
  * cudaStream_t (NULL = default stream); asynchronous w.r.t. the host.

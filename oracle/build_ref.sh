@@ -25,6 +25,9 @@ for s in $SRCS; do
     OBJS="$OBJS $OUT/obj/$s.o"
   fi
 done
+# hierarchical clustering bookkeeping (closest-index rules of the cluster distance matrix)
+$CXX $FLAGS -c "$REF/src/Cluster/DynamicMatrix.cpp" -o "$OUT/obj/Cluster_DynamicMatrix.o"
+OBJS="$OBJS $OUT/obj/Cluster_DynamicMatrix.o"
 $CXX $FLAGS -c "$HERE/ref_driver.cpp" -o "$OUT/obj/ref_driver.o"
 $CXX -shared -fopenmp -o "$OUT/libcpptraj_ref_rmsd.so" "$OUT/obj/ref_driver.o" $OBJS -Wl,--no-undefined
 echo "built $OUT/libcpptraj_ref_rmsd.so"

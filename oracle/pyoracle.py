@@ -40,6 +40,27 @@ def tri_index(n, i, j):
     return n * i - (i + 1) * i // 2 + j - i - 1
 
 
+def _hieragglo(fn, tri, n, linkage, target_clusters, epsilon):
+    """Shared wrapper: (mergeInto, mergeFrom, findMin[nCalls]) of Algorithm_HierAgglo::DoClustering on a cache triangle.
+    linkage 0 single / 1 average / 2 complete; target_clusters, epsilon None = the reference's defaults (1, DBL_MAX)."""
+    tri = np.ascontiguousarray(tri, np.float32)
+    assert tri.size == tri_size(n)
+    into = np.zeros(max(n, 1), np.int32)
+    frm = np.zeros(max(n, 1), np.int32)
+    fmin = np.zeros(max(n, 1), np.float32)
+    nc = C.c_int(0)
+    nm = C.c_int(0)
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rc = fn(_ptr(tri), n, linkage, 1 if target_clusters is None else target_clusters,
+            np.finfo(np.float64).max if epsilon is None else epsilon, _ptr(into), _ptr(frm), _ptr(fmin),
+            C.byref(nc), C.byref(nm))
+    if rc:
+        raise RuntimeError("hieragglo checker failed rc=%d" % rc)
+    return into[:nm.value].copy(), frm[:nm.value].copy(), fmin[:nc.value].copy()
+
+
 class _Base:
     def __init__(self, path):
         if not os.path.exists(path):
@@ -84,6 +105,9 @@ class Oracle(_Base):
         if rc:
             raise RuntimeError("oracle failed rc=%d" % rc)
         return out
+
+    def hieragglo(self, tri, n, linkage=1, target_clusters=None, epsilon=None):
+        return _hieragglo(self.lib.orc_hieragglo, tri, n, linkage, target_clusters, epsilon)
 
     def threads(self):
         return self.lib.orc_num_threads()
@@ -166,6 +190,10 @@ class Reference(_Base):
         L.ref_rmsd_1vN.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+
+    def hieragglo(self, tri, n, linkage=1, target_clusters=None, epsilon=None):
+        """The reference's own Cluster::DynamicMatrix driven by ref_driver.cpp's restated merge loop."""
+        return _hieragglo(self.lib.ref_hieragglo, tri, n, linkage, target_clusters, epsilon)
 
     def threads(self):
         return self.lib.ref_num_threads()

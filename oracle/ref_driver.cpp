@@ -30,6 +30,8 @@
 #include "Matrix.h"
 #include "Matrix_3x3.h"
 #include "Vec3.h"
+#include "Cluster/DynamicMatrix.h"
+#include <limits>
 
 namespace {
 
@@ -269,6 +271,59 @@ int ref_build_centroid(const float* crd, size_t stride, int nTotalFrames, int na
   if (nIn > 0) {
     cframe.Divide((double)nIn);
     std::memcpy(cent, cframe.xAddress(), sizeof(double) * 3 * (size_t)n);
+  }
+  return 0;
+}
+
+// Algorithm_HierAgglo::DoClustering / MergeClosest (src/Cluster/Algorithm_HierAgglo.cpp:97-245) driven through the
+// reference's OWN Cluster::DynamicMatrix (src/Cluster/DynamicMatrix.{h,cpp}: SetCdist / Ignore / FindMin with their
+// closest-index bookkeeping) and Matrix<float>.  Restated here: the cluster list (frame vectors, ascending Num) and the
+// frame-pair linkage loops (:248-350) over the cache triangle, because List/Node/MetricArray drag in the DataSet runtime.
+int ref_hieragglo(const float* tri, int n, int linkage, int targetClusters, double epsilon,
+                  int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges)
+{
+  *nCalls = 0; *nMerges = 0;
+  if (n < 2) return 0;
+  Matrix<float> cache;
+  cache.resize(0L, (size_t)n);
+  std::memcpy(cache.Ptr(), tri, sizeof(float) * cache.size());
+  std::vector< std::vector<int> > fl((size_t)n);
+  std::vector<bool> alive((size_t)n, true);
+  for (int i = 0; i < n; i++) fl[i].assign(1, i);
+  struct Link {
+    static double dist(Matrix<float> const& cache, int linkage, std::vector<int> const& c1, std::vector<int> const& c2) {
+      double acc = (linkage == 0) ? std::numeric_limits<double>::max() : (linkage == 2 ? -1.0 : 0.0);
+      for (std::vector<int>::const_iterator a = c1.begin(); a != c1.end(); ++a)
+        for (std::vector<int>::const_iterator b = c2.begin(); b != c2.end(); ++b) {
+          double Dist = cache.element(*a, *b);
+          if (linkage == 0) { if (Dist < acc) acc = Dist; }
+          else if (linkage == 2) { if (Dist > acc) acc = Dist; }
+          else acc += Dist;
+        }
+      if (linkage == 1) return acc / (double)(c1.size() * c2.size());
+      return acc;
+    }
+  };
+  Cpptraj::Cluster::DynamicMatrix CD;
+  CD.SetupMatrix((size_t)n);
+  for (int c1 = 0; c1 < n; c1++)
+    for (int c2 = c1 + 1; c2 < n; c2++)
+      CD.SetCdist(c1, c2, Link::dist(cache, linkage, fl[c1], fl[c2]));
+  int nClusters = n;
+  for (;;) {
+    int C1, C2;
+    double min = CD.FindMin(C1, C2);
+    findMin[(*nCalls)++] = (float)min;
+    if (min > epsilon) break;
+    mergeInto[*nMerges] = C1; mergeFrom[*nMerges] = C2; (*nMerges)++;
+    fl[C1].insert(fl[C1].end(), fl[C2].begin(), fl[C2].end());
+    fl[C2].clear(); alive[C2] = false;
+    nClusters--;
+    CD.Ignore(C2);
+    for (int k = 0; k < n; k++)
+      if (alive[k] && k != C1) CD.SetCdist(C1, k, Link::dist(cache, linkage, fl[C1], fl[k]));
+    if (nClusters <= targetClusters) break;
+    if (nClusters == 1) break;
   }
   return 0;
 }

@@ -478,3 +478,156 @@ void orc_set_threads(int n)
     (void)n;
 #endif
 }
+
+/* ---- (f) rank 3: hierarchical agglomerative clustering on the pairwise cache --------
+ * Restates Algorithm_HierAgglo::DoClustering / MergeClosest
+ * (src/Cluster/Algorithm_HierAgglo.cpp:97-245) with its frame-pair linkage loops
+ * minDist / maxDist / avgDist (:248-298) and calc{Min,Max,Avg}Dist (:303-350), and the
+ * DynamicMatrix bookkeeping they go through (src/Cluster/DynamicMatrix.h:43-126,
+ * src/Cluster/DynamicMatrix.cpp:7-33): float cluster-distance triangle, ignore flags
+ * and the per-cluster "closest" index with its exact update rules (strict '<',
+ * rescan when the closest distance grew, rescan when the closest was ignored).
+ * tri = the pairwise cache (DataSet_PairwiseCache_MEM::Mat_, src/Matrix.h:110-122),
+ * one initial cluster per cached frame, Num() = cache index
+ * (buildInitialClusters, :86-95).  linkage: 0 single, 1 average, 2 complete
+ * (LINKAGETYPE, src/Cluster/Algorithm_HierAgglo.h:35).  targetClusters / epsilon
+ * are nclusters_ / epsilon_ after DoClustering's defaults (-1 -> 1, -1.0 -> DBL_MAX).
+ * Outputs: mergeInto[m] (C1, the lower Num), mergeFrom[m] (C2), findMin[m] = the
+ * value FindMin returned in MergeClosest call m; *nCalls = number of MergeClosest
+ * calls, *nMerges = merges performed (nCalls-1 when the last call stopped on epsilon). */
+typedef struct {
+    int n;
+    float *mat;
+    unsigned char *ignore;
+    int *closest;
+} orc_dynmat;
+
+static size_t orc_tri_idx(int n, int a, int b)
+{   /* src/Matrix.h:110-122 calcTriIndex */
+    if (a > b) { int t = a; a = b; b = t; }
+    return (size_t)n * (size_t)a - ((size_t)a * ((size_t)a + 1)) / 2 + (size_t)b - (size_t)a - 1;
+}
+static float orc_dm_get(const orc_dynmat *M, int a, int b) { return M->mat[orc_tri_idx(M->n, a, b)]; }
+
+/* DynamicMatrix::updateClosestIdx, src/Cluster/DynamicMatrix.h:43-62 */
+static void orc_dm_update_closest(orc_dynmat *M, int idx)
+{
+    M->closest[idx] = -1;
+    float cur = 0;
+    for (int jdx = 0; jdx != M->n; jdx++) {
+        if (!M->ignore[jdx] && idx != jdx) {
+            if (M->closest[idx] == -1) {
+                M->closest[idx] = jdx;
+                cur = orc_dm_get(M, idx, jdx);
+            } else {
+                float fdist = orc_dm_get(M, idx, jdx);
+                if (fdist < cur) { M->closest[idx] = jdx; cur = fdist; }
+            }
+        }
+    }
+}
+/* DynamicMatrix::SetCdist, src/Cluster/DynamicMatrix.h:65-113 */
+static void orc_dm_set(orc_dynmat *M, int col, int row, float val)
+{
+    int update_col = -1, update_row = -1;
+    if (M->closest[col] < 0) M->closest[col] = row;
+    else {
+        float c = orc_dm_get(M, col, M->closest[col]);
+        if (val < c) M->closest[col] = row;
+        else if (row == M->closest[col] && val > c) update_col = col;
+    }
+    if (M->closest[row] < 0) M->closest[row] = col;
+    else {
+        float c = orc_dm_get(M, row, M->closest[row]);
+        if (val < c) M->closest[row] = col;
+        else if (col == M->closest[row] && val > c) update_row = row;
+    }
+    M->mat[orc_tri_idx(M->n, col, row)] = val;
+    if (update_col != -1) orc_dm_update_closest(M, update_col);
+    if (update_row != -1) orc_dm_update_closest(M, update_row);
+}
+/* DynamicMatrix::Ignore, src/Cluster/DynamicMatrix.h:116-126 */
+static void orc_dm_ignore(orc_dynmat *M, int row)
+{
+    M->ignore[row] = 1;
+    for (int idx = 0; idx != M->n; idx++)
+        if (!M->ignore[idx] && M->closest[idx] == row) orc_dm_update_closest(M, idx);
+}
+/* DynamicMatrix::FindMin, src/Cluster/DynamicMatrix.cpp:7-33 */
+static double orc_dm_findmin(const orc_dynmat *M, int *iOut, int *jOut)
+{
+    float currentMin = 3.402823466e+38F;
+    int minRow = -1, minCol = -1;
+    for (int col = 0; col != M->n; col++) {
+        int row = M->closest[col];
+        if (!M->ignore[col] && row >= 0 && !M->ignore[row]) {
+            float mval = orc_dm_get(M, col, row);
+            if (mval < currentMin) { currentMin = mval; minRow = row; minCol = col; }
+        }
+    }
+    if (minRow < minCol) { *iOut = minRow; *jOut = minCol; } else { *iOut = minCol; *jOut = minRow; }
+    return (double)currentMin;
+}
+/* minDist / maxDist / avgDist, src/Cluster/Algorithm_HierAgglo.cpp:248-298: frame-pair loops over the cache
+ * (MetricArray::Frame_Distance -> CachedDistance, src/Cluster/MetricArray.cpp:599-609), C1 frames outer. */
+static double orc_linkage(const float *tri, int n, int linkage, const int *f1, int n1, const int *f2, int n2)
+{
+    double acc = (linkage == 0) ? 1.7976931348623157e308 : (linkage == 2 ? -1.0 : 0.0);
+    for (int a = 0; a < n1; a++)
+        for (int b = 0; b < n2; b++) {
+            double Dist = (double)tri[orc_tri_idx(n, f1[a], f2[b])];
+            if (linkage == 0) { if (Dist < acc) acc = Dist; }
+            else if (linkage == 2) { if (Dist > acc) acc = Dist; }
+            else acc += Dist;
+        }
+    if (linkage == 1) return acc / (double)(n1 * n2);
+    return acc;
+}
+
+int orc_hieragglo(const float *tri, int n, int linkage, int targetClusters, double epsilon,
+                  int *mergeInto, int *mergeFrom, float *findMin, int *nCalls, int *nMerges)
+{
+    *nCalls = 0; *nMerges = 0;
+    if (n < 2) return 0;
+    orc_dynmat M;
+    M.n = n;
+    size_t nElt = (size_t)n * (size_t)(n - 1) / 2;
+    M.mat = (float *)calloc(nElt, sizeof(float));
+    M.ignore = (unsigned char *)calloc((size_t)n, 1);
+    M.closest = (int *)malloc(sizeof(int) * (size_t)n);
+    /* clusters: frame lists (Cframes::Insert appends, src/Cluster/Cframes.h:36) */
+    int **fl = (int **)malloc(sizeof(int *) * (size_t)n);
+    int *nf = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        M.closest[i] = -1;
+        fl[i] = (int *)malloc(sizeof(int)); fl[i][0] = i; nf[i] = 1;
+    }
+    /* initial cluster distance matrix, :119-137 */
+    for (int c1 = 0; c1 < n; c1++)
+        for (int c2 = c1 + 1; c2 < n; c2++)
+            orc_dm_set(&M, c1, c2, (float)orc_linkage(tri, n, linkage, fl[c1], nf[c1], fl[c2], nf[c2]));
+    int nClusters = n;
+    for (;;) {
+        /* MergeClosest, :170-245 */
+        int C1, C2;
+        double min = orc_dm_findmin(&M, &C1, &C2);
+        findMin[*nCalls] = (float)min;
+        (*nCalls)++;
+        if (min > epsilon) break;
+        mergeInto[*nMerges] = C1; mergeFrom[*nMerges] = C2; (*nMerges)++;
+        fl[C1] = (int *)realloc(fl[C1], sizeof(int) * (size_t)(nf[C1] + nf[C2]));
+        memcpy(fl[C1] + nf[C1], fl[C2], sizeof(int) * (size_t)nf[C2]);
+        nf[C1] += nf[C2];
+        free(fl[C2]); fl[C2] = 0; nf[C2] = 0;
+        nClusters--;
+        orc_dm_ignore(&M, C2);
+        for (int k = 0; k < n; k++)   /* cluster list order = ascending Num */
+            if (fl[k] != 0 && k != C1)
+                orc_dm_set(&M, C1, k, (float)orc_linkage(tri, n, linkage, fl[C1], nf[C1], fl[k], nf[k]));
+        if (nClusters <= targetClusters) break;
+        if (nClusters == 1) break;
+    }
+    for (int i = 0; i < n; i++) free(fl[i]);
+    free(fl); free(nf); free(M.mat); free(M.ignore); free(M.closest);
+    return 0;
+}

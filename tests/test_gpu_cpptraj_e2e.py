@@ -160,6 +160,8 @@ def test_cpptraj_deck_matches_unmodified_reference(tmp_path, name):
     r = subprocess.run([BIN, "-i", "in"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-3000:]
     assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    if name == "cluster_hier_linkages":
+        assert r.stdout.count("initial clusters on the device") == 4, "the device merge loop did not run:\n" + r.stdout[-3000:]
     for fname, kind in outs:
         got_p, want_p = str(tmp_path / fname), os.path.join(gold, fname)
         if kind == "table":

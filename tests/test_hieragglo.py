@@ -1,0 +1,121 @@
+"""Hierarchical agglomerative clustering on the pairwise cache.
+
+CPU part: the C restatement (oracle/rmsd_oracle.c: orc_hieragglo) is pinned against the reference's own
+Cluster::DynamicMatrix compiled where it lies (oracle/_ref: ref_hieragglo) -- merge sequence and FindMin values
+identical, ties included.  GPU part (-m gpu): b200_hieragglo through the C ABI against the restatement: which pair
+merges at every step must be identical (integers: bit-exact), FindMin values bit-equal for single / complete linkage
+and for average linkage on these sizes (the sums are exactly representable)."""
+import numpy as np
+import pytest
+
+from oracle.pyoracle import tri_size
+
+
+def cache_from_points(rng, n, dim=3, quant=None, dup=0):
+    """A float32 distance triangle of n random points (row-major upper triangle = calcTriIndex order)."""
+    x = rng.standard_normal((n, dim)) * 3.0
+    for k in range(dup):                       # exact duplicates: zero distances and equal rows
+        x[rng.integers(n)] = x[rng.integers(n)]
+    d = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1))
+    if quant:
+        d = np.round(d * quant) / quant
+    return d[np.triu_indices(n, 1)].astype(np.float32)
+
+
+CASES = [(2, None, 0), (3, None, 0), (17, None, 2), (64, 4, 0), (150, None, 5), (150, 2, 0), (333, 16, 8)]
+
+
+@pytest.mark.parametrize("linkage", [0, 1, 2])
+def test_restatement_matches_reference_dynamicmatrix(oracle, reference, linkage):
+    rng = np.random.default_rng(100 + linkage)
+    for n, quant, dup in CASES:
+        tri = cache_from_points(rng, n, quant=quant, dup=dup)
+        for target, eps in ((None, None), (5, None), (None, 2.5), (3, 1.0)):
+            a = oracle.hieragglo(tri, n, linkage, target, eps)
+            b = reference.hieragglo(tri, n, linkage, target, eps)
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (n, quant, dup, target, eps)
+
+
+def test_restatement_stop_rules(oracle):
+    rng = np.random.default_rng(7)
+    n = 40
+    tri = cache_from_points(rng, n)
+    into, frm, fmin = oracle.hieragglo(tri, n, 1, 10, None)
+    assert len(into) == n - 10 and len(fmin) == n - 10             # target reached: every call merged
+    into, frm, fmin = oracle.hieragglo(tri, n, 1, None, 1.5)
+    assert len(fmin) == len(into) + 1 and fmin[-1] > 1.5            # the last call only reported the minimum
+    assert np.all(fmin[:-1] <= 1.5) and np.all(into < frm)
+    into, frm, fmin = oracle.hieragglo(tri, n, 1, 100, None)        # target above N: one merge is still attempted
+    assert len(into) == 1                                           # (DoClustering :153-160)
+    assert oracle.hieragglo(np.zeros(0, np.float32), 1, 1)[0].size == 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def assert_same(got, want, what):
+    for name, x, y in zip(("mergeInto", "mergeFrom", "findMin"), got, want):
+        assert x.shape == y.shape, (what, name, x.shape, y.shape)
+        if not np.array_equal(x, y):
+            k = int(np.nonzero(x != y)[0][0])
+            raise AssertionError("%s: %s differs first at merge %d: got %r want %r" % (what, name, k, x[k], y[k]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("linkage", [0, 1, 2])
+def test_gpu_matches_restatement(b200, oracle, linkage):
+    rng = np.random.default_rng(200 + linkage)
+    for n, quant, dup in CASES + [(700, None, 3), (700, 8, 0)]:
+        tri = cache_from_points(rng, n, quant=quant, dup=dup)
+        for target, eps in ((None, None), (5, None), (None, 2.5), (3, 1.0), (10 * n, None)):
+            want = oracle.hieragglo(tri, n, linkage, target, eps)
+            got = b200.hieragglo(tri, n, linkage, target, eps)
+            assert_same(got, want, (n, quant, dup, linkage, target, eps))
+
+
+@pytest.mark.gpu
+def test_gpu_cluster_sizes_agree(b200, oracle, monkeypatch):
+    """The merge loop runs in ONE thread-block cluster; every cluster size must give the same merges."""
+    rng = np.random.default_rng(300)
+    n = 1500
+    tri = cache_from_points(rng, n, quant=32, dup=4)
+    for linkage in (0, 1, 2):
+        want = oracle.hieragglo(tri, n, linkage, 4, None)
+        for team in (1, 2, 8, 16):
+            monkeypatch.setenv("B200_HA_TEAM", str(team))
+            got = b200.hieragglo(tri, n, linkage, 4, None)
+            assert_same(got, want, (linkage, team))
+
+
+@pytest.mark.gpu
+def test_gpu_rmsd_cache_end_to_end(b200, oracle):
+    """cluster hieragglo on an RMSD cache filled by the device path: same merges as the restatement on the same cache,
+    and -- the distances being within 1e-4 A of the reference's -- the same final partition as on the reference's cache
+    for well separated conformers."""
+    from cpptraj_b200.synth import _rotations
+    rng = np.random.default_rng(400)
+    nconf, per, na = 6, 40, 60
+    confs = rng.standard_normal((nconf, na, 3)) * 4.0
+    nf = nconf * per
+    R = _rotations(rng, nf)
+    xyz = np.einsum("fij,faj->fai", R, confs[np.arange(nf) % nconf]) + rng.uniform(-10, 10, (nf, 1, 3))
+    xyz += 0.05 * rng.standard_normal(xyz.shape)
+    crd = xyz.reshape(nf, -1).astype(np.float32)
+    sel = np.arange(na, dtype=np.int32)
+    tri = b200.rms2d_tri(crd, sel)
+    tri_ref = oracle.cluster_tri(crd, sel)
+    assert np.abs(tri.astype(np.float64) - tri_ref).max() <= 1e-4
+    for linkage in (0, 1, 2):
+        got = b200.hieragglo(tri, nf, linkage, nconf, None)
+        assert_same(got, oracle.hieragglo(tri, nf, linkage, nconf, None), linkage)
+        lab = partition(got, nf)
+        lab_ref = partition(oracle.hieragglo(tri_ref, nf, linkage, nconf, None), nf)
+        assert np.array_equal(lab, lab_ref)
+        assert all(len(set(lab[np.arange(nf) % nconf == c])) == 1 for c in range(nconf))
+
+
+def partition(merges, n):
+    """Cluster label (lowest member) of every frame after replaying the merges."""
+    parent = np.arange(n)
+    for a, b in zip(merges[0], merges[1]):
+        parent[parent == b] = a
+    return parent
