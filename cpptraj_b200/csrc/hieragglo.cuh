@@ -34,6 +34,8 @@ struct HaCtl {
   int tieCount[2];    // number of k attaining that minimum
   int nA[2], nB[2];   // list lengths: rows to re-scan before / after the update
   int nCalls, nMerges, stopped;
+  long long clk[8];   // leader thread: cycles per phase (findmin, newrow, ignore-rescan, update, post-rescan), summed
+  long long cnt[4];   // rows re-scanned before / after the update, merges whose row minimum was tied
 };
 
 struct HaArgs {
@@ -45,6 +47,7 @@ struct HaArgs {
   unsigned char* ign; int* nfr;     // merged-away flag, frame count
   float* vnew; double* snew; float* oold;   // the merged cluster's new row, its sums, its old row
   int* listA; int* listB;
+  ha_u64* rkey;        // per cluster: (distance, index) minimum of a pending re-scan, ~0 when none
   HaCtl* ctl;
   int* mergeInto; int* mergeFrom; float* findMin;
 };
@@ -84,20 +87,40 @@ __device__ __forceinline__ ha_u64 ha_block_min(ha_u64 k, ha_u64* sm) {
   return sm[32];
 }
 
-/// DynamicMatrix::updateClosestIdx (DynamicMatrix.h:43-62) for row idx by the whole CTA: lowest index among the minima
-/// over the clusters still present.
-__device__ __forceinline__ void ha_rescan_row(const HaArgs& a, int idx, ha_u64* sm) {
-  ha_u64 best = ~0ull;
-  for (int j = threadIdx.x; j < a.n; j += blockDim.x)
-    if (j != idx && !a.ign[j]) {
-      ha_u64 k = ha_key(a.D[ha_idx(a.n, idx, j)], j);
-      best = k < best ? k : best;
+constexpr int HA_U = 4;   // clusters per thread and batch: all loads of a batch are issued before the first use
+
+/// DynamicMatrix::updateClosestIdx (DynamicMatrix.h:43-62) for every row of a list, by the whole team: each thread scans a
+/// strided slice of every listed row (lowest index among the minima over the clusters still present); the minima meet in
+/// rkey[row] (64-bit atomicMin), to be read after the next cluster barrier.
+__device__ __forceinline__ void ha_team_rescan(const HaArgs& a, const int* list, int nList, int tid, int nThr, ha_u64* sm) {
+  const int n = a.n;
+  for (int e = 0; e < nList; ++e) {
+    const int row = list[e];
+    ha_u64 best = ~0ull;
+    for (int j0 = tid; j0 < n; j0 += nThr * HA_U) {
+      float v[HA_U]; unsigned char ig[HA_U];
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int j = j0 + u * nThr;
+        const bool in = j < n && j != row;
+        ig[u] = in ? a.ign[j] : (unsigned char)1;
+        v[u] = in ? a.D[ha_idx(n, row, j)] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u)
+        if (!ig[u]) { ha_u64 k = ha_key(v[u], j0 + u * nThr); best = k < best ? k : best; }
     }
-  best = ha_block_min(best, sm);
-  if (threadIdx.x == 0) {
-    if (best == ~0ull) { a.closest[idx] = -1; a.cmin[idx] = __int_as_float(0x7f800000); }
-    else { a.closest[idx] = (int)(unsigned int)best; a.cmin[idx] = ha_unord((unsigned int)(best >> 32)); }
+    best = ha_block_min(best, sm);
+    if (threadIdx.x == 0 && best != ~0ull) atomicMin(&a.rkey[row], best);
   }
+}
+/// Takes a re-scan result out of rkey[row] (and re-arms the slot).
+__device__ __forceinline__ void ha_take_rescan(const HaArgs& a, int row, int& closest, float& cmin) {
+  const ha_u64 k = a.rkey[row];
+  a.rkey[row] = ~0ull;
+  closest = (k == ~0ull) ? -1 : (int)(unsigned int)k;
+  cmin = (k == ~0ull) ? __int_as_float(0x7f800000) : ha_unord((unsigned int)(k >> 32));
+  a.closest[row] = closest; a.cmin[row] = cmin;
 }
 
 /// The col-side sequence of SetCdist(C1, k, v_k), k ascending (DynamicMatrix.h:65-113), replayed by one warp: needed only
@@ -150,6 +173,7 @@ __device__ __forceinline__ void ha_tie_replay(const HaArgs& a, int C1, int C2) {
 }
 
 /// All merges in one launch.  Launch with ONE cluster of `team` CTAs x 1024 threads.
+template <int LINK>
 __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
   cg::cluster_group team = cg::this_cluster();
   __shared__ ha_u64 sm[34];
@@ -163,22 +187,38 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
   int nClusters = n;
   int prevC1 = -1, prevK = -1; float prevV = 0.f;   // previous merge: C1's closest when the row minimum was unique
 
+  long long t0 = clock64();
+#define HA_MARK(i) do { if (leader) { long long t1 = clock64(); a.ctl->clk[i] += t1 - t0; t0 = t1; } } while (0)
   for (int m = 0;; ++m) {
     const int p = m & 1;
-    // ---- FindMin (DynamicMatrix.cpp:7-33): lowest column among equal minima
+    // ---- FindMin (DynamicMatrix.cpp:7-33): lowest column among equal minima.  Rows re-scanned after the previous
+    //      update (closest == -2) take their result first; so does the previous C1 when its new row had one minimum.
     ha_u64 best = ~0ull;
-    for (int col = tid; col < n; col += nThr) {
-      if (a.ign[col]) continue;
-      float cm;
-      if (col == prevC1) { cm = prevV; a.closest[col] = prevK; a.cmin[col] = prevV; }
-      else cm = a.cmin[col];
-      if (a.closest[col] < 0 && col != prevC1) continue;
-      ha_u64 k = ha_key(cm, col);
-      best = k < best ? k : best;
+    for (int c0 = tid; c0 < n; c0 += nThr * HA_U) {
+      unsigned char ig[HA_U]; float cm[HA_U]; int cl[HA_U];
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int col = c0 + u * nThr;
+        const bool in = col < n;
+        ig[u] = in ? a.ign[col] : (unsigned char)1;
+        cm[u] = in ? a.cmin[col] : 0.f;
+        cl[u] = in ? a.closest[col] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int col = c0 + u * nThr;
+        if (ig[u]) continue;
+        if (col == prevC1) { cm[u] = prevV; cl[u] = prevK; a.closest[col] = prevK; a.cmin[col] = prevV; }
+        else if (cl[u] == -2) ha_take_rescan(a, col, cl[u], cm[u]);
+        if (cl[u] < 0) continue;
+        ha_u64 k = ha_key(cm[u], col);
+        best = k < best ? k : best;
+      }
     }
     best = ha_block_min(best, sm);
     if (threadIdx.x == 0 && best != ~0ull) atomicMin((ha_u64*)&a.ctl->minKey[p], best);
     team.sync();
+    HA_MARK(0);
     const ha_u64 mk = ctl->minKey[p];
     const float minVal = ha_unord((unsigned int)(mk >> 32));
     const int colMin = (int)(unsigned int)mk;
@@ -196,57 +236,92 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
     --nClusters;
     // ---- new row of the merged cluster; clusters whose closest was C2 are queued for Ignore()'s re-scan
     best = ~0ull;
-    for (int k = tid; k < n; k += nThr) {
-      if (k == C1 || k == C2 || a.ign[k]) continue;
-      const size_t i1 = ha_idx(n, C1, k), i2 = ha_idx(n, C2, k);
-      const float o1 = a.D[i1], o2 = a.D[i2];
-      float v;
-      if (a.linkage == 0) v = o2 < o1 ? o2 : o1;
-      else if (a.linkage == 2) v = o2 > o1 ? o2 : o1;
-      else {
-        const double s = a.S[i1] + a.S[i2];
-        a.snew[k] = s;
-        v = (float)(s / (double)(n1 * a.nfr[k]));
+    for (int k0 = tid; k0 < n; k0 += nThr * HA_U) {
+      unsigned char ig[HA_U]; float o1[HA_U], o2[HA_U]; double s1[HA_U], s2[HA_U]; int cl[HA_U], nf[HA_U];
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int k = k0 + u * nThr;
+        const bool in = k < n && k != C1 && k != C2;
+        ig[u] = in ? a.ign[k] : (unsigned char)1;
+        cl[u] = in ? a.closest[k] : -1;
+        const size_t i1 = in ? ha_idx(n, C1, k) : 0, i2 = in ? ha_idx(n, C2, k) : 0;
+        o1[u] = a.D[i1]; o2[u] = a.D[i2];
+        if (LINK == 1) { s1[u] = a.S[i1]; s2[u] = a.S[i2]; nf[u] = in ? a.nfr[k] : 1; }
       }
-      a.vnew[k] = v; a.oold[k] = o1;
-      if (a.closest[k] == C2) a.listA[atomicAdd((int*)&a.ctl->nA[p], 1)] = k;
-      ha_u64 key = ha_key(v, k);
-      best = key < best ? key : best;
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int k = k0 + u * nThr;
+        if (ig[u]) continue;
+        float v;
+        if (LINK == 0) v = o2[u] < o1[u] ? o2[u] : o1[u];
+        else if (LINK == 2) v = o2[u] > o1[u] ? o2[u] : o1[u];
+        else {
+          const double sum = s1[u] + s2[u];
+          a.snew[k] = sum;
+          v = (float)(sum / (double)(n1 * nf[u]));
+        }
+        a.vnew[k] = v; a.oold[k] = o1[u];
+        if (cl[u] == C2) a.listA[atomicAdd((int*)&a.ctl->nA[p], 1)] = k;
+        ha_u64 key = ha_key(v, k);
+        best = key < best ? key : best;
+      }
     }
     best = ha_block_min(best, sm);
     if (threadIdx.x == 0 && best != ~0ull) atomicMin((ha_u64*)&a.ctl->rowKey[p], best);
     team.sync();
+    HA_MARK(1);
     // ---- Ignore(C2) (DynamicMatrix.h:116-126): re-scan, on the OLD matrix, every cluster whose closest was C2
     const int nA = ctl->nA[p];
     if (nA > 0) {
-      for (int e = cta; e < nA; e += nCta) ha_rescan_row(a, a.listA[e], sm);
+      ha_team_rescan(a, a.listA, nA, tid, nThr, sm);
       team.sync();
+      if (leader) a.ctl->cnt[0] += nA;
     }
+    HA_MARK(2);
     // ---- SetCdist(C1, k, v_k), row side (DynamicMatrix.h:88-101), and the update itself
     const ha_u64 rk = ctl->rowKey[p];
     const unsigned int vminOrd = (unsigned int)(rk >> 32);
-    for (int k = tid; k < n; k += nThr) {
-      if (k == C1 || k == C2 || a.ign[k]) continue;
-      const float v = a.vnew[k];
-      const float cd = a.cmin[k];
-      const int ck = a.closest[k];
-      if (ck < 0 || v < cd) { a.closest[k] = C1; a.cmin[k] = v; }
-      else if (ck == C1 && v > cd) a.listB[atomicAdd((int*)&a.ctl->nB[p], 1)] = k;
-      const size_t i1 = ha_idx(n, C1, k);
-      a.D[i1] = v;
-      if (a.linkage == 1) a.S[i1] = a.snew[k];
-      if (ha_ord(v) == vminOrd) atomicAdd((int*)&a.ctl->tieCount[p], 1);
+    for (int k0 = tid; k0 < n; k0 += nThr * HA_U) {
+      unsigned char ig[HA_U]; float v[HA_U], cd[HA_U]; int ck[HA_U]; double sn[HA_U];
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int k = k0 + u * nThr;
+        const bool in = k < n && k != C1 && k != C2;
+        ig[u] = in ? a.ign[k] : (unsigned char)1;
+        v[u] = in ? a.vnew[k] : 0.f;
+        cd[u] = in ? a.cmin[k] : 0.f;
+        ck[u] = in ? a.closest[k] : -1;
+        if (LINK == 1) sn[u] = in ? a.snew[k] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < HA_U; ++u) {
+        const int k = k0 + u * nThr;
+        if (ig[u]) continue;
+        if (ck[u] == C2) ha_take_rescan(a, k, ck[u], cd[u]);   // Ignore()'s re-scan of this row
+        if (ck[u] < 0 || v[u] < cd[u]) { a.closest[k] = C1; a.cmin[k] = v[u]; }
+        else if (ck[u] == C1 && v[u] > cd[u]) {   // its closest distance grew: re-scan after the update
+          a.closest[k] = -2;
+          a.listB[atomicAdd((int*)&a.ctl->nB[p], 1)] = k;
+        }
+        const size_t i1 = ha_idx(n, C1, k);
+        a.D[i1] = v[u];
+        if (LINK == 1) a.S[i1] = sn[u];
+        if (ha_ord(v[u]) == vminOrd) atomicAdd((int*)&a.ctl->tieCount[p], 1);
+      }
     }
     if (leader) a.nfr[C1] = n1;
     team.sync();
+    HA_MARK(3);
     // ---- re-scans after the update: rows whose closest distance (to C1) grew; C1's own closest
     const int nB = ctl->nB[p];
     const int ties = ctl->tieCount[p];
     if (nB > 0 || ties > 1) {
-      for (int e = cta; e < nB; e += nCta) ha_rescan_row(a, a.listB[e], sm);
+      ha_team_rescan(a, a.listB, nB, tid, nThr, sm);
       if (ties > 1 && cta == 0 && threadIdx.x < 32) ha_tie_replay(a, C1, C2);
       team.sync();
+      if (leader) { a.ctl->cnt[1] += nB; a.ctl->cnt[2] += (ties > 1); }
     }
+    HA_MARK(4);
     if (ties == 1) { prevC1 = C1; prevK = (int)(unsigned int)rk; prevV = ha_unord(vminOrd); }
     else prevC1 = -1;
     if (nClusters <= a.target || nClusters == 1) break;
@@ -270,7 +345,7 @@ __global__ void __launch_bounds__(256) hieragglo_init_kernel(const float* __rest
     if (threadIdx.x == 0 && best != ~0ull) atomicMin(&keys[i], best);
   }
 }
-__global__ void hieragglo_init2_kernel(HaArgs a, const ha_u64* keys, size_t nElt) {
+__global__ void hieragglo_init2_kernel(HaArgs a, ha_u64* keys, size_t nElt) {
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t nT = (size_t)gridDim.x * blockDim.x;
   for (size_t i = t; i < (size_t)a.n; i += nT) {
@@ -278,6 +353,7 @@ __global__ void hieragglo_init2_kernel(HaArgs a, const ha_u64* keys, size_t nElt
     a.closest[i] = (k == ~0ull) ? -1 : (int)(unsigned int)k;
     a.cmin[i] = (k == ~0ull) ? __int_as_float(0x7f800000) : ha_unord((unsigned int)(k >> 32));
     a.ign[i] = 0; a.nfr[i] = 1;
+    keys[i] = ~0ull;   // from here on the buffer is rkey: pending re-scan results
   }
   if (a.S != nullptr)
     for (size_t e = t; e < nElt; e += nT) a.S[e] = (double)a.D[e];
@@ -285,6 +361,8 @@ __global__ void hieragglo_init2_kernel(HaArgs a, const ha_u64* keys, size_t nElt
     a.ctl->minKey[0] = a.ctl->minKey[1] = ~0ull; a.ctl->rowKey[0] = a.ctl->rowKey[1] = ~0ull;
     a.ctl->tieCount[0] = a.ctl->tieCount[1] = 0; a.ctl->nA[0] = a.ctl->nA[1] = 0; a.ctl->nB[0] = a.ctl->nB[1] = 0;
     a.ctl->nCalls = 0; a.ctl->nMerges = 0; a.ctl->stopped = 0;
+    for (int i = 0; i < 8; ++i) a.ctl->clk[i] = 0;
+    for (int i = 0; i < 4; ++i) a.ctl->cnt[i] = 0;
   }
 }
 

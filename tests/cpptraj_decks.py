@@ -108,4 +108,14 @@ cluster L4 @CA hieragglo clusters 3 averagelinkage rms nofit sieve 3 out hl.siev
 """, [("hl.single.dat", "table"), ("hl.single.info", "text"), ("hl.single.eps", "table"), ("hl.avg.dat", "table"),
       ("hl.avg.summary", "text"), ("hl.avg.eps", "table"), ("hl.complete.dat", "table"), ("hl.complete.info", "text"),
       ("hl.complete.eps", "table"), ("hl.sieve.dat", "table"), ("hl.sieve.info", "text")]),
+    # src/Cluster/Cmatrix_Binary.cpp:12-21: the cache filled on the device written by the reference's own binary writer
+    # (savepairdist), read back (readdata) and clustered on the device again from the loaded cache
+    "cluster_cmatrix_roundtrip": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+cluster P1 @CA hieragglo clusters 5 averagelinkage rms savepairdist pairdist cm.bin out p1.dat
+run
+readdata cm.bin name CM2
+cluster P2 @CA hieragglo clusters 4 complete rms pairdist CM2 out p2.dat info p2.info
+""", [("cm.bin", "cmatrix"), ("p1.dat", "table"), ("p2.dat", "table"), ("p2.info", "text")]),
 }

@@ -160,6 +160,8 @@ def test_cpptraj_deck_matches_unmodified_reference(tmp_path, name):
     r = subprocess.run([BIN, "-i", "in"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-3000:]
     assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    if name == "cluster_cmatrix_roundtrip":
+        assert r.stdout.count("initial clusters on the device") == 2, "the device merge loop did not run:\n" + r.stdout[-3000:]
     if name == "cluster_hier_linkages":
         assert r.stdout.count("initial clusters on the device") == 4, "the device merge loop did not run:\n" + r.stdout[-3000:]
     for fname, kind in outs:
@@ -169,6 +171,12 @@ def test_cpptraj_deck_matches_unmodified_reference(tmp_path, name):
             assert got.shape == want.shape, (fname, got.shape, want.shape)
             # values are printed with 4 decimals: the contract (1e-4 A) plus one unit of the last printed digit
             assert np.abs(got - want).max() <= 2.01e-4, (fname, np.abs(got - want).max())
+        elif kind == "cmatrix":
+            # Cmatrix_Binary version 2 (src/Cluster/Cmatrix_Binary.cpp:12-21,150-188): magic, 3 x 8-byte header, float triangle
+            g, w = open(got_p, "rb").read(), open(want_p, "rb").read()
+            assert len(g) == len(w) and g[:28] == w[:28], fname
+            gf, wf = np.frombuffer(g[28:], np.float32), np.frombuffer(w[28:], np.float32)
+            assert np.abs(gf.astype(np.float64) - wf).max() <= 1e-4, (fname, np.abs(gf.astype(np.float64) - wf).max())
         elif kind == "crd":
             got, want = _amber_crd(got_p), _amber_crd(want_p)
             assert got.shape == want.shape, (fname, got.shape, want.shape)
