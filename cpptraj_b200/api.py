@@ -50,6 +50,8 @@ def lib():
     L.b200_rmsd_1vN_set_ref.restype = i
     L.b200_rmsd_build_centroids.argtypes = [vp, sz, i, vp, vp, i, vp, i, vp, i, vp]
     L.b200_rmsd_build_centroids.restype = i
+    L.b200_rmsavgcorr.argtypes = [vp, sz, i, vp, i, vp, vp, vp, i, vp, vp]
+    L.b200_rmsavgcorr.restype = i
     L.b200_hieragglo.argtypes = [vp, i, i, i, dbl, vp, vp, vp, C.POINTER(i), C.POINTER(i)]
     L.b200_hieragglo.restype = i
     L.b200_coords_resident_begin.argtypes = [vp, sz, i, vp, i]
@@ -277,6 +279,20 @@ def build_centroids(crd, atom_idx, frame_lists, mass=None, fit=True):
     _check(lib().b200_rmsd_build_centroids(_p(crd), crd.shape[1], crd.shape[0], _p(frames), _p(offsets), len(frame_lists),
                                            _p(sel), len(sel), _p(mass), int(bool(fit)), _p(out)))
     return out
+
+
+def rmsavgcorr(crd, atom_idx, windows, mass=None, ref_selected=None):
+    """Analysis_RmsAvgCorr::Analyze: (avg, sd) per window size; ref_selected None = 'first' mode."""
+    crd = _crd2d(crd)
+    idx = _arr(atom_idx, np.int32)
+    win = _arr(windows, np.int32)
+    m = _arr(mass, np.float64)
+    ref = None if ref_selected is None else _arr(ref_selected, np.float64).reshape(-1)
+    avg = np.zeros(len(win), np.float64)
+    sd = np.zeros(len(win), np.float64)
+    _check(lib().b200_rmsavgcorr(_p(crd), crd.shape[1], crd.shape[0], _p(idx), len(idx), _p(m), _p(ref), _p(win), len(win),
+                                 _p(avg), _p(sd)))
+    return avg, sd
 
 
 def hieragglo(tri, nframes, linkage=1, target_clusters=None, epsilon=None):

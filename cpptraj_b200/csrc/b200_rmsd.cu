@@ -8,6 +8,7 @@
 #include "rmsd_kernels.cuh"
 #include "pair_i8.cuh"
 #include "hieragglo.cuh"
+#include "avgcorr.cuh"
 #include "host_util.h"
 
 #include <algorithm>
@@ -90,6 +91,7 @@ struct Device {
   // workspaces (grow-only)
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
   DevBuf imgA, imgB, cenA, cenB, dbgS;   // tcgen05 int8 path: operand images, frame centres
+  DevBuf acP, acRms, acMisc;              // rmsavgcorr: prefix sums of the selected coordinates, RMSDs of a window batch, per-window data
   DevBuf haD, haS, haMisc;                // hierarchical clustering: cluster-distance triangle, linkage sums, per-cluster state
   PinBuf hostScal;                        // pinned slot for the few scalars read back per call
   int numSMs = 0;
@@ -118,7 +120,7 @@ struct Device {
       inStage[b].release();
     }
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
-                     &imgA, &imgB, &cenA, &cenB, &dbgS, &haD, &haS, &haMisc};
+                     &imgA, &imgB, &cenA, &cenB, &dbgS, &haD, &haS, &haMisc, &acP, &acRms, &acMisc};
     for (DevBuf* b : all) b->release();
     hostScal.release(); resBuf.release(); resHost = nullptr;
     pool.stop(); poolOut.stop();
@@ -2082,6 +2084,99 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
   {
     std::lock_guard<std::mutex> sl(g_statMu);
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)outBytes;
+  }
+  return B200_OK;
+}
+
+// ---- rmsavgcorr: RMSD of running-averaged coordinates, all window sizes (avgcorr.cuh)
+int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms, const double* mass,
+                    const double* refSelected, const int* windows, int nWindows, double* avgOut, double* sdOut) {
+  if (!crd || !windows || !avgOut || !sdOut) return fail(B200_ERR_ARG, "null argument");
+  if (nFrames < 1 || nWindows < 0) return fail(B200_ERR_ARG, "bad frame or window count");
+  for (int w = 0; w < nWindows; ++w)
+    if (windows[w] < 1 || windows[w] > nFrames) return fail(B200_ERR_ARG, "windows[%d]=%d outside 1..%d", w, windows[w], nFrames);
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc, maxAtom = 0;
+  if ((rc = ensure_init_locked())) return rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  if (nWindows == 0) return B200_OK;
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const size_t width = (size_t)3 * ((size_t)maxAtom + 1);
+  const float* d_frames = nullptr;
+  size_t pitch = width;
+  long rowBase = 0;
+  if ((rc = get_coords(d, d.crd, crd, frameStrideFloats, nFrames, 0, nFrames, width, st, &h2d, &d_frames, &pitch, &rowBase))) return rc;
+  if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
+  if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
+  if (refSelected && (rc = upload_vec(d.planesB, refSelected, (size_t)3 * nAtoms, st))) return rc;
+  double totalMass = 0.0;   // in atom order, as Frame::RMSD_CenteredRef sums it (src/Frame.cpp:1150-1158)
+  for (int k = 0; k < nAtoms; ++k) totalMass += mass ? mass[k] : 1.0;
+  const int ld = 3 * nAtoms;
+  if ((rc = d.acP.reserve(((size_t)nFrames + 1) * ld * sizeof(double)))) return rc;
+  if ((rc = d.scal.reserve(64))) return rc;
+  COUNT_LAUNCH();
+  avgcorr_shift_kernel<<<1, 32, 0, st>>>(d_frames, pitch, rowBase, (const int*)d.idxA.p, nAtoms, (double*)d.scal.p);
+  COUNT_LAUNCH();
+  avgcorr_prefix_kernel<<<(ld + 127) / 128, 128, 0, st>>>(d_frames, pitch, rowBase, (const int*)d.idxA.p, nAtoms, nFrames,
+                                                          (const double*)d.scal.p, (double*)d.acP.p);
+  CU(cudaGetLastError());
+  // windows in batches of bounded RMSD count (one RMSD per window and averaged frame)
+  const long long maxItems = (long long)32 << 20;
+  std::vector<long long> off;
+  std::vector<double> hAvg, hSd;
+  for (int w0 = 0; w0 < nWindows;) {
+    off.assign(1, 0);
+    int w1 = w0, maxPer = 0;
+    while (w1 < nWindows && w1 - w0 < 65535) {
+      const long long items = (long long)nFrames - windows[w1] + 1;
+      if (w1 > w0 && off.back() + items > maxItems) break;
+      off.push_back(off.back() + items);
+      maxPer = std::max<long long>(maxPer, items);
+      ++w1;
+    }
+    const int nW = w1 - w0;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t oWin = 0, oOff = up((size_t)nW * sizeof(int)), oInfo = oOff + up(((size_t)nW + 1) * sizeof(long long)),
+                 oAvg = oInfo + up((size_t)nW * 8 * sizeof(double)), oSd = oAvg + up((size_t)nW * sizeof(double)),
+                 total = oSd + up((size_t)nW * sizeof(double));
+    if ((rc = d.acMisc.reserve(total))) return rc;
+    if ((rc = d.acRms.reserve((size_t)off.back() * sizeof(double)))) return rc;
+    char* base = (char*)d.acMisc.p;
+    CU(cudaMemcpyAsync(base + oWin, windows + w0, (size_t)nW * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(base + oOff, off.data(), ((size_t)nW + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    AvgCorrArgs a;
+    a.P = (const double*)d.acP.p; a.ld = ld; a.nAtoms = nAtoms; a.nFrames = nFrames;
+    a.mass = mass ? (const double*)d.massA.p : nullptr;
+    a.refFixed = refSelected ? (const double*)d.planesB.p : nullptr;
+    a.win = (const int*)(base + oWin); a.itemOff = (const long long*)(base + oOff); a.nW = nW;
+    a.refInfo = (double*)(base + oInfo); a.rms = (double*)d.acRms.p; a.totalMass = totalMass;
+    COUNT_LAUNCH();
+    avgcorr_ref_kernel<<<nW, 256, 0, st>>>(a);
+    CU(cudaGetLastError());
+    COUNT_LAUNCH();
+    {
+      static const int nwin = getenv("B200_AVGCORR_NWIN") ? atoi(getenv("B200_AVGCORR_NWIN")) : 2;   // window sizes per warp (measured, 10k x 1k: 0.42 / 0.31 / 0.35 s for 1 / 2 / 4)
+      const dim3 blk(AVGCORR_WARPS * 32);
+      const unsigned gx = (unsigned)((maxPer + AVGCORR_WARPS - 1) / AVGCORR_WARPS);
+      if (nwin <= 1) avgcorr_kernel<1><<<dim3(gx, nW), blk, 0, st>>>(a);
+      else if (nwin == 2) avgcorr_kernel<2><<<dim3(gx, (nW + 1) / 2), blk, 0, st>>>(a);
+      else avgcorr_kernel<4><<<dim3(gx, (nW + 3) / 4), blk, 0, st>>>(a);
+    }
+    CU(cudaGetLastError());
+    COUNT_LAUNCH();
+    avgcorr_reduce_kernel<<<nW, 256, 0, st>>>(a.rms, a.itemOff, nW, (double*)(base + oAvg), (double*)(base + oSd));
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(avgOut + w0, base + oAvg, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(sdOut + w0, base + oSd, (size_t)nW * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));   // (the staging vectors and the per-batch buffers are reused)
+    w0 = w1;
+  }
+  {
+    std::lock_guard<std::mutex> sl(g_statMu);
+    g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)nWindows * 16.0;
   }
   return B200_OK;
 }

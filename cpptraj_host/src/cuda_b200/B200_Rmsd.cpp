@@ -263,3 +263,26 @@ int Cpptraj::B200::HierAgglo(const float* triangle, int nCached, int linkage, in
   mprintf("\tB200: %i merges of %i initial clusters on the device in %.4f s.\n", nMerges, nCached, t_call.Total());
   return 0;
 }
+
+int Cpptraj::B200::RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
+                              Frame const* fixedRef, std::vector<int> const& windows, std::vector<double>& avg,
+                              std::vector<double>& sd)
+{
+  if (Init()) return 1;
+  avg.assign( windows.size(), 0.0 );
+  sd.assign( windows.size(), 0.0 );
+  if (windows.empty() || crd.Size() < 1) return 0;
+  if (fixedRef != 0 && fixedRef->Natom() != mask.Nselected()) {
+    mprinterr("Error: B200 RMSD: # target atoms (%i) != # reference atoms (%i)\n", mask.Nselected(), fixedRef->Natom());
+    return 1;
+  }
+  Timer t_call;
+  t_call.Start();
+  int err = b200_rmsavgcorr(crd.RawFrames(), crd.FrameStride(), (int)crd.Size(), &(mask.Selected()[0]), mask.Nselected(),
+                            ptr_or_null(mass), (fixedRef != 0 ? fixedRef->xAddress() : 0), &windows[0], (int)windows.size(),
+                            &avg[0], &sd[0]);
+  t_call.Stop();
+  if (err) return b200_err("rmsavgcorr");
+  mprintf("\tB200: %zu window sizes over %zu frames on the device in %.4f s.\n", windows.size(), crd.Size(), t_call.Total());
+  return 0;
+}

@@ -57,6 +57,12 @@ int CentroidDists(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vect
   */
 int BuildCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, bool fit,
                    std::vector<Cluster::Cframes const*> const& clusterFrames, std::vector<Frame*> const& centroids);
+/** rmsavgcorr (Analysis_RmsAvgCorr::Analyze, Analysis_RmsAvgCorr.cpp:119-316): mean and standard deviation of the RMSDs of
+  * the running-averaged frames for every window size of \a windows.  \a fixedRef: the pre-centred reference frame
+  * (selected atoms) or 0 for the "first" mode.  \a avg / \a sd are sized to windows.size().
+  */
+int RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, Frame const* fixedRef,
+               std::vector<int> const& windows, std::vector<double>& avg, std::vector<double>& sd);
 /** Hierarchical agglomerative clustering on an in-memory pairwise cache (Algorithm_HierAgglo::DoClustering /
   * MergeClosest, Cluster/Algorithm_HierAgglo.cpp:97-245, with the DynamicMatrix bookkeeping): all merges run on the
   * device in one launch.  \a triangle: DataSet_PairwiseCache_MEM::Ptr() for \a nCached frames; \a linkage in

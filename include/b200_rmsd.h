@@ -160,6 +160,18 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
                               const int* atomIdx, int nAtoms, const double* mass, int fit,
                               double* centroidsOut);
 
+/* ---- rmsavgcorr: RMSD of running-averaged coordinates -------------------------------------------------
+ * Analysis_RmsAvgCorr::Analyze (src/Analysis_RmsAvgCorr.cpp:119-316).  For every window size windows[w] the frames
+ * t = 0 .. nFrames - W are replaced by the average of frames t .. t+W-1 (selected atoms), each averaged frame is fitted
+ * (Frame::RMSD_CenteredRef, masses of the selected atoms when mass != NULL) to the reference, and avgOut[w] / sdOut[w]
+ * receive the mean and the standard deviation of those RMSDs as the reference forms them (:196-205, :289-297).
+ * refSelected NULL: the "first" mode -- the reference of a window size is its own first averaged frame, centred with
+ * the same weights (:258-272); else 3*nAtoms doubles, the fixed reference exactly as the caller centred it (:86-90).
+ * Window size 1 is the plain trajectory (:176-205).  All frames of crd are used.  Runs on device 0. */
+int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms,
+                    const double* mass, const double* refSelected, const int* windows, int nWindows,
+                    double* avgOut, double* sdOut);
+
 /* ---- cluster: hierarchical agglomerative clustering on the pairwise cache ---------------------------
  * The merge loop of Algorithm_HierAgglo::DoClustering / MergeClosest (src/Cluster/Algorithm_HierAgglo.cpp:97-245) with
  * the Cluster::DynamicMatrix bookkeeping (src/Cluster/DynamicMatrix.h:43-126, DynamicMatrix.cpp:7-33), run on the

@@ -61,6 +61,24 @@ def _hieragglo(fn, tri, n, linkage, target_clusters, epsilon):
     return into[:nm.value].copy(), frm[:nm.value].copy(), fmin[:nc.value].copy()
 
 
+def _rmsavgcorr(fn, extra, crd, sel, windows, mass, ref_sel_xyz):
+    crd = np.ascontiguousarray(crd, np.float32)
+    sel = np.ascontiguousarray(sel, np.int32)
+    windows = np.ascontiguousarray(windows, np.int32)
+    mass = _opt(mass, np.float64)
+    ref = None if ref_sel_xyz is None else np.ascontiguousarray(ref_sel_xyz, np.float64).reshape(-1)
+    avg = np.zeros(len(windows), np.float64)
+    sd = np.zeros(len(windows), np.float64)
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_size_t, C.c_int] + [C.c_int] * len(extra) + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = fn(_ptr(crd), crd.shape[1], crd.shape[0], *extra, _ptr(sel), len(sel), _ptr(mass), _ptr(ref), _ptr(windows),
+            len(windows), _ptr(avg), _ptr(sd))
+    if rc:
+        raise RuntimeError("rmsavgcorr checker failed rc=%d" % rc)
+    return avg, sd
+
+
 class _Base:
     def __init__(self, path):
         if not os.path.exists(path):
@@ -105,6 +123,10 @@ class Oracle(_Base):
         if rc:
             raise RuntimeError("oracle failed rc=%d" % rc)
         return out
+
+    def rmsavgcorr(self, crd, sel, windows, mass=None, ref_sel_xyz=None):
+        """Analysis_RmsAvgCorr::Analyze: (avg, sd) per window size; ref_sel_xyz None = 'first' mode."""
+        return _rmsavgcorr(self.lib.orc_rmsavgcorr, (), crd, sel, windows, mass, ref_sel_xyz)
 
     def hieragglo(self, tri, n, linkage=1, target_clusters=None, epsilon=None):
         return _hieragglo(self.lib.orc_hieragglo, tri, n, linkage, target_clusters, epsilon)
@@ -190,6 +212,12 @@ class Reference(_Base):
         L.ref_rmsd_1vN.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p]
+
+    def rmsavgcorr(self, crd, sel, windows, mass=None, ref_sel_xyz=None, natom_total=None):
+        crd = np.ascontiguousarray(crd, np.float32)
+        sel = np.ascontiguousarray(sel, np.int32)
+        return _rmsavgcorr(self.lib.ref_rmsavgcorr, (natom_total or self._natom_total(crd, sel),), crd, sel, windows, mass,
+                           ref_sel_xyz)
 
     def hieragglo(self, tri, n, linkage=1, target_clusters=None, epsilon=None):
         """The reference's own Cluster::DynamicMatrix driven by ref_driver.cpp's restated merge loop."""

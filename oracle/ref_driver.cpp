@@ -17,6 +17,7 @@
 // the per-frame body of Action_Rmsd::DoAction (src/Action_Rmsd.cpp:361-392),
 // because those classes drag in the whole DataSet/ArgList/Topology runtime.
 #include <vector>
+#include <cmath>
 #include <cstring>
 #include <cstddef>
 #ifdef _OPENMP
@@ -324,6 +325,56 @@ int ref_hieragglo(const float* tri, int n, int linkage, int targetClusters, doub
       if (alive[k] && k != C1) CD.SetCdist(C1, k, Link::dist(cache, linkage, fl[C1], fl[k]));
     if (nClusters <= targetClusters) break;
     if (nClusters == 1) break;
+  }
+  return 0;
+}
+
+// Analysis_RmsAvgCorr::Analyze (src/Analysis_RmsAvgCorr.cpp:119-316) with the reference's own Frame arithmetic
+// (operator+=, operator-=, Divide, CenterOnOrigin, RMSD_CenteredRef); the window loop is restated.
+int ref_rmsavgcorr(const float* crd, size_t stride, int nTotalFrames, int natomTotal, const int* sel, int n, const double* mass,
+                   const double* refSel, const int* windows, int nW, double* avgOut, double* sdOut)
+{
+  Coords C;
+  if (fill(C, crd, stride, nTotalFrames, natomTotal, sel, n, mass)) return 1;
+  bool useMass = (mass != 0);
+  int maxFrame = nTotalFrames;
+  Frame tgtTemplate;
+  tgtTemplate.SetupFrameFromMask(C.mask, C.atoms);
+  Frame refFixed = tgtTemplate;
+  if (refSel != 0) std::memcpy(refFixed.xAddress(), refSel, sizeof(double) * 3 * (size_t)n);
+  int w;
+#pragma omp parallel for schedule(dynamic)
+  for (w = 0; w < nW; w++) {
+    Frame tgtFrame = tgtTemplate, refFrame = refFixed, sumFrame(n);
+    int window = windows[w];
+    double avg = 0.0, stdev = 0.0, d_Nwindow = (double)window;
+    bool first = (refSel == 0);
+    int subtractWindow = 0, frameThreshold = window - 2;
+    sumFrame.ZeroCoords();
+    for (int frame = 0; frame < maxFrame; frame++) {
+      getFrame(C, frame, tgtFrame);
+      if (window != 1) {
+        sumFrame += tgtFrame;
+        if (!(frame > frameThreshold)) continue;
+        tgtFrame.Divide(sumFrame, d_Nwindow);
+      }
+      if (first) {
+        refFrame.SetCoordinates(tgtFrame);
+        refFrame.CenterOnOrigin(useMass);
+        first = false;
+      }
+      double rmsd = tgtFrame.RMSD_CenteredRef(refFrame, useMass);
+      avg += rmsd; stdev += rmsd * rmsd;
+      if (window != 1) {
+        getFrame(C, subtractWindow, tgtFrame);
+        sumFrame -= tgtFrame;
+        ++subtractWindow;
+      }
+    }
+    d_Nwindow = 1.0 / ((double)maxFrame - (double)window + 1.0);
+    avg *= d_Nwindow; stdev *= d_Nwindow; stdev -= (avg * avg);
+    stdev = (stdev > 0.0) ? sqrt(stdev) : 0.0;
+    avgOut[w] = avg; sdOut[w] = stdev;
   }
   return 0;
 }

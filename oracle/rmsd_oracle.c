@@ -631,3 +631,66 @@ int orc_hieragglo(const float *tri, int n, int linkage, int targetClusters, doub
     free(fl); free(nf); free(M.mat); free(M.ignore); free(M.closest);
     return 0;
 }
+
+/* ---- (f) rank 4: rmsavgcorr -----------------------------------------------------------
+ * Analysis_RmsAvgCorr::Analyze, src/Analysis_RmsAvgCorr.cpp:119-316.  Per window size W: a running SUM of the
+ * selected coordinates (sumFrame += frame t, :252; -= frame t-W+1 after use, :283-285), the averaged frame
+ * tgt = sum / W (Frame::Divide, src/Frame.cpp:950-963), in "first" mode the first averaged frame -- centred -- is the
+ * reference of that window size (:258-272), RMSD_CenteredRef of every averaged frame (:273-277), and
+ * avg = sum/n, sd = sqrt(max(0, sum2/n - avg^2)) over the n = F - W + 1 of them (:289-297).  Window size 1 is the
+ * initial pass over the plain frames (:176-205; in "first" mode against the centred frame 0, :134-141).
+ * refSel NULL = "first" mode, else the fixed reference as the caller centred it.  All frames of crd are used. */
+int orc_rmsavgcorr(const float *crd, size_t stride, int nF, const int *sel, int n, const double *mass,
+                   const double *refSel, const int *windows, int nW, double *avgOut, double *sdOut)
+{
+    int useMass = (mass != NULL);
+    int err = 0;
+#pragma omp parallel
+    {
+        double *T = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *A = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *R = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        double *Sum = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+        if (!T || !A || !R || !Sum) {
+#pragma omp atomic write
+            err = 1;
+        } else {
+#pragma omp for schedule(dynamic)
+            for (int w = 0; w < nW; w++) {
+                int window = windows[w];
+                double dW = (double)window, avg = 0.0, sd = 0.0, c[3];
+                int first = (refSel == NULL), sub = 0;
+                if (refSel) memcpy(R, refSel, sizeof(double) * 3 * (size_t)n);
+                for (int i = 0; i < 3 * n; i++) Sum[i] = 0.0;
+                for (int f = 0; f < nF; f++) {
+                    orc_gather(crd, stride, f, sel, n, T);
+                    if (window == 1) {
+                        memcpy(A, T, sizeof(double) * 3 * (size_t)n);
+                    } else {
+                        for (int i = 0; i < 3 * n; i++) Sum[i] += T[i];
+                        if (f <= window - 2) continue;
+                        for (int i = 0; i < 3 * n; i++) A[i] = Sum[i] / dW;
+                    }
+                    if (first) {
+                        memcpy(R, A, sizeof(double) * 3 * (size_t)n);
+                        orc_center_on_origin(R, n, mass, useMass, c);
+                        first = 0;
+                    }
+                    double r = orc_rmsd_centered_ref(A, R, n, mass, useMass, NULL, NULL);
+                    avg += r; sd += r * r;
+                    if (window != 1) {
+                        orc_gather(crd, stride, sub, sel, n, T);
+                        for (int i = 0; i < 3 * n; i++) Sum[i] -= T[i];
+                        sub++;
+                    }
+                }
+                double d = 1.0 / ((double)nF - dW + 1.0);
+                avg *= d; sd *= d; sd -= avg * avg;
+                sd = (sd > 0.0) ? sqrt(sd) : 0.0;
+                avgOut[w] = avg; sdOut[w] = sd;
+            }
+        }
+        free(T); free(A); free(R); free(Sum);
+    }
+    return err;
+}

@@ -118,4 +118,15 @@ run
 readdata cm.bin name CM2
 cluster P2 @CA hieragglo clusters 4 complete rms pairdist CM2 out p2.dat info p2.info
 """, [("cm.bin", "cmatrix"), ("p1.dat", "table"), ("p2.dat", "table"), ("p2.info", "text")]),
+    # test/Test_RmsAvgCorr/RunTest.sh:11-34 (fixed reference; offset; first running-averaged frame as reference) plus
+    # mass weighting with a window limit: every window size on the device (b200_rmsavgcorr)
+    "rmsavgcorr": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+reference {D}/tz2.crd 5
+rmsavgcorr RF :2-12@CA out rac.first.dat first
+rmsavgcorr RM :2-12@CA,C,N out rac.mass.dat first mass stop 40 offset 3
+rmsavgcorr RR :2-12@CA out rac.ref.dat reference
+rmsavgcorr R10 :2-12@CA out rac.ref10.dat reference offset 10
+""", [("rac.first.dat", "table"), ("rac.mass.dat", "table"), ("rac.ref.dat", "table"), ("rac.ref10.dat", "table")]),
 }

@@ -160,6 +160,8 @@ def test_cpptraj_deck_matches_unmodified_reference(tmp_path, name):
     r = subprocess.run([BIN, "-i", "in"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=str(tmp_path))
     assert r.returncode == 0 and "Error" not in r.stdout, r.stdout[-3000:]
     assert "B200 RMSD path" in r.stdout, "the B200 branch did not run:\n" + r.stdout[-2000:]
+    if name == "rmsavgcorr":
+        assert r.stdout.count("window sizes over 101 frames on the device") == 4, "not on the device:\n" + r.stdout[-3000:]
     if name == "cluster_cmatrix_roundtrip":
         assert r.stdout.count("initial clusters on the device") == 2, "the device merge loop did not run:\n" + r.stdout[-3000:]
     if name == "cluster_hier_linkages":

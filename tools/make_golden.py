@@ -88,6 +88,16 @@ def read_save_matrix(path):
     return np.array(rows, np.float64)
 
 
+def read_rst7(path):
+    """Amber ASCII restart: title, atom count, 6F12.7 coordinates."""
+    lines = open(path).read().splitlines()
+    n = int(lines[1].split()[0])
+    vals = []
+    for ln in lines[2:]:
+        vals.extend(float(ln[i:i + 12]) for i in range(0, len(ln.rstrip()), 12))
+    return np.array(vals[:3 * n], np.float64).reshape(n, 3)
+
+
 def synth(seed, nframes, natoms, natom_total=None, stride_extra=0):
     """Small deterministic trajectory in the BASELINE cfg-2 style (see cpptraj_b200.synth)."""
     from cpptraj_b200.synth import make_trajectory
@@ -115,6 +125,11 @@ def main():
         nofit=read_save_matrix(os.path.join(t2d, "nofit.dat.save")),
         nomod=read_save_matrix(os.path.join(trm, "NoMod.dat.save"))[:, 0],
         previous=read_save_matrix(os.path.join(trm, "Previous.dat.save"))[:, 0],
+        # test/Test_RmsAvgCorr/RunTest.sh:11-34: fixed reference (avg.CA.rst7), the same with offset 10, "first" mode
+        rmsavgcorr_ref=read_save_matrix(os.path.join(REF, "test", "Test_RmsAvgCorr", "rmscorr.dat.save")),
+        rmsavgcorr_ref10=read_save_matrix(os.path.join(REF, "test", "Test_RmsAvgCorr", "rmscorr.10.dat.save")),
+        rmsavgcorr_first=read_save_matrix(os.path.join(REF, "test", "Test_RmsAvgCorr", "rmscorr.first.dat.save")),
+        avg_ca_rst7=read_rst7(os.path.join(REF, "test", "Test_RmsAvgCorr", "avg.CA.rst7")),
     )
     np.savez_compressed(os.path.join(OUT, "ref_saves.npz"), **saves)
 
