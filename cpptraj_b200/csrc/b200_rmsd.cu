@@ -192,6 +192,10 @@ struct Timer {  // collects (start,stop) events; resolved after a sync
 std::mutex g_streamMu;
 Timer g_streamTimer;
 long g_streamLaunches = 0;
+// the whole one-vs-many pass of the device-pointer API (asynchronous: its events are resolved later as well)
+Timer g_devPassTimer;
+long g_devPasses = 0;
+double g_devPassFrames = 0.0;
 
 bool host_ptr_is_pinned(const void* p) {
   cudaPointerAttributes at;
@@ -1221,7 +1225,11 @@ int b200_shard_rows(int nFrames, int shardRank, int shardCount, int* row0, int* 
 void b200_set_profiling(int on) { g_profiling = (on != 0); }
 int b200_set_mma_variant(int v) { if (v < 0 || v > 3) return fail(B200_ERR_ARG, "variant must be 0..3"); g_variant.store(v); return B200_OK; }
 void b200_reset_stats(void) {
-  { std::lock_guard<std::mutex> tl(g_streamMu); if (!g_streamTimer.ev.empty()) { cudaDeviceSynchronize(); g_streamTimer.resolve(); } g_streamLaunches = 0; }
+  {
+    std::lock_guard<std::mutex> tl(g_streamMu);
+    if (!g_streamTimer.ev.empty() || !g_devPassTimer.ev.empty()) { cudaDeviceSynchronize(); g_streamTimer.resolve(); g_devPassTimer.resolve(); }
+    g_streamLaunches = 0; g_devPasses = 0; g_devPassFrames = 0.0;
+  }
   std::lock_guard<std::mutex> lk(g_statMu);
   g_stats = b200_stats();
   g_launches.store(0);
@@ -1230,12 +1238,13 @@ void b200_get_stats(b200_stats* out) {
   if (!out) return;
   {
     std::lock_guard<std::mutex> tl(g_streamMu);
-    if (!g_streamTimer.ev.empty()) {
+    if (!g_streamTimer.ev.empty() || !g_devPassTimer.ev.empty()) {
       cudaDeviceSynchronize();   // (the one-vs-many kernels run on the current device's streams)
-      const double ms = g_streamTimer.resolve();
+      const double ms = g_streamTimer.resolve(), msPass = g_devPassTimer.resolve();
       std::lock_guard<std::mutex> lk(g_statMu);
       g_stats.onevn_stream_ms += ms; g_stats.onevn_stream_launches += g_streamLaunches;
-      g_streamLaunches = 0;
+      g_stats.onevn_ms += msPass; g_stats.onevn_launches += g_devPasses; g_stats.frames_1vN += g_devPassFrames;
+      g_streamLaunches = 0; g_devPasses = 0; g_devPassFrames = 0.0;
     }
   }
   std::lock_guard<std::mutex> lk(g_statMu);
@@ -1529,8 +1538,8 @@ template <typename T>
 static bool onevn_use_v2(size_t stride, int nAtoms, int fit) {
   if (!fit) return false;
   if (const char* e = getenv("B200_1VN_V2")) return atoi(e) != 0;
-  const size_t parts = 2 * onevn_max_chunks(stride, ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T)));
-  return parts * 128 <= (size_t)nAtoms * 3 * sizeof(T) / 2 && parts <= 256;   // partial records (128 B each) <= half the bytes read per frame
+  const size_t parts = onevn_max_chunks(stride, ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T)));   // one record per frame and chunk
+  return parts * 128 <= (size_t)nAtoms * 3 * sizeof(T) / 4 && parts <= 256;   // partial records (128 B each) <= a quarter of the bytes read per frame
 }
 static size_t onevn_ws_bytes(size_t stride, int nFrames) {
   const size_t maxChunks = onevn_max_chunks(stride, ONEVN2_CHUNK_BYTES / 24);   // (double frames: the smaller chunk)
@@ -1542,7 +1551,10 @@ static size_t onevn_ws_bytes(size_t stride, int nFrames) {
 template <typename T>
 static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, const int* d_atomIdx, int nAtoms,
                      const double* refw, const double* refsum, int fit, double* rmsd, double* rot, double* trans,
-                     void* ws, cudaStream_t st, const int* d_frameIdx = nullptr, long srcBase = 0) {
+                     void* ws, cudaStream_t st, const int* d_frameIdx = nullptr, long srcBase = 0,
+                     const double* setupRef = nullptr, const double* setupMass = nullptr) {
+  // setupRef != nullptr: refw / refsum are still to be derived from this reference (3 nAtoms doubles) and these masses;
+  // that happens inside the one preparation launch below
   const bool v2 = onevn_use_v2<T>(stride, nAtoms, fit);
   const int APC = v2 ? ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T)) : ONEVN_S_CHUNK_BYTES / (3 * (int)sizeof(T));
   const int maxChunks = (int)onevn_max_chunks(stride, APC);
@@ -1564,11 +1576,11 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
       attr[dev & 63][slot].store(true, std::memory_order_release);
     }
     COUNT_LAUNCH();
-    onevn_chunks_kernel<<<1, 256, 0, st>>>(d_atomIdx, nAtoms, APC, maxChunks, hdr, kLo);
+    onevn_prep_kernel<<<1, 1024, 0, st>>>(setupRef, setupMass, nAtoms, const_cast<double*>(refw), const_cast<double*>(refsum),
+                                          const_cast<double*>(refw) + (size_t)4 * nAtoms, d_atomIdx, APC, maxChunks, hdr, kLo,
+                                          v2 ? partSum : nullptr);
     const int sms = numSMs > 0 ? numSMs : 148;
     if (v2) {
-      COUNT_LAUNCH();
-      onevn_parts_kernel<<<1, 256, 0, st>>>(refw + (size_t)4 * nAtoms, hdr, kLo, partSum);
       OneVN2Args sa;
       sa.crd = d_crd; sa.stride = stride; sa.frameIdx = d_frameIdx; sa.srcBase = srcBase; sa.nFrames = nFrames;
       sa.atomIdx = d_atomIdx; sa.nAtoms = nAtoms; sa.refmw = refw + (size_t)4 * nAtoms; sa.hdr = hdr; sa.kLo = kLo; sa.rec = rec;
@@ -1592,13 +1604,22 @@ static int onevn_run(int numSMs, const void* d_crd, size_t stride, int nFrames, 
       onevn_finish_kernel<<<(nFrames + 127) / 128, 128, 0, st>>>(rec, hdr, nFrames, refsum, fit, rmsd, rot, trans);
     }
   }
+  else if (setupRef) {
+    COUNT_LAUNCH();
+    onevn_setup_kernel<<<1, 256, 0, st>>>(setupRef, setupMass, nAtoms, const_cast<double*>(refw), const_cast<double*>(refsum),
+                                          const_cast<double*>(refw) + (size_t)4 * nAtoms);
+  }
   OneVNArgs a;
   a.crd = d_crd; a.stride = stride; a.frameIdx = d_frameIdx; a.srcBase = srcBase; a.nFrames = nFrames;
   a.atomIdx = d_atomIdx; a.nAtoms = nAtoms;
   a.refw = refw; a.refsum = refsum; a.skipIf = stream ? hdr : nullptr; a.fit = fit;
   a.rmsd = rmsd; a.rot = rot; a.trans = trans;
   COUNT_LAUNCH();
-  onevn_kernel<T><<<(nFrames + ONEVN_FB - 1) / ONEVN_FB, ONEVN_THREADS, 0, st>>>(a);
+  {   // the general kernel returns at once when the streaming path took the call: a small grid keeps that cheap
+    const int nGroups = (nFrames + ONEVN_FB - 1) / ONEVN_FB;
+    const int cap = 8 * (numSMs > 0 ? numSMs : 148);
+    onevn_kernel<T><<<stream ? std::min(nGroups, cap) : nGroups, ONEVN_THREADS, 0, st>>>(a);
+  }
   CU(cudaGetLastError());
   return B200_OK;
 }
@@ -1835,21 +1856,13 @@ int b200_dev_rmsd_1vN(const float* d_crd, size_t frameStrideFloats, int nFrames,
   if ((rc = d->onevnWs.reserve(refBytes + onevn_ws_bytes(frameStrideFloats, nFrames)))) return rc;
   double* refw = (double*)d->onevnWs.p;
   double* refsum = refw + (size_t)8 * nAtoms;
-  COUNT_LAUNCH();
-  onevn_setup_kernel<<<1, 256, 0, st>>>(d_refSelected, d_mass, nAtoms, refw, refsum, refw + (size_t)4 * nAtoms);
-  Timer t;
-  if (g_profiling) t.begin(st);
+  // (profiling: the events are only recorded here and resolved by b200_get_stats -- the call stays asynchronous)
+  if (g_profiling) { std::lock_guard<std::mutex> tl(g_streamMu); if (g_devPassTimer.begin(st)) { ++g_devPasses; g_devPassFrames += (double)nFrames; } }
   rc = onevn_run<float>(d->numSMs, d_crd, frameStrideFloats, nFrames, d_atomIdx, nAtoms, refw, refsum, fit ? 1 : 0, d_rmsdOut,
-                        fit ? d_rotOut : nullptr, fit ? d_transOut : nullptr, (char*)d->onevnWs.p + refBytes, st);
-  if (g_profiling) t.end(st);
-  if (rc) return rc;
-  if (g_profiling) {
-    CU(cudaStreamSynchronize(st));
-    const double ms = t.resolve();
-    std::lock_guard<std::mutex> sl(g_statMu);
-    g_stats.onevn_ms += ms; g_stats.onevn_launches += 1; g_stats.frames_1vN += (double)nFrames;
-  }
-  return B200_OK;
+                        fit ? d_rotOut : nullptr, fit ? d_transOut : nullptr, (char*)d->onevnWs.p + refBytes, st, nullptr, 0,
+                        d_refSelected, d_mass);
+  if (g_profiling) { std::lock_guard<std::mutex> tl(g_streamMu); g_devPassTimer.end(st); }
+  return rc;
 }
 
 
@@ -1959,11 +1972,9 @@ int host_centroids_on_device(Device& d, const float* crd, size_t stride, int nFr
     double* dist = (double*)(base + refBytes + wsBytes);
     t.begin(st);
     for (int k = 0; k < K; ++k) {
-      COUNT_LAUNCH();
-      onevn_setup_kernel<<<1, 256, 0, st>>>((const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass, nAtoms, refw, refsum,
-                                            refw + (size_t)4 * nAtoms);
       if ((rc = onevn_run<float>(d.numSMs, d_list0, width, nP, (const int*)d.idxA.p, nAtoms, refw, refsum, fit ? 1 : 0,
-                                 dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, rowBase))) return rc;
+                                 dist + (size_t)k * nP, nullptr, nullptr, ws, st, d_fidx, rowBase,
+                                 (const double*)d.crdB.p + (size_t)k * 3 * nAtoms, d_mass))) return rc;
     }
     COUNT_LAUNCH();
     centroid_argmin_kernel<<<(nP + 255) / 256, 256, 0, st>>>(dist, nP, K, distOut ? dOutT : nullptr, dClosest, dClosestDist);

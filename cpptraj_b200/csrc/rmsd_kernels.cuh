@@ -553,7 +553,10 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
   __shared__ double red[ONEVN_THREADS / 32][ONEVN_FB][14];
   if (a.skipIf && a.skipIf[2] != 0) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int fbase = blockIdx.x * ONEVN_FB;
+  const int nGroups = (a.nFrames + ONEVN_FB - 1) / ONEVN_FB;
+  for (int grp = blockIdx.x; grp < nGroups; grp += gridDim.x) {
+  if (grp != (int)blockIdx.x) __syncthreads();   // (red[] of the previous group has been read)
+  const int fbase = grp * ONEVN_FB;
   const T* crd = reinterpret_cast<const T*>(a.crd);
   const T* src[ONEVN_FB];
   double o[ONEVN_FB][3];
@@ -640,6 +643,7 @@ __global__ void __launch_bounds__(ONEVN_THREADS) onevn_kernel(OneVNArgs a) {
       }
     }
   }
+  }   // frame groups
 }
 
 // ----------------------------------------------------------------------------
@@ -682,35 +686,35 @@ struct OneVNStreamArgs {
 };
 
 /// Chunk table of the streaming kernel.  One block.  atomsPerChunk = ONEVN_S_CHUNK_BYTES / (3 * sizeof(T)).
-__global__ void __launch_bounds__(256) onevn_chunks_kernel(const int* atomIdx, int nAtoms, int atomsPerChunk, int maxChunks,
-                                                           int* hdr, int* kLo) {
-  __shared__ int sMin, sMax, sSorted;
-  if (threadIdx.x == 0) { sMin = 0x7fffffff; sMax = -1; sSorted = 1; }
+__device__ __forceinline__ void onevn_chunks_body(const int* atomIdx, int nAtoms, int atomsPerChunk, int maxChunks,
+                                                  int* hdr, int* kLo) {
+  // One pass, no dependent loads: a sorted selection starts at its first and ends at its last entry; atom k opens every
+  // chunk between its predecessor's chunk (exclusive) and its own (inclusive): kLo[c] = first k with atom >= a0 + c * APC.
+  __shared__ int sSorted;
+  if (threadIdx.x == 0) sSorted = 1;
   __syncthreads();
-  int mn = 0x7fffffff, mx = -1, ok = 1;
+  const int a0 = atomIdx ? atomIdx[0] : 0;
+  const int aMax = atomIdx ? atomIdx[nAtoms - 1] : nAtoms - 1;
+  const int nCh = aMax >= a0 ? (aMax - a0) / atomsPerChunk + 1 : 0;
+  int ok = (aMax >= a0) ? 1 : 0;
   for (int k = threadIdx.x; k < nAtoms; k += blockDim.x) {
     const int a = atomIdx ? atomIdx[k] : k;
-    mn = min(mn, a); mx = max(mx, a);
-    if (k + 1 < nAtoms && atomIdx && atomIdx[k + 1] <= a) ok = 0;
+    const int prev = k > 0 ? (atomIdx ? atomIdx[k - 1] : k - 1) : a0 - 1;
+    if (k > 0 && prev >= a) ok = 0;
+    if (a < a0 || a > aMax) { ok = 0; continue; }
+    const int cHi = (a - a0) / atomsPerChunk;
+    const int cLo = (k > 0 && prev >= a0) ? (prev - a0) / atomsPerChunk + 1 : 0;
+    for (int c = cLo; c <= cHi && c <= maxChunks; ++c) kLo[c] = k;
   }
-  atomicMin(&sMin, mn); atomicMax(&sMax, mx);
+  if (threadIdx.x == 0 && nCh >= 0 && nCh <= maxChunks) kLo[nCh] = nAtoms;
   if (!ok) atomicAnd(&sSorted, 0);
   __syncthreads();
-  const int a0 = sMin;
-  const int nCh = (sMax - sMin) / atomsPerChunk + 1;
-  const bool usable = sSorted && nCh <= maxChunks;
+  const bool usable = sSorted && nCh >= 1 && nCh <= maxChunks;
   if (threadIdx.x == 0) { hdr[0] = a0; hdr[1] = usable ? nCh : 0; hdr[2] = usable ? 1 : 0; }
-  if (!usable) return;
-  for (int c = threadIdx.x; c <= nCh; c += blockDim.x) {
-    const long target = (long)a0 + (long)c * atomsPerChunk;   // first k with atom >= target
-    int lo = 0, hi = nAtoms;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      const long a = atomIdx ? atomIdx[mid] : mid;
-      if (a < target) lo = mid + 1; else hi = mid;
-    }
-    kLo[c] = lo;
-  }
+}
+__global__ void __launch_bounds__(256) onevn_chunks_kernel(const int* atomIdx, int nAtoms, int atomsPerChunk, int maxChunks,
+                                                           int* hdr, int* kLo) {
+  onevn_chunks_body(atomIdx, nAtoms, atomsPerChunk, maxChunks, hdr, kLo);
 }
 
 constexpr int ONEVN_S_THREADS = 2 * ONEVN_THREADS;   // 16 warps: threads [0,256) take frames 0,1 of the stage, [256,512) frames 2,3
@@ -924,7 +928,8 @@ constexpr int ONEVN2_UNROLL = B200_ONEVN2_UNROLL;
 constexpr int ONEVN2_STAGE_BYTES = ONEVN2_FR * ONEVN2_BUF_BYTES;
 constexpr int ONEVN2_REF_BYTES = ONEVN2_MAX_APC * 32;            // (m rx, m ry, m rz, m) of the chunk's selected atoms
 constexpr int ONEVN2_IDX_BYTES = ONEVN2_MAX_APC * 4 + 32;
-constexpr int ONEVN2_SMEM_BYTES = ONEVN2_REF_BYTES + ONEVN2_IDX_BYTES + ONEVN2_STAGES * ONEVN2_STAGE_BYTES + 128;
+constexpr int ONEVN2_SMEM_BYTES = ONEVN2_REF_BYTES + ONEVN2_IDX_BYTES + ONEVN2_STAGES * ONEVN2_STAGE_BYTES + 128 +
+                                  ONEVN2_STAGES * 2 * ONEVN2_FR * 16 * 8;   // + the pair buffers
 constexpr int ONEVN2_CONSUMERS = 2 * ONEVN2_STAGES;             // warps: two per stage
 constexpr int ONEVN2_THREADS = 32 * (ONEVN2_CONSUMERS + 1);     // + the producer warp
 
@@ -957,16 +962,50 @@ __device__ __forceinline__ double onevn2_cvt(float v) {
 }
 __device__ __forceinline__ double onevn2_cvt(double v) { return v; }
 
+/// Sums 13 per-lane values over the warp; lane x (and x + 16) receives the total of v[x & 15] (0 for x & 15 >= 13).
+/// Halving exchange: at the step with lane mask 8 a lane keeps the half of the (zero-padded) 16 values that its bit 3
+/// selects and adds the partner's copy of that half, then 8 -> 4 -> 2 -> 1 values and one last exchange across the half
+/// warps: 16 shuffle+add pairs instead of the 65 of thirteen butterfly reductions.
+__device__ __forceinline__ double warp_transpose_sum13(const double (&v)[13], int lane) {
+  double a[8], b[4], c[2];
+  const bool u8 = (lane & 8) != 0, u4 = (lane & 4) != 0, u2 = (lane & 2) != 0, u1 = (lane & 1) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const double hi = (i + 8 < 13) ? v[i + 8] : 0.0;
+    const double keep = u8 ? hi : v[i], send = u8 ? v[i] : hi;
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const double keep = u4 ? a[i + 4] : a[i], send = u4 ? a[i] : a[i + 4];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const double keep = u2 ? b[i + 2] : b[i], send = u2 ? b[i] : b[i + 2];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  const double keep = u1 ? c[1] : c[0], send = u1 ? c[0] : c[1];
+  double r = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  r += __shfl_xor_sync(0xffffffffu, r, 16);
+  return r;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2Args a) {
   if (a.hdr[2] == 0) return;   // selection not sorted: onevn_kernel (launched later) does the work
   constexpr int APC = ONEVN2_CHUNK_BYTES / (3 * (int)sizeof(T));
   extern __shared__ __align__(128) unsigned char smem_o2[];
-  double4* sref = reinterpret_cast<double4*>(smem_o2);
+  // (m rx, m ry) and (m rz, m) of the chunk's selected atoms as two double2 arrays: a warp's 16-byte loads are then
+  // 16 bytes apart (conflict-free); as one double4 array they were 32 bytes apart, a 2-way bank conflict on every load
+  // (ncu, profiles/r2_onevn_stream2_kernel_ncu_raw.csv: 12.6 M conflict wavefronts of 37 M shared-load wavefronts)
+  double2* srefA = reinterpret_cast<double2*>(smem_o2);
+  double2* srefB = srefA + ONEVN2_MAX_APC;
   unsigned char* sidxRaw = smem_o2 + ONEVN2_REF_BYTES;
   unsigned char* ring = sidxRaw + ONEVN2_IDX_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + ONEVN2_STAGES * ONEVN2_STAGE_BYTES);
   uint64_t* empty = full + ONEVN2_STAGES;
+  double* pairBuf = reinterpret_cast<double*>(empty + ONEVN2_STAGES);   // [stage][parity][frame][16]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a0 = a.hdr[0], nCh = a.hdr[1];
   const int P = (int)gridDim.x / nCh;                    // CTAs per chunk (the host sizes the grid as nCh * P)
@@ -984,7 +1023,8 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
   }
   // the chunk's reference atoms and atom numbers: resident for the life of the CTA
   for (int i = tid; i < nSel; i += ONEVN2_THREADS) {
-    sref[i] = reinterpret_cast<const double4*>(a.refmw)[kA + i];
+    const double4 r4 = reinterpret_cast<const double4*>(a.refmw)[kA + i];
+    srefA[i] = make_double2(r4.x, r4.y); srefB[i] = make_double2(r4.z, r4.w);
     if (a.atomIdx) reinterpret_cast<int*>(sidxRaw)[i] = a.atomIdx[kA + i] - chunkA0;
   }
   __syncthreads();
@@ -1026,9 +1066,13 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
   const int h = warp & 1, myStage = warp >> 1;
   const int half0 = (nSel + 1) / 2;
   const int kBeg = h ? half0 : 0, kEnd = h ? nSel : half0;
-  const int part = 2 * c + h;
-  const int nParts = 2 * nCh;
-  for (int n = myStage; n < myPairs; n += ONEVN2_STAGES) {
+  // one record per (frame, chunk): the warp of the upper half hands its sums to the warp of the lower half through
+  // pairBuf (both use the chunk's first selected atom as origin, so the sums simply add); a 64-thread named barrier per
+  // frame pair, buffers alternating with the iteration parity
+  const int part = c;
+  const int nParts = nCh;
+  int iter = 0;
+  for (int n = myStage; n < myPairs; n += ONEVN2_STAGES, ++iter) {
     const int st = myStage;   // (n % STAGES == myStage by construction)
     mbar_wait(smem_u32(&full[st]), (uint32_t)((n / ONEVN2_STAGES) & 1));
     const unsigned char* sbuf = ring + st * ONEVN2_STAGE_BYTES;
@@ -1041,8 +1085,8 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
       const size_t row = a.frameIdx ? (size_t)((long)a.frameIdx[fr] - a.srcBase) : (size_t)fr;
       const size_t off = (row * a.stride + (size_t)3 * (size_t)chunkA0) * sizeof(T);
       fp[f] = reinterpret_cast<const T*>(sbuf + f * ONEVN2_BUF_BYTES + (off & 15));
-      // local origin: the first selected atom of this part (keeps the sums small, costs no global read)
-      const int at0 = a.atomIdx ? sidx[kBeg < kEnd ? kBeg : 0] : (kA + kBeg - chunkA0);
+      // local origin: the first selected atom of the chunk (keeps the sums small, costs no global read)
+      const int at0 = a.atomIdx ? sidx[0] : (kA - chunkA0);
       o[f][0] = onevn2_cvt(fp[f][3 * at0]); o[f][1] = onevn2_cvt(fp[f][3 * at0 + 1]); o[f][2] = onevn2_cvt(fp[f][3 * at0 + 2]);
     }
     double acc[ONEVN2_FR][13];
@@ -1053,7 +1097,8 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
 #pragma unroll ONEVN2_UNROLL
     for (int kk = kBeg + lane; kk < kEnd; kk += 32) {
       const int at = a.atomIdx ? sidx[kk] : (kA + kk - chunkA0);
-      const double4 rw = sref[kk];
+      const double2 rwa = srefA[kk], rwb = srefB[kk];
+      double4 rw; rw.x = rwa.x; rw.y = rwa.y; rw.z = rwb.x; rw.w = rwb.y;
 #pragma unroll
       for (int f = 0; f < ONEVN2_FR; ++f) {
         const T* p = fp[f] + 3 * at;
@@ -1068,31 +1113,36 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
     // the stage's bytes have been consumed: hand it back before the reduction
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[st]));
+    double mine[ONEVN2_FR];   // lane x keeps sum x (x < 13), lanes 13..15 the origin
 #pragma unroll
-    for (int f = 0; f < ONEVN2_FR; ++f) {
-      const int fr = f0 + f;
-      double mine = 0.0;      // lane x keeps sum x (x < 13), lanes 13..15 the origin
+    for (int f = 0; f < ONEVN2_FR; ++f) mine[f] = warp_transpose_sum13(acc[f], lane);
+    double* pb = pairBuf + ((myStage * 2 + (iter & 1)) * ONEVN2_FR) * 16;
+    if (h == 1 && lane < 13) {
 #pragma unroll
-      for (int x = 0; x < 13; ++x) {
-        const double v = warp_sum(acc[f][x]);
-        if (lane == x) mine = v;
+      for (int f = 0; f < ONEVN2_FR; ++f) pb[f * 16 + lane] = mine[f];
+    }
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + myStage) : "memory");
+    if (h == 0) {
+#pragma unroll
+      for (int f = 0; f < ONEVN2_FR; ++f) {
+        const int fr = f0 + f;
+        double v = mine[f];
+        if (lane < 13) v += pb[f * 16 + lane];
+        else if (lane < 16) v = o[f][lane - 13];
+        if (fr < a.nFrames && lane < 16) a.rec[((size_t)fr * nParts + part) * 16 + lane] = v;
       }
-      if (lane >= 13 && lane < 16) mine = o[f][lane - 13];
-      if (fr < a.nFrames && lane < 16) a.rec[((size_t)fr * nParts + part) * 16 + lane] = mine;
     }
   }
 }
 
 /// Per-part constants of the reference for onevn_finish2_kernel: partSum[p] = (sum m rx, sum m ry, sum m rz, sum m)
-/// over the selected atoms of part p = 2 * chunk + half.  One block.
-__global__ void __launch_bounds__(256) onevn_parts_kernel(const double* refmw, const int* hdr, const int* kLo, double* partSum) {
+/// over the selected atoms of part p = chunk p.  One block.
+__device__ __forceinline__ void onevn_parts_body(const double* refmw, const int* hdr, const int* kLo, double* partSum) {
   if (hdr[2] == 0) return;
-  const int nParts = 2 * hdr[1];
+  const int nParts = hdr[1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int p = warp; p < nParts; p += nw) {
-    const int c = p >> 1, h = p & 1;
-    const int kA = kLo[c], nSel = kLo[c + 1] - kA, half0 = (nSel + 1) / 2;
-    const int kb = kA + (h ? half0 : 0), ke = kA + (h ? nSel : half0);
+    const int kb = kLo[p], ke = kLo[p + 1];
     double s0 = 0, s1 = 0, s2 = 0, sm = 0;
     for (int k = kb + lane; k < ke; k += 32) {
       const double4 r = reinterpret_cast<const double4*>(refmw)[k];
@@ -1103,14 +1153,20 @@ __global__ void __launch_bounds__(256) onevn_parts_kernel(const double* refmw, c
   }
 }
 
-/// One thread per frame: the partial records of its parts, shifted to the origin of the first non-empty part and
-/// added up, then the same solve as onevn_finish_kernel.
+__global__ void __launch_bounds__(256) onevn_parts_kernel(const double* refmw, const int* hdr, const int* kLo, double* partSum) {
+  onevn_parts_body(refmw, hdr, kLo, partSum);
+}
+
+/// One thread per frame: the partial records of its parts (one per chunk), shifted to the origin of the first non-empty
+/// part and added up, then the same solve as onevn_finish_kernel.  (Measured alternatives: half a warp per frame with
+/// coalesced record loads and shuffles -- twice as slow: the solve's registers cap the occupancy and the part loop is a
+/// chain of dependent loads; 256 frames per block in two phases -- five times as slow: too few blocks.)
 __global__ void __launch_bounds__(128) onevn_finish2_kernel(const double* rec, const int* hdr, const int* kLo, const double* partSum,
                                                             int nFrames, const double* refsum, double* rmsd, double* rot, double* trans) {
   if (hdr[2] == 0) return;
   const int fr = blockIdx.x * blockDim.x + threadIdx.x;
   if (fr >= nFrames) return;
-  const int nParts = 2 * hdr[1];
+  const int nParts = hdr[1];
   const double M = refsum[3];
   if (M < 1e-14) { rmsd[fr] = -1.0; return; }   // src/Frame.cpp:1160-1163
   double v[13];
@@ -1119,12 +1175,12 @@ __global__ void __launch_bounds__(128) onevn_finish2_kernel(const double* rec, c
   double ox = 0.0, oy = 0.0, oz = 0.0;
   bool have = false;
   for (int p = 0; p < nParts; ++p) {
-    {   // parts without selected atoms wrote no (or an empty) record
-      const int nSel = kLo[(p >> 1) + 1] - kLo[p >> 1], half0 = (nSel + 1) / 2;
-      if (((p & 1) ? nSel - half0 : half0) <= 0) continue;
-    }
+    if (kLo[p + 1] - kLo[p] <= 0) continue;   // chunks without selected atoms wrote no record
     const double mp = partSum[4 * p + 3];
-    const double* r = rec + ((size_t)fr * nParts + p) * 16;
+    const double2* r2 = reinterpret_cast<const double2*>(rec + ((size_t)fr * nParts + p) * 16);
+    double r[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const double2 t = r2[i]; r[2 * i] = t.x; r[2 * i + 1] = t.y; }
     if (!have) { ox = r[13]; oy = r[14]; oz = r[15]; have = true; }
     const double dx = r[13] - ox, dy = r[14] - oy, dz = r[15] - oz;   // x - o* = (x - o_p) + d
     const double sx = partSum[4 * p], sy = partSum[4 * p + 1], sz = partSum[4 * p + 2];
@@ -1191,9 +1247,9 @@ __global__ void __launch_bounds__(256) centroid_argmin_rows_kernel(const float* 
 }
 
 /// refw[k] = (rx, ry, rz, m); refsum = (sum m r, M, sum m|r|^2).  One block.
-__global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum,
-                                                          double* refmw = nullptr) {
-  __shared__ double part[8][5];
+__device__ __forceinline__ void onevn_setup_body(const double* ref, const double* mass, int n, double* refw, double* refsum,
+                                                 double* refmw) {
+  __shared__ double part[32][5];
   double s0 = 0, s1 = 0, s2 = 0, sm = 0, sg = 0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const double m = mass ? mass[k] : 1.0;
@@ -1211,6 +1267,22 @@ __global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, con
     for (int i = 0; i < nw; ++i) t += part[i][threadIdx.x];   // fixed order: deterministic
     refsum[threadIdx.x] = t;
   }
+}
+
+__global__ void __launch_bounds__(256) onevn_setup_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum,
+                                                          double* refmw = nullptr) {
+  onevn_setup_body(ref, mass, n, refw, refsum, refmw);
+}
+/// Everything a one-vs-many pass needs before the streaming kernel, in ONE launch of one 1024-thread block (three
+/// single-block launches of 12-16 us each before): the reference set-up (skipped when ref == nullptr: a streaming handle
+/// did it when the reference was loaded), the chunk table, and -- variant 2, partSum != nullptr -- the per-part sums.
+__global__ void __launch_bounds__(1024) onevn_prep_kernel(const double* ref, const double* mass, int n, double* refw, double* refsum,
+                                                          double* refmw, const int* atomIdx, int atomsPerChunk, int maxChunks,
+                                                          int* hdr, int* kLo, double* partSum) {
+  if (ref) onevn_setup_body(ref, mass, n, refw, refsum, refmw);
+  onevn_chunks_body(atomIdx, n, atomsPerChunk, maxChunks, hdr, kLo);
+  __syncthreads();   // (refmw, hdr, kLo were written by this block: visible to it after the barrier)
+  if (partSum) onevn_parts_body(refmw, hdr, kLo, partSum);
 }
 
 // ----------------------------------------------------------------------------

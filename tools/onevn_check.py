@@ -28,4 +28,6 @@ e0.record()
 for _ in range(10): step()
 e1.record(); torch.cuda.synchronize()
 s = b.get_stats(); ms = e0.elapsed_time(e1) / 10
-print("  %.3f ms/pass  %.2f M frames/s  %.0f GB/s  (kernels %.3f ms)" % (ms, nF / ms / 1e3, 12.0 * nA * nF / ms / 1e6, s["onevn_ms"] / 10))
+print("  %.3f ms/pass  %.2f M frames/s  %.0f GB/s  (kernels %.3f ms, streaming kernel alone %.3f ms = %.0f GB/s)"
+      % (ms, nF / ms / 1e3, 12.0 * nA * nF / ms / 1e6, s["onevn_ms"] / 10, s["onevn_stream_ms"] / max(1, s["onevn_stream_launches"]),
+         12.0 * nA * nF / (s["onevn_stream_ms"] / max(1, s["onevn_stream_launches"])) / 1e6))
