@@ -581,14 +581,23 @@ def onevn_bench(ctx, name, cfg, steps, warmup, cpu_seconds):
     sel = np.arange(nA, dtype=np.int32)
     ref_raw = h_crd.numpy()[7].reshape(-1, 3).astype(np.float64)
     ref = ref_raw - ref_raw.mean(0)
-    d_crd = h_crd.cuda()
+    torch.cuda.empty_cache()
+    d_block = h_crd.cuda()
     d_sel = torch.from_numpy(sel).cuda()
     d_ref = torch.from_numpy(ref).cuda()
-    d_rms = torch.empty(blockF, dtype=torch.float64, device="cuda")
+    # the rank's whole share resident in HBM (the block replicated on the device: 60 GB for the million frames on one
+    # GPU) and ONE call per step over all of it; where that does not fit, one call per block
+    try:
+        d_crd = d_block.repeat(reps, 1) if reps > 1 else d_block
+        callF, calls = myF, 1
+    except RuntimeError:
+        torch.cuda.empty_cache()
+        d_crd, callF, calls = d_block, blockF, reps
+    d_rms = torch.empty(callF, dtype=torch.float64, device="cuda")
 
     def dev_pass():
-        for _ in range(reps):
-            b.dev_rmsd_1vN(d_crd, stride, blockF, d_sel, nA, d_ref, d_rms, stream=ctx.stream)
+        for _ in range(calls):
+            b.dev_rmsd_1vN(d_crd, stride, callF, d_sel, nA, d_ref, d_rms, stream=ctx.stream)
 
     for _ in range(max(1, warmup)):
         dev_pass()
@@ -612,13 +621,17 @@ def onevn_bench(ctx, name, cfg, steps, warmup, cpu_seconds):
     total_frames = myF * world
     value = total_frames * steps / (ms * 1e-3)
     # parity and argmin against the reference on the block (the million frames are the block repeated)
-    got = d_rms.cpu().numpy()
+    got_all = d_rms.cpu().numpy()
+    got = got_all[:blockF]
+    replicas_equal = bool(np.array_equal(got_all.reshape(-1, blockF), np.broadcast_to(got, (callF // blockF, blockF))))
     impl, kind, cores = cpu_impl()
     t0 = time.perf_counter()
     want = impl.rmsd_1vN(h_crd.numpy(), sel, ref_raw)
     cpu_dt = time.perf_counter() - t0
     parity = {"max_abs_diff_A": ctx.reduce(float(np.abs(got - want).max())), "argmin_ref": int(np.argmin(want)),
-              "checker": kind, "how": "all %d frames of the block against the reference's RMSD_CenteredRef" % blockF}
+              "checker": kind, "how": "all %d frames of the block against the reference's RMSD_CenteredRef; the other "
+                                      "replicas of the block bit-equal to the first: %s" % (blockF, replicas_equal)}
+    parity["replicas_bit_equal"] = replicas_equal
     # e2e: streamed from pinned host through the streaming handle (push / flush), argmin on the fly
     with b.Rmsd1vN(ref, sel, None, True, False) as h:
         def e2e_pass():
@@ -641,12 +654,12 @@ def onevn_bench(ctx, name, cfg, steps, warmup, cpu_seconds):
     # kernel, per-frame finish) is reported beside it
     k_launches = max(1, st["onevn_stream_launches"])
     k_ms = st["onevn_stream_ms"] / k_launches if st["onevn_stream_ms"] > 0 else st["onevn_ms"] / launches
-    gbs = 12.0 * nA * blockF / (k_ms * 1e-3) / 1e9
-    gbs_pass = 12.0 * nA * blockF / (st["onevn_ms"] / launches * 1e-3) / 1e9
+    gbs = 12.0 * nA * callF / (k_ms * 1e-3) / 1e9
+    gbs_pass = 12.0 * nA * callF / (st["onevn_ms"] / launches * 1e-3) / 1e9
     res = {
         "metric": "one-vs-many fitted RMSD frames/sec (rmsd action)", "unit": "frames/s",
         "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "dtype": "f64",
-        "config": {"workload": "%s: %s; %d frames per rank and step" % (name, cfg["what"], myF),
+        "config": {"workload": "%s: %s; %d frames per rank and step, %d call(s) of %d frames resident in HBM" % (name, cfg["what"], myF, calls, callF),
                    "sharding": "frames over %d rank(s), argmin = min over ranks" % world, "seed": cfg["seed"]},
         "e2e": {"value": total_frames / e2e_s, "unit": "frames/s", "ms_per_step": 1e3 * e2e_s,
                 "h2d_bytes_per_step": ctx.reduce(st2["h2d_bytes"] / max(1, min(steps, 3))),
@@ -654,13 +667,15 @@ def onevn_bench(ctx, name, cfg, steps, warmup, cpu_seconds):
                 "h2d_gbs_per_rank": 12.0 * nA * myF / e2e_s / 1e9,
                 "api": "b200_rmsd_1vN_push_f32 from pinned host + flush (PCIe-bound)"},
         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm if hbm else None,
-                     "traffic": 1.227e9 if (nA == 5000 and blockF == 20000) else None,
-                     "traffic_source": "from_profile: profiles/r2_onevn_stream2_kernel_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+                     "traffic": 1.214e9 * (callF / blockF) if (nA == 5000 and blockF == 20000) else None,
+                     "traffic_source": "from_profile: profiles/r2_onevn_stream2_kernel_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum "
+                                       "of one launch over one 20,000-frame block, scaled to the frames of a launch)",
+                     "frames_per_launch": callF,
                      "launches": int(st["onevn_stream_launches"]), "avg_launch_ms": k_ms,
                      "whole_pass": {"achieved": gbs_pass, "frac": gbs_pass / hbm if hbm else None, "avg_ms": st["onevn_ms"] / launches,
                                     "what": "chunk table + part sums + streaming kernel + per-frame finish kernel"},
                      "kernel": "onevn_stream2_kernel<float> (chunk-major: reference chunk resident in smem, frames through a 6-stage TMA ring, "
-                               "13 FP64 sums per frame and part)",
+                               "13 FP64 sums per frame and chunk)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth); achieved = 12*N bytes per frame (SURVEY 8d) / "
                                     "CUDA-event time of the streaming kernel",
                      "kernel_share_of_step": st["onevn_stream_ms"] / own if own > 0 else None},
