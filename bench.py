@@ -760,6 +760,51 @@ def cpptraj_leg(cfg, cpu_seconds):
             out["ratio"] = out["cpptraj_b200"]["value"] / out["cpptraj_omp"]["value"]
     else:
         out["cpptraj_omp"] = {"unavailable": "oracle/_ref/cpptraj_plain/cpptraj.OMP not staged"}
+    # ---- the two other cpptraj commands of the path that are dominated by device work: hierarchical clustering (cache
+    #      fill + every merge on the device) and rmsavgcorr (all window sizes); the unmodified binary gets a prefix
+    def run_deck(binary, text, env, pats):
+        open(os.path.join(w, "in"), "w").write(text)
+        t0 = time.perf_counter()
+        r = subprocess.run([binary, "-i", "in"], cwd=w, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+        res = {"wall_s": time.perf_counter() - t0}
+        if os.environ.get("B200_BENCH_CPPTRAJ_LOG"):
+            open(os.environ["B200_BENCH_CPPTRAJ_LOG"], "a").write("==== %s\n%s\n%s\n" % (binary, text, r.stdout))
+        if r.returncode != 0 or "Error" in r.stdout:
+            return {"error": r.stdout[-600:]}
+        for k, pat in pats.items():
+            m = re.search(pat, r.stdout)
+            if m:
+                res[k] = float(m.group(1))
+        return res
+
+    cores = host_cores()
+    omp_env = dict(os.environ, OMP_NUM_THREADS=str(cores))
+    cl_pats = {"pairwise_s": r"Pairwise Calc\.\s*:\s*([0-9.]+) s", "clustering_s": r"TIME:\s+Clustering\s*:\s*([0-9.]+) s",
+               "analyses_s": r"TIME: Analyses took ([0-9.]+) seconds", "device_merges_s": r"initial clusters on the device in ([0-9.]+) s"}
+    cl_deck = "noprogress\nparm t.pdb\ntrajin t.binpos 1 %d\ncluster C1 @CA hieragglo clusters 10 averagelinkage rms\nrun\n"
+    nB, nO = nF, min(nF, 1500)
+    out["cluster_hieragglo"] = {"deck": "cluster C1 @CA hieragglo clusters 10 averagelinkage rms (in-memory pairwise cache)",
+                                "cpptraj_b200": dict(run_deck(b200_bin, cl_deck % nB, dict(os.environ), cl_pats), frames=nB)}
+    if os.path.exists(omp_bin):
+        out["cluster_hieragglo"]["cpptraj_omp"] = dict(run_deck(omp_bin, cl_deck % nO, omp_env, cl_pats), frames=nO, threads=cores,
+                                                       note="the UNMODIFIED reference binary on the first %d frames; its merge loop "
+                                                            "costs O(cluster size x frames) cache reads per merge" % nO)
+    ra_pats = {"analyses_s": r"TIME: Analyses took ([0-9.]+) seconds", "device_s": r"frames on the device in ([0-9.]+) s"}
+    ra_deck = "noprogress\nparm t.pdb\ntrajin t.binpos 1 %d\nrmsavgcorr RA @CA first\nrun\n"
+    nB, nO = nF, min(nF, 2500)
+    rmsds = lambda n: n * (n + 1) / 2.0 - 1.0      # window sizes 1 .. n-1: sum of (n - W + 1)
+    out["rmsavgcorr"] = {"deck": "rmsavgcorr RA @CA first (every window size)", "unit": "averaged-frame RMSDs/s",
+                         "cpptraj_b200": dict(run_deck(b200_bin, ra_deck % nB, dict(os.environ), ra_pats), frames=nB)}
+    if out["rmsavgcorr"]["cpptraj_b200"].get("analyses_s"):
+        out["rmsavgcorr"]["cpptraj_b200"]["value"] = rmsds(nB) / out["rmsavgcorr"]["cpptraj_b200"]["analyses_s"]
+    if os.path.exists(omp_bin):
+        o = dict(run_deck(omp_bin, ra_deck % nO, omp_env, ra_pats), frames=nO, threads=cores,
+                 note="the UNMODIFIED reference binary on the first %d frames (cost ~ frames^2 x atoms)" % nO)
+        if o.get("analyses_s"):
+            o["value"] = rmsds(nO) / o["analyses_s"]
+            if out["rmsavgcorr"]["cpptraj_b200"].get("value"):
+                out["rmsavgcorr"]["ratio"] = out["rmsavgcorr"]["cpptraj_b200"]["value"] / o["value"]
+        out["rmsavgcorr"]["cpptraj_omp"] = o
     for f in os.listdir(w):
         os.remove(os.path.join(w, f))
     os.rmdir(w)

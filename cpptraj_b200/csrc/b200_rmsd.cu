@@ -92,7 +92,7 @@ struct Device {
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
   DevBuf imgA, imgB, cenA, cenB, dbgS;   // tcgen05 int8 path: operand images, frame centres
   DevBuf acP, acRms, acMisc;              // rmsavgcorr: prefix sums of the selected coordinates, RMSDs of a window batch, per-window data
-  DevBuf haD, haS, haMisc;                // hierarchical clustering: cluster-distance triangle, linkage sums, per-cluster state
+  DevBuf haTri, haD, haS, haMisc;         // hierarchical clustering: uploaded cache triangle, n x n cluster distances, linkage sums, per-cluster state
   PinBuf hostScal;                        // pinned slot for the few scalars read back per call
   int numSMs = 0;
   DevBuf outChunk[NSLOT];
@@ -120,7 +120,7 @@ struct Device {
       inStage[b].release();
     }
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
-                     &imgA, &imgB, &cenA, &cenB, &dbgS, &haD, &haS, &haMisc, &acP, &acRms, &acMisc};
+                     &imgA, &imgB, &cenA, &cenB, &dbgS, &haTri, &haD, &haS, &haMisc, &acP, &acRms, &acMisc};
     for (DevBuf* b : all) b->release();
     hostScal.release(); resBuf.release(); resHost = nullptr;
     pool.stop(); poolOut.stop();
@@ -2208,14 +2208,16 @@ int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetCluster
   cudaStream_t st = d.stream[0];
   const size_t n = (size_t)nFrames, nElt = n * (n - 1) / 2;
   double h2d = 0.0;
-  if ((rc = d.haD.reserve(nElt * sizeof(float)))) return rc;
+  if ((rc = d.haTri.reserve(nElt * sizeof(float)))) return rc;
   {   // the triangle as rows of 1 Mi floats (+ a remainder row): pinned -> DMA, pageable -> staged by the copy pool
     const size_t W = (size_t)1 << 20, rows = nElt / W, rem = nElt - rows * W;
     const bool pinned = host_ptr_is_pinned(tri);
-    if (rows && (rc = upload_rows(d, (float*)d.haD.p, tri, W, 0, (int)rows, W, pinned, st, &h2d))) return rc;
-    if (rem && (rc = upload_rows(d, (float*)d.haD.p + rows * W, tri + rows * W, rem, 0, 1, rem, pinned, st, &h2d))) return rc;
+    if (rows && (rc = upload_rows(d, (float*)d.haTri.p, tri, W, 0, (int)rows, W, pinned, st, &h2d))) return rc;
+    if (rem && (rc = upload_rows(d, (float*)d.haTri.p + rows * W, tri + rows * W, rem, 0, 1, rem, pinned, st, &h2d))) return rc;
   }
-  if (linkage == 1 && (rc = d.haS.reserve(nElt * sizeof(double)))) return rc;
+  // symmetric n x n working matrices (rows contiguous): 4 bytes per entry, + 8 for the sums of average linkage
+  if ((rc = d.haD.reserve(n * n * sizeof(float)))) return rc;
+  if (linkage == 1 && (rc = d.haS.reserve(n * n * sizeof(double)))) return rc;
   // per-cluster state, 256-byte aligned pieces of one allocation
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
   size_t off = 0;
@@ -2232,6 +2234,8 @@ int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetCluster
   const size_t oFrom = off;    off += up(n * sizeof(int));
   const size_t oFind = off;    off += up(n * sizeof(float));
   const size_t oIgn = off;     off += up(n);
+  const size_t oLb2 = off;     off += up(n * sizeof(float));
+  const size_t oRlb = off;     off += up(n * sizeof(unsigned int));
   const size_t oCtl = off;     off += up(sizeof(HaCtl));
   if ((rc = d.haMisc.reserve(off))) return rc;
   char* base = (char*)d.haMisc.p;
@@ -2242,15 +2246,13 @@ int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetCluster
   a.nfr = (int*)(base + oNfr); a.vnew = (float*)(base + oVnew); a.snew = (double*)(base + oSnew); a.oold = (float*)(base + oOold);
   a.listA = (int*)(base + oListA); a.listB = (int*)(base + oListB); a.ctl = (HaCtl*)(base + oCtl);
   a.mergeInto = (int*)(base + oInto); a.mergeFrom = (int*)(base + oFrom); a.findMin = (float*)(base + oFind);
-  ha_u64* keys = (ha_u64*)(base + oKeys);
-  a.rkey = keys;
-  CU(cudaMemsetAsync(keys, 0xff, n * sizeof(ha_u64), st));
-  const int initGrid = std::min<int>(nFrames - 1, d.numSMs * 8);
+  a.rkey = (ha_u64*)(base + oKeys); a.lb2 = (float*)(base + oLb2); a.rlb = (unsigned int*)(base + oRlb);
+  CU(cudaMemsetAsync(a.ign, 0, n, st));
   COUNT_LAUNCH();
-  hieragglo_init_kernel<<<initGrid, 256, 0, st>>>(a.D, nFrames, keys);
+  hieragglo_expand_kernel<<<std::min<int>(nFrames, d.numSMs * 16), 256, 0, st>>>((const float*)d.haTri.p, nFrames, a.D, a.S);
   CU(cudaGetLastError());
   COUNT_LAUNCH();
-  hieragglo_init2_kernel<<<d.numSMs * 4, 256, 0, st>>>(a, keys, nElt);
+  hieragglo_init_kernel<<<std::min<int>((nFrames + 7) / 8, d.numSMs * 16), 256, 0, st>>>(a);
   CU(cudaGetLastError());
   // one thread-block cluster runs every merge: CTAs per cluster from the cluster count (env B200_HA_TEAM overrides)
   int team = nFrames < 2048 ? 1 : nFrames < 8192 ? 4 : 16;   // (measured: 30,000 clusters, average linkage: 127 / 42 / 23 us per merge with 1 / 4 / 16 CTAs)

@@ -13,8 +13,14 @@
 // so a merge costs O(N).  Everything that decides WHICH pair merges is replicated exactly: FindMin takes the lowest
 // column among equal minima, a cluster's closest index changes only on a strictly smaller distance, is re-scanned
 // (lowest index among equal minima) when its closest distance grew or its closest cluster was merged away, and the
-// history-dependent tie case of the merged cluster's own closest index is replayed sequentially.
+// history-dependent tie case of the merged cluster's own closest index is replayed sequentially.  A re-scan (O(N)) is
+// skipped when its outcome is certain: every cluster keeps a lower bound lb2 of its distances to all clusters other
+// than its closest one (exact after a scan, only ever lowered in between); a new distance to the merged cluster that
+// is strictly below lb2 makes the merged cluster the closest whatever the scan would have found.
 //
+// Layout: the cluster distances live in a full symmetric n x n matrix (expanded once from the cache triangle), so the
+// two rows a merge combines and every row that has to be re-scanned are contiguous; an update writes the row and
+// (scattered) the column of the merged cluster.
 // Execution: ONE thread-block cluster (1..16 CTAs of 1024 threads) runs all merges in a single launch; the phases of a
 // merge are separated by cluster barriers (hardware barrier + acquire/release at cluster scope) instead of kernel
 // launches or grid-wide atomics: 3 barriers per merge in the common case.  Per merge each thread handles a strided slice
@@ -39,7 +45,7 @@ struct HaCtl {
 };
 
 struct HaArgs {
-  float* D;            // cluster-distance triangle (starts as the pairwise cache), src/Matrix.h:110-122 layout
+  float* D;            // cluster distances, symmetric n x n (row-major; the diagonal is unused)
   double* S;           // average linkage: sums of frame-pair distances (same layout), else null
   int n, linkage, target;
   double eps;
@@ -48,6 +54,8 @@ struct HaArgs {
   float* vnew; double* snew; float* oold;   // the merged cluster's new row, its sums, its old row
   int* listA; int* listB;
   ha_u64* rkey;        // per cluster: (distance, index) minimum of a pending re-scan, ~0 when none
+  unsigned int* rlb;   // ... and the second smallest distance of that re-scan (ordered bits), 0xffffffff when none
+  float* lb2;          // per cluster: a lower bound of its distances to every cluster other than closest[]
   HaCtl* ctl;
   int* mergeInto; int* mergeFrom; float* findMin;
 };
@@ -60,10 +68,6 @@ __device__ __forceinline__ float ha_unord(unsigned int u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 __device__ __forceinline__ ha_u64 ha_key(float v, int idx) { return ((ha_u64)ha_ord(v) << 32) | (unsigned int)idx; }
-__device__ __forceinline__ size_t ha_idx(int n, int a, int b) {
-  if (a > b) { int t = a; a = b; b = t; }
-  return (size_t)n * (size_t)a - ((size_t)a * ((size_t)a + 1)) / 2 + (size_t)b - (size_t)a - 1;
-}
 __device__ __forceinline__ ha_u64 ha_warp_min(ha_u64 k) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
@@ -89,14 +93,73 @@ __device__ __forceinline__ ha_u64 ha_block_min(ha_u64 k, ha_u64* sm) {
 
 constexpr int HA_U = 4;   // clusters per thread and batch: all loads of a batch are issued before the first use
 
-/// DynamicMatrix::updateClosestIdx (DynamicMatrix.h:43-62) for every row of a list, by the whole team: each thread scans a
-/// strided slice of every listed row (lowest index among the minima over the clusters still present); the minima meet in
-/// rkey[row] (64-bit atomicMin), to be read after the next cluster barrier.
+/// Smallest (distance, index) key and second smallest distance (ordered bits; 0xffffffff = none) of a set of entries.
+struct HaMin2 { ha_u64 best; unsigned int sec; };
+__device__ __forceinline__ void ha_m2_add(HaMin2& m, ha_u64 key) {
+  const ha_u64 hi = key < m.best ? m.best : key;
+  m.best = key < m.best ? key : m.best;
+  m.sec = min(m.sec, (unsigned int)(hi >> 32));
+}
+__device__ __forceinline__ HaMin2 ha_m2_merge(const HaMin2& x, const HaMin2& y) {
+  HaMin2 r;
+  const ha_u64 hi = x.best < y.best ? y.best : x.best;
+  r.best = x.best < y.best ? x.best : y.best;
+  r.sec = min(min(x.sec, y.sec), (unsigned int)(hi >> 32));
+  return r;
+}
+__device__ __forceinline__ HaMin2 ha_m2_warp(HaMin2 m) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    HaMin2 t;
+    t.best = __shfl_xor_sync(0xffffffffu, m.best, o);
+    t.sec = __shfl_xor_sync(0xffffffffu, m.sec, o);
+    m = ha_m2_merge(m, t);
+  }
+  return m;
+}
+__device__ __forceinline__ float ha_lb_of(unsigned int sec) { return sec == 0xffffffffu ? __int_as_float(0x7f800000) : ha_unord(sec); }
+
+/// One row's minimum and second minimum over the clusters still present, by one warp (the row is contiguous).
+__device__ __forceinline__ HaMin2 ha_warp_row_min(const HaArgs& a, int row, int lane) {
+  const int n = a.n;
+  const float* R = a.D + (size_t)row * n;
+  HaMin2 m; m.best = ~0ull; m.sec = 0xffffffffu;
+  for (int j0 = lane; j0 < n; j0 += 32 * HA_U) {
+    float v[HA_U]; unsigned char ig[HA_U];
+#pragma unroll
+    for (int u = 0; u < HA_U; ++u) {
+      const int j = j0 + 32 * u;
+      const bool in = j < n && j != row;
+      ig[u] = in ? a.ign[j] : (unsigned char)1;
+      v[u] = in ? R[j] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < HA_U; ++u)
+      if (!ig[u]) ha_m2_add(m, ha_key(v[u], j0 + 32 * u));
+  }
+  return ha_m2_warp(m);
+}
+
+/// DynamicMatrix::updateClosestIdx (DynamicMatrix.h:43-62) for every row of a list (lowest index among the minima over
+/// the clusters still present); the results go to rkey[row] / rlb[row], to be read after the next cluster barrier.  A
+/// short list: the whole team scans each row (one round of loads per row).  A long one (a big cluster was merged away
+/// and was the closest of many): one warp per row, all warps of the team side by side.
 __device__ __forceinline__ void ha_team_rescan(const HaArgs& a, const int* list, int nList, int tid, int nThr, ha_u64* sm) {
   const int n = a.n;
+  if (nList > 8) {
+    const int lane = threadIdx.x & 31, nWarps = nThr >> 5;
+    for (int e = tid >> 5; e < nList; e += nWarps) {
+      const int row = list[e];
+      const HaMin2 m = ha_warp_row_min(a, row, lane);
+      if (lane == 0) { a.rkey[row] = m.best; a.rlb[row] = m.sec; }
+    }
+    return;
+  }
+  unsigned int* smSec = reinterpret_cast<unsigned int*>(sm + 34);
   for (int e = 0; e < nList; ++e) {
     const int row = list[e];
-    ha_u64 best = ~0ull;
+    const float* R = a.D + (size_t)row * n;
+    HaMin2 m; m.best = ~0ull; m.sec = 0xffffffffu;
     for (int j0 = tid; j0 < n; j0 += nThr * HA_U) {
       float v[HA_U]; unsigned char ig[HA_U];
 #pragma unroll
@@ -104,23 +167,39 @@ __device__ __forceinline__ void ha_team_rescan(const HaArgs& a, const int* list,
         const int j = j0 + u * nThr;
         const bool in = j < n && j != row;
         ig[u] = in ? a.ign[j] : (unsigned char)1;
-        v[u] = in ? a.D[ha_idx(n, row, j)] : 0.f;
+        v[u] = in ? R[j] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < HA_U; ++u)
-        if (!ig[u]) { ha_u64 k = ha_key(v[u], j0 + u * nThr); best = k < best ? k : best; }
+        if (!ig[u]) ha_m2_add(m, ha_key(v[u], j0 + u * nThr));
     }
-    best = ha_block_min(best, sm);
-    if (threadIdx.x == 0 && best != ~0ull) atomicMin(&a.rkey[row], best);
+    m = ha_m2_warp(m);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m.best; smSec[threadIdx.x >> 5] = m.sec; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      HaMin2 t;
+      const bool have = threadIdx.x < (blockDim.x >> 5);
+      t.best = have ? sm[threadIdx.x] : ~0ull; t.sec = have ? smSec[threadIdx.x] : 0xffffffffu;
+      t = ha_m2_warp(t);
+      if (threadIdx.x == 0 && t.best != ~0ull) {
+        // every key that does not end up as the row's minimum passes through here as a candidate for the second minimum
+        const ha_u64 old = atomicMin(&a.rkey[row], t.best);
+        const ha_u64 loser = old < t.best ? t.best : old;
+        atomicMin(&a.rlb[row], min(t.sec, (unsigned int)(loser >> 32)));
+      }
+    }
   }
 }
-/// Takes a re-scan result out of rkey[row] (and re-arms the slot).
-__device__ __forceinline__ void ha_take_rescan(const HaArgs& a, int row, int& closest, float& cmin) {
+/// Takes a re-scan result out of rkey[row] / rlb[row] (and re-arms the slots).
+__device__ __forceinline__ void ha_take_rescan(const HaArgs& a, int row, int& closest, float& cmin, float& lb) {
   const ha_u64 k = a.rkey[row];
-  a.rkey[row] = ~0ull;
+  const unsigned int sec = a.rlb[row];
+  a.rkey[row] = ~0ull; a.rlb[row] = 0xffffffffu;
   closest = (k == ~0ull) ? -1 : (int)(unsigned int)k;
   cmin = (k == ~0ull) ? __int_as_float(0x7f800000) : ha_unord((unsigned int)(k >> 32));
-  a.closest[row] = closest; a.cmin[row] = cmin;
+  lb = ha_lb_of(sec);
+  a.closest[row] = closest; a.cmin[row] = cmin; a.lb2[row] = lb;
 }
 
 /// The col-side sequence of SetCdist(C1, k, v_k), k ascending (DynamicMatrix.h:65-113), replayed by one warp: needed only
@@ -169,14 +248,14 @@ __device__ __forceinline__ void ha_tie_replay(const HaArgs& a, int C1, int C2) {
       if (start >= 32) break;
     }
   }
-  if (lane == 0) { a.closest[C1] = c; a.cmin[C1] = a.vnew[c]; }
+  if (lane == 0) { a.closest[C1] = c; a.cmin[C1] = a.vnew[c]; a.lb2[C1] = a.vnew[c]; }
 }
 
 /// All merges in one launch.  Launch with ONE cluster of `team` CTAs x 1024 threads.
 template <int LINK>
 __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
   cg::cluster_group team = cg::this_cluster();
-  __shared__ ha_u64 sm[34];
+  __shared__ ha_u64 sm[34 + 16];   // block reductions (+ 32 second minima)
   const int nCta = (int)team.num_blocks();
   const int cta = (int)team.block_rank();
   const int tid = cta * blockDim.x + threadIdx.x;
@@ -208,8 +287,8 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
       for (int u = 0; u < HA_U; ++u) {
         const int col = c0 + u * nThr;
         if (ig[u]) continue;
-        if (col == prevC1) { cm[u] = prevV; cl[u] = prevK; a.closest[col] = prevK; a.cmin[col] = prevV; }
-        else if (cl[u] == -2) ha_take_rescan(a, col, cl[u], cm[u]);
+        if (col == prevC1) { cm[u] = prevV; cl[u] = prevK; a.closest[col] = prevK; a.cmin[col] = prevV; a.lb2[col] = prevV; }
+        else if (cl[u] == -2) { float lbTmp; ha_take_rescan(a, col, cl[u], cm[u], lbTmp); }
         if (cl[u] < 0) continue;
         ha_u64 k = ha_key(cm[u], col);
         best = k < best ? k : best;
@@ -237,14 +316,15 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
     // ---- new row of the merged cluster; clusters whose closest was C2 are queued for Ignore()'s re-scan
     best = ~0ull;
     for (int k0 = tid; k0 < n; k0 += nThr * HA_U) {
-      unsigned char ig[HA_U]; float o1[HA_U], o2[HA_U]; double s1[HA_U], s2[HA_U]; int cl[HA_U], nf[HA_U];
+      unsigned char ig[HA_U]; float o1[HA_U], o2[HA_U], lb[HA_U]; double s1[HA_U], s2[HA_U]; int cl[HA_U], nf[HA_U];
 #pragma unroll
       for (int u = 0; u < HA_U; ++u) {
         const int k = k0 + u * nThr;
         const bool in = k < n && k != C1 && k != C2;
         ig[u] = in ? a.ign[k] : (unsigned char)1;
         cl[u] = in ? a.closest[k] : -1;
-        const size_t i1 = in ? ha_idx(n, C1, k) : 0, i2 = in ? ha_idx(n, C2, k) : 0;
+        lb[u] = in ? a.lb2[k] : 0.f;
+        const size_t i1 = in ? (size_t)C1 * n + k : 0, i2 = in ? (size_t)C2 * n + k : 0;
         o1[u] = a.D[i1]; o2[u] = a.D[i2];
         if (LINK == 1) { s1[u] = a.S[i1]; s2[u] = a.S[i2]; nf[u] = in ? a.nfr[k] : 1; }
       }
@@ -261,7 +341,12 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
           v = (float)(sum / (double)(n1 * nf[u]));
         }
         a.vnew[k] = v; a.oold[k] = o1[u];
-        if (cl[u] == C2) a.listA[atomicAdd((int*)&a.ctl->nA[p], 1)] = k;
+        if (cl[u] == C2) {
+          // Ignore(C2) would re-scan this row and SetCdist(C1, k, v) compare v with what it found: below the bound on
+          // every other distance the merged cluster is the closest whatever the scan finds
+          if (v < lb[u]) { a.closest[k] = C1; a.cmin[k] = v; }
+          else a.listA[atomicAdd((int*)&a.ctl->nA[p], 1)] = k;
+        }
         ha_u64 key = ha_key(v, k);
         best = key < best ? key : best;
       }
@@ -282,7 +367,7 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
     const ha_u64 rk = ctl->rowKey[p];
     const unsigned int vminOrd = (unsigned int)(rk >> 32);
     for (int k0 = tid; k0 < n; k0 += nThr * HA_U) {
-      unsigned char ig[HA_U]; float v[HA_U], cd[HA_U]; int ck[HA_U]; double sn[HA_U];
+      unsigned char ig[HA_U]; float v[HA_U], cd[HA_U], lb[HA_U]; int ck[HA_U]; double sn[HA_U];
 #pragma unroll
       for (int u = 0; u < HA_U; ++u) {
         const int k = k0 + u * nThr;
@@ -290,6 +375,7 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
         ig[u] = in ? a.ign[k] : (unsigned char)1;
         v[u] = in ? a.vnew[k] : 0.f;
         cd[u] = in ? a.cmin[k] : 0.f;
+        lb[u] = in ? a.lb2[k] : 0.f;
         ck[u] = in ? a.closest[k] : -1;
         if (LINK == 1) sn[u] = in ? a.snew[k] : 0.0;
       }
@@ -297,15 +383,19 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
       for (int u = 0; u < HA_U; ++u) {
         const int k = k0 + u * nThr;
         if (ig[u]) continue;
-        if (ck[u] == C2) ha_take_rescan(a, k, ck[u], cd[u]);   // Ignore()'s re-scan of this row
-        if (ck[u] < 0 || v[u] < cd[u]) { a.closest[k] = C1; a.cmin[k] = v[u]; }
-        else if (ck[u] == C1 && v[u] > cd[u]) {   // its closest distance grew: re-scan after the update
-          a.closest[k] = -2;
-          a.listB[atomicAdd((int*)&a.ctl->nB[p], 1)] = k;
-        }
-        const size_t i1 = ha_idx(n, C1, k);
-        a.D[i1] = v[u];
-        if (LINK == 1) a.S[i1] = sn[u];
+        if (ck[u] == C2) ha_take_rescan(a, k, ck[u], cd[u], lb[u]);   // Ignore()'s re-scan of this row
+        if (ck[u] < 0 || v[u] < cd[u]) {
+          if (ck[u] >= 0 && ck[u] != C1) a.lb2[k] = fminf(lb[u], cd[u]);   // the old closest is now one of the others
+          a.closest[k] = C1; a.cmin[k] = v[u];
+        } else if (ck[u] == C1) {
+          if (v[u] > cd[u]) {   // its closest distance grew
+            if (v[u] < lb[u]) a.cmin[k] = v[u];   // still strictly below every other distance: no re-scan
+            else { a.closest[k] = -2; a.listB[atomicAdd((int*)&a.ctl->nB[p], 1)] = k; }
+          }
+        } else if (v[u] < lb[u]) a.lb2[k] = v[u];   // a distance to a cluster other than the closest one
+        const size_t i1 = (size_t)C1 * n + k, i2 = (size_t)k * n + C1;
+        a.D[i1] = v[u]; a.D[i2] = v[u];
+        if (LINK == 1) { a.S[i1] = sn[u]; a.S[i2] = sn[u]; }
         if (ha_ord(v[u]) == vminOrd) atomicAdd((int*)&a.ctl->tieCount[p], 1);
       }
     }
@@ -328,36 +418,36 @@ __global__ void __launch_bounds__(1024, 1) hieragglo_kernel(HaArgs a) {
   }
 }
 
-/// closest / cmin of the initial matrix: one pass over the triangle, (distance, index) minima by 64-bit atomicMin.
-__global__ void __launch_bounds__(256) hieragglo_init_kernel(const float* __restrict__ D, int n, ha_u64* keys) {
-  __shared__ ha_u64 sm[34];
-  for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
+/// The symmetric n x n matrix from the cache triangle (src/Matrix.h:110-122): block i copies row i of the triangle
+/// (contiguous) to D[i][i+1..] and, scattered, to D[i+1..][i].
+__global__ void __launch_bounds__(256) hieragglo_expand_kernel(const float* __restrict__ tri, int n, float* __restrict__ D,
+                                                               double* __restrict__ S) {
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
     const size_t base = (size_t)n * (size_t)i - ((size_t)i * ((size_t)i + 1)) / 2 - (size_t)i - 1;   // + j
-    ha_u64 best = ~0ull;
+    if (threadIdx.x == 0) { D[(size_t)i * n + i] = 0.f; if (S) S[(size_t)i * n + i] = 0.0; }
     for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
-      const float v = D[base + j];
-      ha_u64 kr = ha_key(v, j);
-      best = kr < best ? kr : best;
-      ha_u64 kc = ha_key(v, i);
-      if (kc < *(volatile ha_u64*)&keys[j]) atomicMin(&keys[j], kc);
+      const float v = tri[base + j];
+      D[(size_t)i * n + j] = v; D[(size_t)j * n + i] = v;
+      if (S) { S[(size_t)i * n + j] = (double)v; S[(size_t)j * n + i] = (double)v; }
     }
-    best = ha_block_min(best, sm);
-    if (threadIdx.x == 0 && best != ~0ull) atomicMin(&keys[i], best);
   }
 }
-__global__ void hieragglo_init2_kernel(HaArgs a, ha_u64* keys, size_t nElt) {
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t nT = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = t; i < (size_t)a.n; i += nT) {
-    ha_u64 k = keys[i];
-    a.closest[i] = (k == ~0ull) ? -1 : (int)(unsigned int)k;
-    a.cmin[i] = (k == ~0ull) ? __int_as_float(0x7f800000) : ha_unord((unsigned int)(k >> 32));
-    a.ign[i] = 0; a.nfr[i] = 1;
-    keys[i] = ~0ull;   // from here on the buffer is rkey: pending re-scan results
+/// closest / cmin of the initial matrix (one warp per row: lowest index among the minima, as the sequence of SetCdist
+/// calls of the initial build leaves it) and the per-cluster state.
+__global__ void __launch_bounds__(256) hieragglo_init_kernel(HaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nW = (gridDim.x * blockDim.x) >> 5;
+  for (int i = w; i < a.n; i += nW) {
+    const HaMin2 m = ha_warp_row_min(a, i, lane);
+    if (lane == 0) {
+      const ha_u64 k = m.best;
+      a.closest[i] = (k == ~0ull) ? -1 : (int)(unsigned int)k;
+      a.cmin[i] = (k == ~0ull) ? __int_as_float(0x7f800000) : ha_unord((unsigned int)(k >> 32));
+      a.lb2[i] = ha_lb_of(m.sec);
+      a.nfr[i] = 1; a.rkey[i] = ~0ull; a.rlb[i] = 0xffffffffu;
+    }
   }
-  if (a.S != nullptr)
-    for (size_t e = t; e < nElt; e += nT) a.S[e] = (double)a.D[e];
-  if (t == 0) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
     a.ctl->minKey[0] = a.ctl->minKey[1] = ~0ull; a.ctl->rowKey[0] = a.ctl->rowKey[1] = ~0ull;
     a.ctl->tieCount[0] = a.ctl->tieCount[1] = 0; a.ctl->nA[0] = a.ctl->nA[1] = 0; a.ctl->nB[0] = a.ctl->nB[1] = 0;
     a.ctl->nCalls = 0; a.ctl->nMerges = 0; a.ctl->stopped = 0;

@@ -185,7 +185,8 @@ int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, con
  * *nMerges = merges (nCalls - 1 when the last call stopped on epsilon).  The caller replays the merges on its cluster
  * list (Node::MergeFrames, List::RemoveCluster).  Which pair merges, ties included, is the reference's choice exactly;
  * single and complete linkage distances are exact, average-linkage sums are kept in double (see hieragglo.cuh).
- * Device memory: 4 bytes per pair, 12 for average linkage.  Runs on device 0. */
+ * Device memory: the uploaded triangle plus a symmetric nFrames x nFrames working matrix, 4 bytes per entry (12 for
+ * average linkage: 50,000 frames = 5 + 10 (+ 20) GB).  Runs on device 0. */
 int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetClusters, double epsilon,
                    int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges);
 
