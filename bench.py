@@ -18,8 +18,10 @@ One JSON line is printed by rank 0:
     value      whole job, inputs (raw float32 COORDS) resident in HBM, CUDA events on the launching stream
     e2e        same metric through the C ABI with pinned HOST buffers: H2D of the COORDS, kernels, D2H of the result inside
                the timed region; `host_ceiling` = what N ranks copying device -> pinned host at once reach on this box
-               (measured here), `frac_of_d2h_ceiling` = the run's own D2H rate against it; `pageable` = the same call with
-               the pageable / never-touched buffers cpptraj passes (N == 1)
+               (measured here), `frac_of_d2h_ceiling` = the run's own D2H rate against it; `host_ceiling.duplex_ms` = the time
+               the box needs to move one step's H2D and D2H bytes at the same time with nothing else running (the two
+               directions of the link slow each other down) and `copy_floor_frac` = that floor / the step's e2e time;
+               `pageable` = the same call with the pageable / never-touched buffers cpptraj passes (N == 1)
     roofline   dominant kernel (tcgen05 int8 pair kernel when eligible, else FP64 DMMA; one-vs-many streaming kernel for
                cfg3): algorithmic work / CUDA-event kernel time against a peak measured live by a probe kernel
     parity     every rank checks sampled rows of ITS OWN band (24 rows x up to 2,048 columns) of the e2e result against the
@@ -307,7 +309,7 @@ class Ctx:
         return float(t.item())
 
 
-def host_ceiling(ctx, nbytes):
+def host_ceiling(ctx, nbytes, h2d_bytes=0, d2h_bytes=0):
     """All ranks copy device -> pinned host (then host -> device) at the same time: aggregate GB/s of this box."""
     torch = ctx.torch
     n = int(min(nbytes, 2 << 30))
@@ -325,6 +327,27 @@ def host_ceiling(ctx, nbytes):
         out[name] = ctx.reduce(float(n), "sum") / best / 1e9
     del dev, pin
     torch.cuda.empty_cache()
+    # both directions at once, with this rank's own byte counts of one step: the time the box needs merely to move a
+    # step's inputs in and its results out over a full-duplex link (the two directions slow each other down)
+    if h2d_bytes and d2h_bytes:
+        hn, dn = int(min(h2d_bytes, 4 << 30)), int(min(d2h_bytes, 4 << 30))
+        d_in = torch.empty(hn, dtype=torch.uint8, device="cuda"); p_in = torch.empty(hn, dtype=torch.uint8, pin_memory=True)
+        d_out = torch.empty(dn, dtype=torch.uint8, device="cuda"); p_out = torch.empty(dn, dtype=torch.uint8, pin_memory=True)
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        best = 1e9
+        for _ in range(3):
+            ctx.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(s1):
+                d_in.copy_(p_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                p_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            best = min(best, ctx.reduce(time.perf_counter() - t0))
+        out["duplex_ms"] = 1e3 * best * (h2d_bytes / hn)
+        del d_in, p_in, d_out, p_out
+        torch.cuda.empty_cache()
     return out
 
 
@@ -489,7 +512,7 @@ def tri_bench(ctx, name, cfg, steps, warmup, cpu_seconds, light=False):
     chk2 = float(h_out[: min(nelt, 1 << 20)].double().sum().item()) if nelt else 0.0
     if abs(chk - chk2) > 1e-3 * max(1.0, abs(chk)):
         raise RuntimeError("device-resident and host-path results disagree: %r vs %r" % (chk, chk2))
-    ceil = host_ceiling(ctx, nelt * 4)
+    ceil = host_ceiling(ctx, nelt * 4, st2["h2d_bytes"] / steps, st2["d2h_bytes"] / steps)
     d2h_rate = d2h_total / (e2e_s / steps) / 1e9
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": 1e3 * e2e_s / steps,
@@ -497,6 +520,11 @@ def tri_bench(ctx, name, cfg, steps, warmup, cpu_seconds, light=False):
            "host_ceiling": {"d2h_gbs": ceil["d2h"], "h2d_gbs": ceil["h2d"],
                             "how": "all %d rank(s) copy device <-> pinned host at the same time, best of 3" % world},
            "d2h_gbs_all_ranks": d2h_rate, "frac_of_d2h_ceiling": d2h_rate / ceil["d2h"] if ceil["d2h"] > 0 else None}
+    if ceil.get("duplex_ms"):
+        e2e["host_ceiling"]["duplex_ms"] = ceil["duplex_ms"]
+        e2e["host_ceiling"]["duplex_how"] = ("every rank copies one step's own H2D and D2H bytes at the same time, on two streams, nothing else "
+                                             "running: the floor of a step's end-to-end time on this box")
+        e2e["copy_floor_frac"] = ceil["duplex_ms"] / (1e3 * e2e_s / steps)
 
     # =================== parity: every rank, rows of its own band, against the reference's own arithmetic ===================
     parity = None
@@ -817,7 +845,7 @@ def summary(res):
     keep["metric"], keep["unit"] = keep["metric"] or METRIC, keep["unit"] or UNIT
     keep["workload"] = res["config"]["workload"]
     e = res["e2e"]
-    keep["e2e"] = {k: e.get(k) for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "frac_of_d2h_ceiling",
+    keep["e2e"] = {k: e.get(k) for k in ("value", "ms_per_step", "h2d_bytes_per_step", "d2h_bytes_per_step", "frac_of_d2h_ceiling", "copy_floor_frac",
                                          "host_ceiling", "h2d_gbs_per_rank") if k in e}
     r = res["roofline"]
     keep["roofline"] = {k: r.get(k) for k in ("bound", "achieved", "peak", "unit", "frac", "executed", "frac_executed", "engine") if k in r}

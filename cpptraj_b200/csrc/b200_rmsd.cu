@@ -87,6 +87,7 @@ constexpr int NIN = 2;     // pinned ring slots for staged uploads of pageable C
 struct Device {
   int id = -1;
   cudaStream_t stream[NSLOT] = {};
+  cudaStream_t copyIn = nullptr;          // uploads of the pipelined host path: DMA back to back, never behind a kernel
   cudaEvent_t done[NSLOT] = {};
   // workspaces (grow-only)
   DevBuf crd, crdB, idxA, idxB, frameIdx, massA, massB, planesA, planesB, GA, GB, scal, onevnWs;
@@ -114,6 +115,8 @@ struct Device {
       stream[s] = nullptr; done[s] = nullptr;
       outChunk[s].release(); outStage[s].release();
     }
+    if (copyIn) cudaStreamDestroy(copyIn);
+    copyIn = nullptr;
     for (int b = 0; b < NIN; ++b) {
       if (inFree[b]) cudaEventDestroy(inFree[b]);
       inFree[b] = nullptr; inUsed[b] = false;
@@ -229,6 +232,7 @@ int init_device(Device& d, int id) {
     CU(cudaEventCreateWithFlags(&d.done[s], cudaEventDisableTiming));
   }
   for (int b = 0; b < NIN; ++b) CU(cudaEventCreateWithFlags(&d.inFree[b], cudaEventDisableTiming));
+  CU(cudaStreamCreateWithFlags(&d.copyIn, cudaStreamNonBlocking));
   return B200_OK;
 }
 
@@ -958,7 +962,9 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
   OutRing ring(d, outTri, host_ptr_is_pinned(outFirst), outFirst, outElts, true);
   // (ring slots are reserved at first use: in a fresh process pinning slot k+1 overlaps the work queued for slot k)
   std::vector<cudaEvent_t> evs;
-  auto cleanup = [&]() { for (cudaEvent_t e : evs) cudaEventDestroy(e); evs.clear(); };
+  cudaStream_t sCopy = d.copyIn;
+  // (every exit: the uploads queued ahead have left the caller's buffer and the device copy is quiescent)
+  auto cleanup = [&]() { cudaStreamSynchronize(sCopy); for (cudaEvent_t e : evs) cudaEventDestroy(e); evs.clear(); };
   const float* d_crd = (const float*)d.crd.p;
   const long srcBase = (long)f0;      // row r of the device copy is frame f0 + r
   Timer tpair;
@@ -967,9 +973,45 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
   const bool pinnedScale = qs > 0;
   if (pinnedScale && i8_worst_error(qs, nAtoms, total) > I8_MAX_WORST_ERROR) return B200_OK;
   long nLaunch = 0;
+  // B200_PIPE_TRACE=1: a time line of the pipeline on stderr (events after every upload, band kernel and download)
+  static const bool trace = getenv("B200_PIPE_TRACE") != nullptr;
+  struct TraceEv { cudaEvent_t e; int chunk; char what; };
+  std::vector<TraceEv> tev;
+  cudaEvent_t tStart = nullptr;
+  auto mark = [&](cudaStream_t strm, int chunk, char what) {
+    if (!trace) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, strm); tev.push_back({e, chunk, what});
+  };
+  if (trace) { cudaEventCreate(&tStart); cudaEventRecord(tStart, sIn); }
+  // Uploads go through a stream of their own, chunk after chunk without a kernel in between (on the stream that also
+  // carries the statistics / quantisation kernels the next copy waited for those, and those for SMs the band kernels
+  // hold: measured, the 120 MB of cfg2 took 4.1 ms instead of 2.2).  Pinned COORDS: every copy is queued up front;
+  // pageable: the copy pool stages one chunk ahead of the kernels.
+  std::vector<cudaEvent_t> evUp(chunks.size(), nullptr);
+  size_t nextUp = 0;
+  {   // order after whatever the caller's earlier calls left on sIn (selection and mass uploads above are on sIn)
+    cudaEvent_t e0;
+    CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+    evs.push_back(e0);
+    CU(cudaEventRecord(e0, sIn));
+    CU(cudaStreamWaitEvent(sCopy, e0, 0));
+  }
+  auto enqueue_upload = [&](size_t k) -> int {
+    const int fa = chunks[k].fa, fb = chunks[k].fb;
+    int r = upload_rows(d, (float*)d.crd.p + (size_t)(fa - f0) * width, crd, stride, fa, fb, width, pinnedIn, sCopy, &h2d);
+    if (r) return r;
+    CU(cudaEventCreateWithFlags(&evUp[k], cudaEventDisableTiming));
+    evs.push_back(evUp[k]);
+    CU(cudaEventRecord(evUp[k], sCopy));
+    mark(sCopy, (int)k, 'U');
+    return B200_OK;
+  };
   for (size_t k = 0; k < chunks.size(); ++k) {
     const int fa = chunks[k].fa, fb = chunks[k].fb;
-    if ((rc = upload_rows(d, (float*)d.crd.p + (size_t)(fa - f0) * width, crd, stride, fa, fb, width, pinnedIn, sIn, &h2d))) { cleanup(); return rc; }
+    const size_t upTo = pinnedIn ? chunks.size() : std::min(chunks.size(), k + 2);
+    for (; nextUp < upTo; ++nextUp)
+      if ((rc = enqueue_upload(nextUp))) { cleanup(); return rc; }
+    CU(cudaStreamWaitEvent(sIn, evUp[k], 0));
     if ((rc = i8_stats(q, d_crd, width, nullptr, srcBase, fa, (const int*)d.idxA.p, nAtoms, d_mass, d_mass, d_maxBits, sIn, fb))) { cleanup(); return rc; }
     if (k == 0 && !pinnedScale) {
       // scale from the top chunk, with headroom for the frames not seen yet
@@ -998,8 +1040,10 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     tpair.begin(st);
     if ((rc = run_pair_i8_band(d, q, q, lo, hi, true, qs, d_total, (float*)d.outChunk[s].p, base, 0, nullptr, st))) { cleanup(); return rc; }
     tpair.end(st);
+    mark(st, (int)k, 'K');
     ++nLaunch;
     if ((rc = ring.download(s, base, n, st))) { cleanup(); return rc; }
+    mark(st, (int)k, 'D');
   }
   // did the scale hold for every frame?
   {
@@ -1007,9 +1051,20 @@ int host_tri_pipelined_i8(Device& d, const float* crd, size_t stride, int nFrame
     unsigned int* hBits = (unsigned int*)d.hostScal.p;
     CU(cudaMemcpyAsync(hBits, d_maxBits, sizeof(unsigned int), cudaMemcpyDeviceToHost, sIn));
     CU(cudaStreamSynchronize(sIn));
+    CU(cudaStreamSynchronize(sCopy));
     if ((rc = ring.drain())) { cleanup(); return rc; }
     for (int s = 1; s < NSLOT; ++s) CU(cudaStreamSynchronize(d.stream[s]));
     cleanup();
+    if (trace) {
+      fprintf(stderr, "pipeline trace (ms after the first enqueue; U upload done, K band kernel done, D download done; rows of the chunk):\n");
+      for (const TraceEv& t : tev) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, tStart, t.e);
+        fprintf(stderr, "  %c chunk %2d [%5d,%5d) %.3f\n", t.what, t.chunk, chunks[t.chunk].fa, chunks[t.chunk].fb, ms);
+        cudaEventDestroy(t.e);
+      }
+      cudaEventDestroy(tStart);
+    }
     float mx;
     std::memcpy(&mx, hBits, 4);
     if (!((double)mx * std::ldexp(1.0, qs) <= (double)I8_QMAX)) {

@@ -5,6 +5,8 @@ Cluster::DynamicMatrix compiled where it lies (oracle/_ref: ref_hieragglo) -- me
 identical, ties included.  GPU part (-m gpu): b200_hieragglo through the C ABI against the restatement: which pair
 merges at every step must be identical (integers: bit-exact), FindMin values bit-equal for single / complete linkage
 and for average linkage on these sizes (the sums are exactly representable)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -111,6 +113,32 @@ def test_gpu_rmsd_cache_end_to_end(b200, oracle):
         lab_ref = partition(oracle.hieragglo(tri_ref, nf, linkage, nconf, None), nf)
         assert np.array_equal(lab, lab_ref)
         assert all(len(set(lab[np.arange(nf) % nconf == c])) == 1 for c in range(nconf))
+
+
+@pytest.mark.gpu
+def test_gpu_tight_cluster_long_rescan_lists(b200, oracle):
+    """A quarter of the frames are rigid copies of one conformation (RMSDs ~1e-6 A apart), every 64th frame is a bit-exact
+    duplicate: the tight cluster is the closest of almost every other cluster, so merging it away queues hundreds of
+    rows for a re-scan -- the long-list path (one warp per row), the lower-bound shortcut that skips re-scans whose
+    outcome is certain, zero distances and exact ties, all against the restatement."""
+    from cpptraj_b200.synth import make_trajectory
+    nf, na = 900, 40
+    crd, _ = make_trajectory(31, nf, na)
+    tri = b200.rms2d_tri(crd, np.arange(na, dtype=np.int32))
+    assert (tri == 0).sum() >= nf // 64                      # the duplicates
+    for linkage in (0, 1, 2):
+        for target, eps in ((1, None), (7, None), (None, 1.0)):
+            want = oracle.hieragglo(tri, nf, linkage, target, eps)
+            for team in (None, 4):
+                if team is None:
+                    os.environ.pop("B200_HA_TEAM", None)
+                else:
+                    os.environ["B200_HA_TEAM"] = str(team)
+                try:
+                    got = b200.hieragglo(tri, nf, linkage, target, eps)
+                finally:
+                    os.environ.pop("B200_HA_TEAM", None)
+                assert_same(got, want, (linkage, target, eps, team))
 
 
 def partition(merges, n):
