@@ -345,7 +345,7 @@ def host_ceiling(ctx, nbytes, h2d_bytes=0, d2h_bytes=0):
                 p_out.copy_(d_out, non_blocking=True)
             torch.cuda.synchronize()
             best = min(best, ctx.reduce(time.perf_counter() - t0))
-        out["duplex_ms"] = 1e3 * best * (h2d_bytes / hn)
+        out["duplex_ms"] = 1e3 * best * max(h2d_bytes / hn, d2h_bytes / dn)   # (probe buffers are capped at 4 GB each)
         del d_in, p_in, d_out, p_out
         torch.cuda.empty_cache()
     return out

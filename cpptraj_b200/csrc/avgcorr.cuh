@@ -18,13 +18,17 @@ namespace b200 {
 __global__ void __launch_bounds__(128) avgcorr_prefix_kernel(const float* __restrict__ crd, size_t stride, long srcBase,
                                                              const int* __restrict__ atomIdx, int nAtoms, int nFrames,
                                                              const double* __restrict__ shift, double* __restrict__ P) {
+  // output column c = plane * nAtoms + atom (x plane, y plane, z plane): a warp of avgcorr_kernel then reads 32
+  // consecutive doubles per coordinate (interleaved xyz rows cost three 24-byte-strided loads per atom: ncu showed the
+  // L1 data pipe at 74 % with the FP64 pipe at 43 %)
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int ld = 3 * nAtoms;
   if (c >= ld) return;
-  const size_t col = (size_t)3 * (size_t)(atomIdx ? atomIdx[c / 3] : c / 3) + (size_t)(c % 3);
+  const int plane = c / nAtoms, atom = c - plane * nAtoms;
+  const size_t col = (size_t)3 * (size_t)(atomIdx ? atomIdx[atom] : atom) + (size_t)plane;
   // A common origin near the molecule (the centre of frame 0's selection) is removed first: the fit removes every
   // frame's own centre anyway, and the sums formed from uncentred coordinates then cancel far less.
-  const double sh = shift[c % 3];
+  const double sh = shift[plane];
   double acc = 0.0;
   P[c] = 0.0;
   const float* src = crd + col - (size_t)srcBase * stride;
@@ -54,10 +58,10 @@ __global__ void avgcorr_shift_kernel(const float* __restrict__ crd, size_t strid
 }
 
 struct AvgCorrArgs {
-  const double* P;         // [nFrames+1][ld] prefix sums, row 0 = 0
+  const double* P;         // [nFrames+1][ld] prefix sums, row 0 = 0; a row is three planes x | y | z of nAtoms doubles
   int ld, nAtoms, nFrames;
   const double* mass;      // nullable: per selected atom
-  const double* refFixed;  // nullable: fixed reference (3 nAtoms doubles, as the caller centred it); null = "first"
+  const double* refFixed;  // nullable: fixed reference as the caller centred it, plane-major like a row of P; null = "first"
   const int* win;          // window sizes of this batch
   const long long* itemOff;  // [nW+1]: first RMSD slot of each window
   int nW;
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) avgcorr_ref_kernel(AvgCorrArgs a) {
     double s[3] = {0.0, 0.0, 0.0};
     for (int k = threadIdx.x; k < a.nAtoms; k += blockDim.x) {
       const double m = a.mass ? a.mass[k] : 1.0;
-      for (int d = 0; d < 3; ++d) s[d] += m * (R[3 * k + d] / div);
+      for (int d = 0; d < 3; ++d) s[d] += m * (R[d * a.nAtoms + k] / div);
     }
     for (int d = 0; d < 3; ++d) s[d] = warp_sum(s[d]);
     if (lane == 0) for (int d = 0; d < 3; ++d) sh[wp][d] = s[d];
@@ -95,7 +99,7 @@ __global__ void __launch_bounds__(256) avgcorr_ref_kernel(AvgCorrArgs a) {
   for (int k = threadIdx.x; k < a.nAtoms; k += blockDim.x) {
     const double m = a.mass ? a.mass[k] : 1.0;
     for (int d = 0; d < 3; ++d) {
-      const double r = R[3 * k + d] / div - c[d];
+      const double r = R[d * a.nAtoms + k] / div - c[d];
       g += m * r * r; sr[d] += m * r;
     }
   }
@@ -143,12 +147,13 @@ __global__ void __launch_bounds__(AVGCORR_WARPS * 32, (NWIN <= 2 ? 2 : 1)) avgco
   }
   for (int k = lane; k < a.nAtoms; k += 32) {
     const double m = a.mass ? a.mass[k] : 1.0;
-    const double p0 = Pt[3 * k], p1 = Pt[3 * k + 1], p2 = Pt[3 * k + 2];
+    const int ky = a.nAtoms + k, kz = 2 * a.nAtoms + k;
+    const double p0 = Pt[k], p1 = Pt[ky], p2 = Pt[kz];
 #pragma unroll
     for (int j = 0; j < NWIN; ++j) {
-      const double dx = Pu[j][3 * k] - p0, dy = Pu[j][3 * k + 1] - p1, dz = Pu[j][3 * k + 2] - p2;
+      const double dx = Pu[j][k] - p0, dy = Pu[j][ky] - p1, dz = Pu[j][kz] - p2;
       const double mx = m * dx, my = m * dy, mz = m * dz;
-      const double rx = R[j][3 * k], ry = R[j][3 * k + 1], rz = R[j][3 * k + 2];
+      const double rx = R[j][k], ry = R[j][ky], rz = R[j][kz];
       sa[j][0] += mx; sa[j][1] += my; sa[j][2] += mz;
       saa[j] += mx * dx + my * dy + mz * dz;
       S[j][0] += mx * rx; S[j][1] += mx * ry; S[j][2] += mx * rz;

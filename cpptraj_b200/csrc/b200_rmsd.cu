@@ -2177,7 +2177,13 @@ int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, con
   if ((rc = get_coords(d, d.crd, crd, frameStrideFloats, nFrames, 0, nFrames, width, st, &h2d, &d_frames, &pitch, &rowBase))) return rc;
   if ((rc = upload_vec(d.idxA, atomIdx, (size_t)nAtoms, st))) return rc;
   if (mass && (rc = upload_vec(d.massA, mass, (size_t)nAtoms, st))) return rc;
-  if (refSelected && (rc = upload_vec(d.planesB, refSelected, (size_t)3 * nAtoms, st))) return rc;
+  std::vector<double> refPlanes;   // the fixed reference plane-major (x | y | z), like a row of the prefix sums
+  if (refSelected) {
+    refPlanes.resize((size_t)3 * nAtoms);
+    for (int k = 0; k < nAtoms; ++k)
+      for (int c = 0; c < 3; ++c) refPlanes[(size_t)c * nAtoms + k] = refSelected[3 * (size_t)k + c];
+    if ((rc = upload_vec(d.planesB, refPlanes.data(), (size_t)3 * nAtoms, st))) return rc;
+  }
   double totalMass = 0.0;   // in atom order, as Frame::RMSD_CenteredRef sums it (src/Frame.cpp:1150-1158)
   for (int k = 0; k < nAtoms; ++k) totalMass += mass ? mass[k] : 1.0;
   const int ld = 3 * nAtoms;

@@ -125,7 +125,7 @@ def test_gpu_tight_cluster_long_rescan_lists(b200, oracle):
     nf, na = 900, 40
     crd, _ = make_trajectory(31, nf, na)
     tri = b200.rms2d_tri(crd, np.arange(na, dtype=np.int32))
-    assert (tri == 0).sum() >= nf // 64                      # the duplicates
+    assert (tri < 1e-5).sum() >= nf // 64                    # the duplicates and the rigid copies
     for linkage in (0, 1, 2):
         for target, eps in ((1, None), (7, None), (None, 1.0)):
             want = oracle.hieragglo(tri, nf, linkage, target, eps)
