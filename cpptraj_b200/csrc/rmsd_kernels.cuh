@@ -904,7 +904,9 @@ __global__ void __launch_bounds__(128) onevn_finish_kernel(const double* rec, co
 // Here a CTA owns ONE 1024-atom chunk of the selection for its whole life: the chunk's reference (pre-multiplied by
 // the masses) and atom numbers are loaded into shared memory once; what streams through a 6-deep mbarrier ring is
 // frame data only: one stage = the chunk's span of two frames (2 x 12 KB, two bulk copies issued by a producer warp).
-// Two consumer warps per stage (one per half of the chunk's selected atoms) accumulate 13 FP64 sums for both frames
+// Six consumer warp pairs take the stages in turn (seven ring slots: a pair that hands a slot back moves on to a slot
+// that is already filled instead of waiting for the refill of its own); the two warps of a pair (one per half of the
+// chunk's selected atoms) accumulate 13 FP64 sums for both frames
 // relative to a local origin (the chunk's first atom of each frame, read from the stage itself), reduce them inside
 // the warp and write one 16-double partial record per (frame, part); no CTA-wide barrier in the steady state.
 // onevn_finish2_kernel (one thread per frame) shifts the partial sums to a common origin, adds them up and solves.
@@ -915,7 +917,10 @@ constexpr int ONEVN2_MAX_APC = ONEVN2_CHUNK_BYTES / 12;          // 1024
 constexpr int ONEVN2_FR = 2;                                     // frames per stage
 constexpr int ONEVN2_BUF_BYTES = ONEVN2_CHUNK_BYTES + 32;        // + alignment slack at both ends
 #ifndef B200_ONEVN2_STAGES
-#define B200_ONEVN2_STAGES 6
+#define B200_ONEVN2_STAGES 7
+#endif
+#ifndef B200_ONEVN2_PAIRS
+#define B200_ONEVN2_PAIRS 6   // consumer warp pairs; fewer than ring slots: a pair that frees a slot moves on to another, already filled one
 #endif
 #ifndef B200_ONEVN2_UNROLL
 #define B200_ONEVN2_UNROLL 2   // (+3 % over 1; 7 stages and an integer-pipe float->double conversion measured no better / worse)
@@ -924,13 +929,14 @@ constexpr int ONEVN2_BUF_BYTES = ONEVN2_CHUNK_BYTES + 32;        // + alignment 
 #define B200_ONEVN2_ICVT 0
 #endif
 constexpr int ONEVN2_STAGES = B200_ONEVN2_STAGES;
+constexpr int ONEVN2_PAIRS = B200_ONEVN2_PAIRS;
 constexpr int ONEVN2_UNROLL = B200_ONEVN2_UNROLL;
 constexpr int ONEVN2_STAGE_BYTES = ONEVN2_FR * ONEVN2_BUF_BYTES;
 constexpr int ONEVN2_REF_BYTES = ONEVN2_MAX_APC * 32;            // (m rx, m ry, m rz, m) of the chunk's selected atoms
 constexpr int ONEVN2_IDX_BYTES = ONEVN2_MAX_APC * 4 + 32;
 constexpr int ONEVN2_SMEM_BYTES = ONEVN2_REF_BYTES + ONEVN2_IDX_BYTES + ONEVN2_STAGES * ONEVN2_STAGE_BYTES + 128 +
-                                  ONEVN2_STAGES * 2 * ONEVN2_FR * 16 * 8;   // + the pair buffers
-constexpr int ONEVN2_CONSUMERS = 2 * ONEVN2_STAGES;             // warps: two per stage
+                                  ONEVN2_PAIRS * 2 * ONEVN2_FR * 16 * 8;   // + the pair buffers
+constexpr int ONEVN2_CONSUMERS = 2 * ONEVN2_PAIRS;              // warps: two per consumer pair
 constexpr int ONEVN2_THREADS = 32 * (ONEVN2_CONSUMERS + 1);     // + the producer warp
 
 struct OneVN2Args {
@@ -1005,7 +1011,7 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
   unsigned char* ring = sidxRaw + ONEVN2_IDX_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + ONEVN2_STAGES * ONEVN2_STAGE_BYTES);
   uint64_t* empty = full + ONEVN2_STAGES;
-  double* pairBuf = reinterpret_cast<double*>(empty + ONEVN2_STAGES);   // [stage][parity][frame][16]
+  double* pairBuf = reinterpret_cast<double*>(empty + ONEVN2_STAGES);   // [pair][parity][frame][16]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int a0 = a.hdr[0], nCh = a.hdr[1];
   const int P = (int)gridDim.x / nCh;                    // CTAs per chunk (the host sizes the grid as nCh * P)
@@ -1062,8 +1068,8 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
     }
     return;
   }
-  // ===================== consumers: warp w works on stage w / 2, half w % 2 of the chunk's selected atoms =====================
-  const int h = warp & 1, myStage = warp >> 1;
+  // ===================== consumers: warp w belongs to pair w / 2 and works on half w % 2 of the chunk's selected atoms =====================
+  const int h = warp & 1, myPair = warp >> 1;
   const int half0 = (nSel + 1) / 2;
   const int kBeg = h ? half0 : 0, kEnd = h ? nSel : half0;
   // one record per (frame, chunk): the warp of the upper half hands its sums to the warp of the lower half through
@@ -1072,8 +1078,8 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
   const int part = c;
   const int nParts = nCh;
   int iter = 0;
-  for (int n = myStage; n < myPairs; n += ONEVN2_STAGES, ++iter) {
-    const int st = myStage;   // (n % STAGES == myStage by construction)
+  for (int n = myPair; n < myPairs; n += ONEVN2_PAIRS, ++iter) {
+    const int st = n % ONEVN2_STAGES;
     mbar_wait(smem_u32(&full[st]), (uint32_t)((n / ONEVN2_STAGES) & 1));
     const unsigned char* sbuf = ring + st * ONEVN2_STAGE_BYTES;
     const int f0 = (k + n * P) * ONEVN2_FR;
@@ -1116,12 +1122,12 @@ __global__ void __launch_bounds__(ONEVN2_THREADS, 1) onevn_stream2_kernel(OneVN2
     double mine[ONEVN2_FR];   // lane x keeps sum x (x < 13), lanes 13..15 the origin
 #pragma unroll
     for (int f = 0; f < ONEVN2_FR; ++f) mine[f] = warp_transpose_sum13(acc[f], lane);
-    double* pb = pairBuf + ((myStage * 2 + (iter & 1)) * ONEVN2_FR) * 16;
+    double* pb = pairBuf + ((myPair * 2 + (iter & 1)) * ONEVN2_FR) * 16;
     if (h == 1 && lane < 13) {
 #pragma unroll
       for (int f = 0; f < ONEVN2_FR; ++f) pb[f * 16 + lane] = mine[f];
     }
-    asm volatile("bar.sync %0, 64;" ::"r"(1 + myStage) : "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + myPair) : "memory");
     if (h == 0) {
 #pragma unroll
       for (int f = 0; f < ONEVN2_FR; ++f) {
