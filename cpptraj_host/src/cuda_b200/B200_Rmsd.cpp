@@ -31,6 +31,8 @@ static void b200_do_init() {
   Timer t_init;
   t_init.Start();
   b200_init_rc = b200_init(want, &b200_init_used);
+  // in the background (InitAsync): also pin the staging slots and load the kernels; a synchronous Init() does not wait for that
+  if (b200_init_rc == 0 && b200_async_started) b200_warmup();
   t_init.Stop();
   b200_init_seconds = t_init.Total();
 }

@@ -46,6 +46,10 @@ extern "C" {
 int b200_init(int ngpu_requested, int* ngpu_used);
 /* Same, with explicit CUDA device ordinals (one process per GPU: pass LOCAL_RANK). */
 int b200_init_devices(const int* deviceIds, int n);
+/* Optional, after b200_init: reserves the device chunk buffers and loads the main kernels, so that the first call of
+ * a process does not pay for it (a cpptraj command does it on a background thread at set-up, while the trajectory is
+ * read; the pattern of src/Cpptraj.cpp:120-135 is a synchronous probe). */
+int b200_warmup(void);
 void b200_shutdown(void);
 const char* b200_last_error(void);
 int b200_version(void);
