@@ -38,10 +38,13 @@ constexpr int I8_BLK_BYTES = 128 * I8_KC;    // 8192
 /// (tcgen05.mma.cta_group::2, M256 N256); each CTA stages its own A row group and ONE of the two B row
 /// groups, so shared-memory fill, operand reads and L2 -> SM traffic per SM drop by a third and a stage holds
 /// 128 atoms (4 MMAs) in the same footprint.
+#ifndef B200_I8_TPW
+#define B200_I8_TPW 1           // tiles per FP64 window (1 or 2); 2 keeps a tile's covariance in shared memory: fewer ring slots
+#endif
 template <int CG> struct I8Geom;
 template <> struct I8Geom<1> {
   static constexpr int BPS = 1;      // 64-atom blocks per stage
-  static constexpr int STAGES = 5;
+  static constexpr int STAGES = B200_I8_TPW == 2 ? 3 : 5;
   static constexpr int BBLK = 2;     // B blocks per 64 atoms held by this CTA
 };
 #ifndef B200_I8_CG2_BPS
@@ -333,9 +336,6 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // the same number of tiles (+-1), groups running at the same time work on neighbouring columns
 // (their A rows stay in L2).
 // ----------------------------------------------------------------------------
-#ifndef B200_I8_TPW
-#define B200_I8_TPW 1           // tiles per FP64 window (1 or 2)
-#endif
 constexpr int I8_TPW = B200_I8_TPW;
 static_assert(I8_TPW == 1 || I8_TPW == 2, "tiles per FP64 window");
 #ifndef B200_I8_DRAIN_WARPS
@@ -352,8 +352,11 @@ constexpr int I8_XJ_DBL = 128 * 3 + 11;      // entries per column frame: 3 per 
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 88480
 constexpr int I8_MAX_STAGES = 8;
 constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 2;
+// I8_TPW == 2: the covariance (9 doubles) and 2 E0 of the tile that waits for the next FP64 window, one slot per solve
+// thread, [entry][thread] (conflict-free); in registers it did not fit the 96-register budget (spills, slower)
+constexpr int I8_HELD_BYTES = I8_TPW == 2 ? 10 * I8_SOLVE_WARPS * 32 * 8 : 0;
 template <int CG> __host__ __device__ constexpr int i8_smem_bytes() {
-  return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 32 + 256;
+  return I8Geom<CG>::STAGES * i8_stage_bytes<CG>() + I8_XBUF_BYTES + 32 + 256 + I8_HELD_BYTES;
 }
 static_assert(I8_NBARS * 8 + 8 <= 256, "barrier block");
 static_assert(I8_XBUF_BYTES % 32 == 0, "barrier alignment");
@@ -543,6 +546,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   uint64_t* fpDone = bars + 2 * I8_MAX_STAGES + 12;    // [1]  FP64 window of a tile closed (CG 2: by both CTAs; leader's copy)
   uint64_t* fpLocal = bars + 2 * I8_MAX_STAGES + 13;   // [1]  same, this CTA's solve warps only: the drain warps start on the next tile
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
+  double* heldBuf = reinterpret_cast<double*>(xbufRaw + I8_XBUF_BYTES + 32 + 256);   // (I8_TPW == 2 only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = CG == 1 ? 0u : cluster_ctarank();   // 0 = leader (issues the MMAs)
@@ -809,8 +813,22 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         r2 = (float)(i8_relative_gap_slow(S[0], S[1], S[2], S[3], S[4], S[5], S[6], S[7], S[8], cq.e0) * (cq.e0 * outScale));
       if (valid) a.out[idx] = (r2 > 0.f) ? sqrtf(r2) : 0.f;
     };
-    // A tile held back for the next window (I8_TPW == 2): its covariance, 2 E0 and output slot.
-    double Sh[9], gh = 1.0;
+    // the same for the held tile: its covariance is re-read from shared memory only on the (rare) guarded path
+    auto finish_pair_held = [&](const I8Quartic& cq, bool valid, size_t idx) {
+      float r2;
+      const bool ok = i8_root(cq, outScale, valid, &r2);
+      if (valid && !ok) {
+        const double* hp = heldBuf + (u * 32 + lane);
+        constexpr int HS2 = I8_SOLVE_WARPS * 32;
+        r2 = (float)(i8_relative_gap_slow(hp[0], hp[HS2], hp[2 * HS2], hp[3 * HS2], hp[4 * HS2], hp[5 * HS2], hp[6 * HS2], hp[7 * HS2],
+                                          hp[8 * HS2], cq.e0) * (cq.e0 * outScale));
+      }
+      if (valid) a.out[idx] = (r2 > 0.f) ? sqrtf(r2) : 0.f;
+    };
+    // A tile held back for the next window (I8_TPW == 2): its covariance and 2 E0 wait in shared memory, its output slot
+    // in registers.
+    double* held = heldBuf + (u * 32 + lane);
+    constexpr int HS = I8_SOLVE_WARPS * 32;   // stride between the entries of one thread
     bool heldLive = false, heldValid = false;
     size_t heldIdx = 0;
     int itN, jtN;
@@ -858,8 +876,8 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       const bool windowTile = I8_TPW == 1 || (n & 1) == 0 || !hasNext;
       if (!windowTile) {
 #pragma unroll
-        for (int x = 0; x < 9; ++x) Sh[x] = S[x];
-        gh = ga + gb;   // (one FP64 add under the MMAs per held tile)
+        for (int x = 0; x < 9; ++x) held[x * HS] = S[x];
+        held[9 * HS] = ga + gb;   // (one FP64 add under the MMAs per held tile)
         heldLive = true; heldValid = valid; heldIdx = idx;
       } else {
         c0 = (DBG && dbgClk) ? clock64() : 0;
@@ -869,7 +887,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0; cqh = cq;
         if (plain) {
           // everything that must be FP64 (E0 too: outside the window its instructions crawl on the critical path)
-          if (I8_TPW == 2 && heldLive) cqh = i8_coeffs(Sh, gh * halfToInt);
+          if (I8_TPW == 2 && heldLive) {
+            double Sh[9];
+#pragma unroll
+            for (int x = 0; x < 9; ++x) Sh[x] = held[x * HS];
+            cqh = i8_coeffs(Sh, held[9 * HS] * halfToInt);
+          }
           cq = i8_coeffs(S, (ga + gb) * halfToInt);
           asm volatile("" ::"d"(cq.q0), "d"(cq.q1), "d"(cq.q2), "d"(cqh.q0), "d"(cqh.q1), "d"(cqh.q2) : "memory");   // computed before the arrive below
         }
@@ -882,7 +905,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         // ---- 3. roots and stores (under the MMAs of the next tiles)
         const long long cR = (DBG && dbgClk) ? clock64() : 0;
         if (plain) {
-          if (I8_TPW == 2 && heldLive) finish_pair(cqh, Sh, heldValid, heldIdx);
+          if (I8_TPW == 2 && heldLive) finish_pair_held(cqh, heldValid, heldIdx);
           finish_pair(cq, S, valid, idx);
         } else if (!(DBG && dbgMode == 6)) {
           if (valid) a.out[idx] = (float)(S[0] + S[4] + S[8]);
