@@ -2180,18 +2180,12 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
 }
 
 // ---- rmsavgcorr: RMSD of running-averaged coordinates, all window sizes (avgcorr.cuh)
-int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms, const double* mass,
-                    const double* refSelected, const int* windows, int nWindows, double* avgOut, double* sdOut) {
-  if (!crd || !windows || !avgOut || !sdOut) return fail(B200_ERR_ARG, "null argument");
-  if (nFrames < 1 || nWindows < 0) return fail(B200_ERR_ARG, "bad frame or window count");
-  for (int w = 0; w < nWindows; ++w)
-    if (windows[w] < 1 || windows[w] > nFrames) return fail(B200_ERR_ARG, "windows[%d]=%d outside 1..%d", w, windows[w], nFrames);
-  std::lock_guard<std::mutex> lk(g_mu);
-  int rc, maxAtom = 0;
-  if ((rc = ensure_init_locked())) return rc;
-  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+/// The window sizes windows[0..nWindows) on one device (prefix sums built there).
+static int avgcorr_on_device(Device& d, const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms,
+                             int maxAtom, const double* mass, const double* refSelected, const int* windows, int nWindows,
+                             double* avgOut, double* sdOut) {
+  int rc;
   if (nWindows == 0) return B200_OK;
-  Device& d = g_devs[0];
   CU(cudaSetDevice(d.id));
   cudaStream_t st = d.stream[0];
   double h2d = 0.0;
@@ -2275,6 +2269,35 @@ int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, con
     std::lock_guard<std::mutex> sl(g_statMu);
     g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)nWindows * 16.0;
   }
+  return B200_OK;
+}
+
+int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms, const double* mass,
+                    const double* refSelected, const int* windows, int nWindows, double* avgOut, double* sdOut) {
+  if (!crd || !windows || !avgOut || !sdOut) return fail(B200_ERR_ARG, "null argument");
+  if (nFrames < 1 || nWindows < 0) return fail(B200_ERR_ARG, "bad frame or window count");
+  for (int w = 0; w < nWindows; ++w)
+    if (windows[w] < 1 || windows[w] > nFrames) return fail(B200_ERR_ARG, "windows[%d]=%d outside 1..%d", w, windows[w], nFrames);
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc, maxAtom = 0;
+  if ((rc = ensure_init_locked())) return rc;
+  if ((rc = validate_sel(atomIdx, nAtoms, frameStrideFloats, &maxAtom))) return rc;
+  if (nWindows == 0) return B200_OK;
+  // Window sizes are independent: with several devices, device k takes windows k, k + nd, ... (the cost of a window size
+  // falls with its size: interleaving balances) and builds its own prefix sums.
+  const int nd = (nWindows >= 64 * (int)g_devs.size()) ? (int)g_devs.size() : 1;
+  if (nd == 1) return avgcorr_on_device(g_devs[0], crd, frameStrideFloats, nFrames, atomIdx, nAtoms, maxAtom, mass, refSelected,
+                                        windows, nWindows, avgOut, sdOut);
+  std::vector<std::vector<int>> win(nd);
+  std::vector<std::vector<double>> av(nd), sd(nd);
+  for (int w = 0; w < nWindows; ++w) win[w % nd].push_back(windows[w]);
+  for (int k = 0; k < nd; ++k) { av[k].resize(win[k].size()); sd[k].resize(win[k].size()); }
+  rc = for_each_device([&](int k) {
+    return avgcorr_on_device(g_devs[k], crd, frameStrideFloats, nFrames, atomIdx, nAtoms, maxAtom, mass, refSelected,
+                             win[k].data(), (int)win[k].size(), av[k].data(), sd[k].data());
+  });
+  if (rc) return rc;
+  for (int w = 0; w < nWindows; ++w) { avgOut[w] = av[w % nd][w / nd]; sdOut[w] = sd[w % nd][w / nd]; }
   return B200_OK;
 }
 

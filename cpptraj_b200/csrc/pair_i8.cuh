@@ -350,8 +350,11 @@ constexpr int I8_WARP_MMA = I8_WARP_PRODUCER + 1;                   // 19
 constexpr int I8_THREADS = 32 * (I8_WARP_MMA + 1);                  // 640
 constexpr int I8_XJ_DBL = 128 * 3 + 11;      // entries per column frame: 3 per operand row + pad; odd => conflict-free LDS / STS
 constexpr int I8_XBUF_BYTES = I8_TILE_J * I8_XJ_DBL * 8;  // 88480
-constexpr int I8_MAX_STAGES = 8;
-constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 2;
+constexpr int I8_MAX_STAGES = 6;
+constexpr int I8_NBARS = 2 * I8_MAX_STAGES + 4 + 8 + 2 + 2;
+#ifndef B200_I8_EARLY_WINDOW
+#define B200_I8_EARLY_WINDOW 0   // 1: the FP64 window opens when the last MMA of the next tile has been ISSUED (not completed)
+#endif
 // I8_TPW == 2: the covariance (9 doubles) and 2 E0 of the tile that waits for the next FP64 window, one slot per solve
 // thread, [entry][thread] (conflict-free); in registers it did not fit the 96-register budget (spills, slower)
 constexpr int I8_HELD_BYTES = I8_TPW == 2 ? 10 * I8_SOLVE_WARPS * 32 * 8 : 0;
@@ -545,6 +548,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
   uint64_t* xEmpty = bars + 2 * I8_MAX_STAGES + 8;     // [4]  exchange group read
   uint64_t* fpDone = bars + 2 * I8_MAX_STAGES + 12;    // [1]  FP64 window of a tile closed (CG 2: by both CTAs; leader's copy)
   uint64_t* fpLocal = bars + 2 * I8_MAX_STAGES + 13;   // [1]  same, this CTA's solve warps only: the drain warps start on the next tile
+  uint64_t* winOpen = bars + 2 * I8_MAX_STAGES + 14;   // [2]  the last MMA of a tile has been issued (B200_I8_EARLY_WINDOW)
   uint32_t* tmemBaseSlot = reinterpret_cast<uint32_t*>(bars + I8_NBARS);
   double* heldBuf = reinterpret_cast<double*>(xbufRaw + I8_XBUF_BYTES + 32 + 256);   // (I8_TPW == 2 only)
 
@@ -564,6 +568,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
     }
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&accFull[b]), 1); mbar_init(smem_u32(&accEmpty[b]), I8_DRAIN_WARPS * CG); }
     for (int g = 0; g < 4; ++g) { mbar_init(smem_u32(&xFull[g]), 4); mbar_init(smem_u32(&xEmpty[g]), I8_SOLVE_WARPS / 2); }
+    mbar_init(smem_u32(&winOpen[0]), 1); mbar_init(smem_u32(&winOpen[1]), 1);
     mbar_init(smem_u32(fpDone), I8_SOLVE_WARPS * CG);
     mbar_init(smem_u32(fpLocal), I8_SOLVE_WARPS);
     mbar_fence_init();
@@ -665,7 +670,13 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
           }
         }
         umma_commit<CG>(smem_u32(&emptyBar[stage]));
-        if (c + BPS >= a.nC) umma_commit<CG>(smem_u32(&accFull[b]));   // last stage of the tile: accumulator complete
+        if (c + BPS >= a.nC) {
+          umma_commit<CG>(smem_u32(&accFull[b]));   // last stage of the tile: accumulator complete
+          if (B200_I8_EARLY_WINDOW) {   // tell the solve warps of both CTAs now: their wake-up overlaps the MMAs' completion
+            mbar_arrive(smem_u32(&winOpen[b]));
+            if constexpr (CG == 2) mbar_arrive_cluster(cluster_map(smem_u32(&winOpen[b]), 1));
+          }
+        }
         }
         __syncwarp();
         if (++stage == depth) { stage = 0; phase ^= 1u; }
@@ -881,7 +892,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
         heldLive = true; heldValid = valid; heldIdx = idx;
       } else {
         c0 = (DBG && dbgClk) ? clock64() : 0;
-        if (hasNext) mbar_wait(smem_u32(&accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
+        if (hasNext) mbar_wait(smem_u32(B200_I8_EARLY_WINDOW ? &winOpen[(n + 1) & 1] : &accFull[(n + 1) & 1]), (uint32_t)(((n + 1) >> 1) & 1));
         const long long cF = (DBG && dbgClk) ? clock64() : 0;
         I8Quartic cq, cqh;
         cq.q0 = cq.q1 = cq.q2 = 0.0; cq.e0 = 1.0; cqh = cq;

@@ -171,7 +171,8 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
  * receive the mean and the standard deviation of those RMSDs as the reference forms them (:196-205, :289-297).
  * refSelected NULL: the "first" mode -- the reference of a window size is its own first averaged frame, centred with
  * the same weights (:258-272); else 3*nAtoms doubles, the fixed reference exactly as the caller centred it (:86-90).
- * Window size 1 is the plain trajectory (:176-205).  All frames of crd are used.  Runs on device 0. */
+ * Window size 1 is the plain trajectory (:176-205).  All frames of crd are used.  64 or more window sizes per device: the
+ * window sizes are dealt round-robin to all initialised devices (each builds its own prefix sums). */
 int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, const int* atomIdx, int nAtoms,
                     const double* mass, const double* refSelected, const int* windows, int nWindows,
                     double* avgOut, double* sdOut);

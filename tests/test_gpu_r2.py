@@ -304,5 +304,11 @@ def test_single_process_multi_device(oracle):
         dist, closest, cdist = b.frames_to_centroids(big, sel, cen, mass=mass)
         wantd = np.stack([oracle.rmsd_1vN(big, sel, cen[k], mass=mass) for k in range(6)], axis=1)
         assert maxdiff(dist, wantd) <= TOL and np.array_equal(closest, dist.argmin(1))
+        # rmsavgcorr: the window sizes are dealt to the devices; every device builds its own prefix sums
+        win = np.arange(1, 601, dtype=np.int32)
+        many_ac = b.rmsavgcorr(c[:600], sel, win, mass=mass)
+        b.init(1)
+        one_ac = b.rmsavgcorr(c[:600], sel, win, mass=mass)
+        assert np.array_equal(many_ac[0], one_ac[0]) and np.array_equal(many_ac[1], one_ac[1])
     finally:
         b.shutdown()
