@@ -129,4 +129,15 @@ rmsavgcorr RM :2-12@CA,C,N out rac.mass.dat first mass stop 40 offset 3
 rmsavgcorr RR :2-12@CA out rac.ref.dat reference
 rmsavgcorr R10 :2-12@CA out rac.ref10.dat reference offset 10
 """, [("rac.first.dat", "table"), ("rac.mass.dat", "table"), ("rac.ref.dat", "table"), ("rac.ref10.dat", "table")]),
+    # src/Cluster/Results_Coords.cpp:331-377: reference structures assigned to clusters by the RMSD of the best
+    # representative to every reference (nearest reference, cut-off naming), one frames x references call
+    "cluster_assignrefs": ("""noprogress
+parm {D}/tz2.parm7
+trajin {D}/tz2.crd
+reference {D}/tz2.crd 1 [first]
+reference {D}/tz2.crd 50 [mid]
+reference {D}/tz2.crd 100 [late]
+cluster C1 @CA clusters 5 rms out ar.out summary ar.summary.dat assignrefs refcut 2.0 refmask @CA
+cluster C2 :2-12 clusters 4 rms mass summary ar.mass.summary.dat assignrefs refcut 1.0 refmask :2-12@CA,C,N
+""", [("ar.out", "table"), ("ar.summary.dat", "text"), ("ar.mass.summary.dat", "text")]),
 }
