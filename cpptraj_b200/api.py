@@ -52,6 +52,14 @@ def lib():
     L.b200_rmsd_build_centroids.restype = i
     L.b200_rmsavgcorr.argtypes = [vp, sz, i, vp, i, vp, vp, vp, i, vp, vp]
     L.b200_rmsavgcorr.restype = i
+    L.b200_cache_resident_begin.argtypes = [vp, i]
+    L.b200_cache_resident_begin.restype = i
+    L.b200_cache_resident_end.argtypes = [vp]
+    L.b200_cache_resident_end.restype = i
+    L.b200_cache_cluster_sums.argtypes = [vp, i, vp, vp, i, vp, vp, vp]
+    L.b200_cache_cluster_sums.restype = i
+    L.b200_cache_cluster_links.argtypes = [vp, i, vp, i, vp, vp, vp, vp]
+    L.b200_cache_cluster_links.restype = i
     L.b200_hieragglo.argtypes = [vp, i, i, i, dbl, vp, vp, vp, C.POINTER(i), C.POINTER(i)]
     L.b200_hieragglo.restype = i
     L.b200_coords_resident_begin.argtypes = [vp, sz, i, vp, i]
@@ -293,6 +301,38 @@ def rmsavgcorr(crd, atom_idx, windows, mass=None, ref_selected=None):
     _check(lib().b200_rmsavgcorr(_p(crd), crd.shape[1], crd.shape[0], _p(idx), len(idx), _p(m), _p(ref), _p(win), len(win),
                                  _p(avg), _p(sd)))
     return avg, sd
+
+
+def cache_resident_begin(tri, nframes):
+    tri = _arr(tri, np.float32)
+    _check(lib().b200_cache_resident_begin(_p(tri), nframes))
+    return tri            # (keep this array alive and pass IT to the calls that should find the resident copy)
+
+
+def cache_resident_end(tri=None):
+    _check(lib().b200_cache_resident_end(_p(tri) if tri is not None else None))
+
+
+def cache_cluster_sums(tri, nframes, member_lists):
+    """(cum, up, up2) per listed member, concatenated in list order (BestReps cumulative distance; Summary's within-cluster sums)."""
+    tri = _arr(tri, np.float32)
+    members = np.ascontiguousarray(np.concatenate([np.asarray(m, np.int32) for m in member_lists]) if member_lists else np.zeros(0, np.int32), np.int32)
+    offsets = np.zeros(len(member_lists) + 1, np.int32)
+    offsets[1:] = np.cumsum([len(m) for m in member_lists])
+    cum = np.zeros(len(members), np.float64); up = np.zeros_like(cum); up2 = np.zeros_like(cum)
+    _check(lib().b200_cache_cluster_sums(_p(tri), nframes, _p(members), _p(offsets), len(member_lists), _p(cum), _p(up), _p(up2)))
+    return cum, up, up2
+
+
+def cache_cluster_links(tri, nframes, label, nclusters):
+    """(min, max, sum, count) tables [K, K] (entries c1 < c2) of the cached distances between clusters."""
+    tri = _arr(tri, np.float32)
+    label = _arr(label, np.int32)
+    K = nclusters
+    mn = np.zeros((K, K), np.float64); mx = np.zeros((K, K), np.float64); sm = np.zeros((K, K), np.float64)
+    cnt = np.zeros((K, K), np.int64)
+    _check(lib().b200_cache_cluster_links(_p(tri), nframes, _p(label), K, _p(mn), _p(mx), _p(sm), _p(cnt)))
+    return mn, mx, sm, cnt
 
 
 def hieragglo(tri, nframes, linkage=1, target_clusters=None, epsilon=None):

@@ -104,6 +104,8 @@ struct Device {
   int inNext = 0;
   // COORDS kept on the device between calls (b200_coords_resident_begin/end): the leading resWidth floats of all frames
   const float* resHost = nullptr; size_t resStride = 0, resWidth = 0; int resFrames = 0; DevBuf resBuf;
+  // pairwise cache kept on the device between calls (b200_cache_resident_begin/end): the triangle of cacheN frames
+  const float* cacheHost = nullptr; int cacheN = 0; DevBuf cacheBuf;
   CopyPool pool;                          // staging of pageable inputs (and everything else on the calling thread)
   CopyPool poolOut;                       // delivery of pageable results (driven by OutRing's own thread)
   void destroy() {
@@ -125,7 +127,7 @@ struct Device {
     DevBuf* all[] = {&crd, &crdB, &idxA, &idxB, &frameIdx, &massA, &massB, &planesA, &planesB, &GA, &GB, &scal, &onevnWs,
                      &imgA, &imgB, &cenA, &cenB, &dbgS, &haTri, &haD, &haS, &haMisc, &acP, &acRms, &acMisc};
     for (DevBuf* b : all) b->release();
-    hostScal.release(); resBuf.release(); resHost = nullptr;
+    hostScal.release(); resBuf.release(); resHost = nullptr; cacheBuf.release(); cacheHost = nullptr; cacheN = 0;
     pool.stop(); poolOut.stop();
     id = -1;
   }
@@ -2301,6 +2303,133 @@ int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, con
   return B200_OK;
 }
 
+/// Device copy of a cache triangle of n frames: the resident one when the caller announced it (b200_cache_resident_begin),
+/// else an upload into the device's scratch (rows of 1 Mi floats + a remainder: pinned -> DMA, pageable -> staged by the
+/// copy pool).
+static int get_cache(Device& d, const float* tri, int n, cudaStream_t st, double* h2d, const float** d_tri, DevBuf* into = nullptr) {
+  if (!into && d.cacheHost == tri && d.cacheN == n && d.cacheBuf.p) { *d_tri = (const float*)d.cacheBuf.p; return B200_OK; }
+  DevBuf& buf = into ? *into : d.haTri;
+  const size_t nElt = (size_t)n * (size_t)(n - 1) / 2;
+  int rc;
+  if ((rc = buf.reserve(std::max<size_t>(nElt, 1) * sizeof(float)))) return rc;
+  const size_t W = (size_t)1 << 20, rows = nElt / W, rem = nElt - rows * W;
+  const bool pinned = host_ptr_is_pinned(tri);
+  if (rows && (rc = upload_rows(d, (float*)buf.p, tri, W, 0, (int)rows, W, pinned, st, h2d))) return rc;
+  if (rem && (rc = upload_rows(d, (float*)buf.p + rows * W, tri + rows * W, rem, 0, 1, rem, pinned, st, h2d))) return rc;
+  *d_tri = (const float*)buf.p;
+  return B200_OK;
+}
+
+int b200_cache_resident_begin(const float* tri, int nCached) {
+  if (!tri || nCached < 2) return fail(B200_ERR_ARG, "bad cache");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  d.cacheHost = nullptr; d.cacheN = 0;
+  double h2d = 0.0;
+  const float* d_tri = nullptr;
+  if ((rc = get_cache(d, tri, nCached, d.stream[0], &h2d, &d_tri, &d.cacheBuf))) return rc;
+  CU(cudaStreamSynchronize(d.stream[0]));
+  d.cacheHost = tri; d.cacheN = nCached;
+  std::lock_guard<std::mutex> sl(g_statMu);
+  g_stats.h2d_bytes += h2d;
+  return B200_OK;
+}
+
+int b200_cache_resident_end(const float* tri) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_devs.empty()) return B200_OK;
+  Device& d = g_devs[0];
+  if (tri && d.cacheHost != tri) return B200_OK;
+  cudaSetDevice(d.id);
+  d.cacheHost = nullptr; d.cacheN = 0;
+  d.cacheBuf.release();
+  return B200_OK;
+}
+
+int b200_cache_cluster_sums(const float* tri, int nCached, const int* members, const int* offsets, int nClusters,
+                            double* cumOut, double* upOut, double* up2Out) {
+  if (!tri || !members || !offsets || !cumOut || nClusters <= 0 || nCached < 2) return fail(B200_ERR_ARG, "bad argument");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  const int total = offsets[nClusters];
+  if (offsets[0] != 0 || total < 0) return fail(B200_ERR_ARG, "bad offsets");
+  if (total == 0) return B200_OK;
+  std::vector<int> clusterOf((size_t)total);
+  for (int c = 0; c < nClusters; ++c) {
+    if (offsets[c + 1] < offsets[c]) return fail(B200_ERR_ARG, "offsets not ascending");
+    for (int p = offsets[c]; p < offsets[c + 1]; ++p) {
+      if (members[p] < 0 || members[p] >= nCached) return fail(B200_ERR_ARG, "members[%d]=%d outside the cache", p, members[p]);
+      clusterOf[p] = c;
+    }
+  }
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const float* d_tri = nullptr;
+  if ((rc = get_cache(d, tri, nCached, st, &h2d, &d_tri))) return rc;
+  if ((rc = upload_vec(d.frameIdx, members, (size_t)total, st))) return rc;
+  if ((rc = upload_vec(d.idxB, offsets, (size_t)nClusters + 1, st))) return rc;
+  if ((rc = upload_vec(d.idxA, clusterOf.data(), (size_t)total, st))) return rc;
+  if ((rc = d.planesB.reserve((size_t)3 * total * sizeof(double)))) return rc;
+  double* dc = (double*)d.planesB.p;
+  COUNT_LAUNCH();
+  cache_cluster_sums_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_tri, nCached, (const int*)d.frameIdx.p, (const int*)d.idxB.p,
+                                                                (const int*)d.idxA.p, total, dc, upOut ? dc + total : nullptr,
+                                                                up2Out ? dc + 2 * (size_t)total : nullptr);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cumOut, dc, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (upOut) CU(cudaMemcpyAsync(upOut, dc + total, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (up2Out) CU(cudaMemcpyAsync(up2Out, dc + 2 * (size_t)total, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  std::lock_guard<std::mutex> sl(g_statMu);
+  g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)total * 8.0 * (1 + (upOut != nullptr) + (up2Out != nullptr));
+  return B200_OK;
+}
+
+int b200_cache_cluster_links(const float* tri, int nCached, const int* label, int nClusters, double* minOut, double* maxOut,
+                             double* sumOut, long long* countOut) {
+  if (!tri || !label || !minOut || !maxOut || !sumOut || !countOut || nClusters <= 0 || nCached < 2) return fail(B200_ERR_ARG, "bad argument");
+  if (nClusters > 4096) return fail(B200_ERR_ARG, "more than 4096 clusters");
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc;
+  if ((rc = ensure_init_locked())) return rc;
+  for (int f = 0; f < nCached; ++f)
+    if (label[f] >= nClusters) return fail(B200_ERR_ARG, "label[%d]=%d >= %d clusters", f, label[f], nClusters);
+  Device& d = g_devs[0];
+  CU(cudaSetDevice(d.id));
+  cudaStream_t st = d.stream[0];
+  double h2d = 0.0;
+  const float* d_tri = nullptr;
+  if ((rc = get_cache(d, tri, nCached, st, &h2d, &d_tri))) return rc;
+  if ((rc = upload_vec(d.frameIdx, label, (size_t)nCached, st))) return rc;
+  const size_t K2 = (size_t)nClusters * nClusters;
+  std::vector<LinkCell> cells(K2);
+  for (LinkCell& c : cells) { c.mn = 0xffffffffu; c.mx = 0u; c.cnt = 0ull; c.sum = 0.0; }
+  if ((rc = upload_vec(d.planesB, cells.data(), K2, st))) return rc;
+  const size_t smem = K2 * sizeof(LinkCell) <= 40960 ? K2 * sizeof(LinkCell) : 0;
+  COUNT_LAUNCH();
+  cache_cluster_links_kernel<<<std::min(nCached - 1, d.numSMs * 8), 256, smem, st>>>(d_tri, nCached, (const int*)d.frameIdx.p, nClusters,
+                                                                                   (LinkCell*)d.planesB.p);
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cells.data(), d.planesB.p, K2 * sizeof(LinkCell), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  auto unord = [](unsigned int u) { unsigned int b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; std::memcpy(&f, &b, 4); return (double)f; };
+  for (size_t x = 0; x < K2; ++x) {
+    countOut[x] = (long long)cells[x].cnt;
+    sumOut[x] = cells[x].sum;
+    minOut[x] = cells[x].cnt ? unord(cells[x].mn) : 0.0;
+    maxOut[x] = cells[x].cnt ? unord(cells[x].mx) : 0.0;
+  }
+  std::lock_guard<std::mutex> sl(g_statMu);
+  g_stats.h2d_bytes += h2d; g_stats.d2h_bytes += (double)(K2 * sizeof(LinkCell));
+  return B200_OK;
+}
+
 // ---- cluster: hierarchical agglomerative clustering on the cache triangle (hieragglo.cuh)
 int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetClusters, double epsilon,
                    int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges) {
@@ -2317,13 +2446,8 @@ int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetCluster
   cudaStream_t st = d.stream[0];
   const size_t n = (size_t)nFrames, nElt = n * (n - 1) / 2;
   double h2d = 0.0;
-  if ((rc = d.haTri.reserve(nElt * sizeof(float)))) return rc;
-  {   // the triangle as rows of 1 Mi floats (+ a remainder row): pinned -> DMA, pageable -> staged by the copy pool
-    const size_t W = (size_t)1 << 20, rows = nElt / W, rem = nElt - rows * W;
-    const bool pinned = host_ptr_is_pinned(tri);
-    if (rows && (rc = upload_rows(d, (float*)d.haTri.p, tri, W, 0, (int)rows, W, pinned, st, &h2d))) return rc;
-    if (rem && (rc = upload_rows(d, (float*)d.haTri.p + rows * W, tri + rows * W, rem, 0, 1, rem, pinned, st, &h2d))) return rc;
-  }
+  const float* d_tri = nullptr;
+  if ((rc = get_cache(d, tri, nFrames, st, &h2d, &d_tri))) return rc;
   // symmetric n x n working matrices (rows contiguous): 4 bytes per entry, + 8 for the sums of average linkage
   if ((rc = d.haD.reserve(n * n * sizeof(float)))) return rc;
   if (linkage == 1 && (rc = d.haS.reserve(n * n * sizeof(double)))) return rc;
@@ -2358,7 +2482,7 @@ int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetCluster
   a.rkey = (ha_u64*)(base + oKeys); a.lb2 = (float*)(base + oLb2); a.rlb = (unsigned int*)(base + oRlb);
   CU(cudaMemsetAsync(a.ign, 0, n, st));
   COUNT_LAUNCH();
-  hieragglo_expand_kernel<<<std::min<int>(nFrames, d.numSMs * 16), 256, 0, st>>>((const float*)d.haTri.p, nFrames, a.D, a.S);
+  hieragglo_expand_kernel<<<std::min<int>(nFrames, d.numSMs * 16), 256, 0, st>>>(d_tri, nFrames, a.D, a.S);
   CU(cudaGetLastError());
   COUNT_LAUNCH();
   hieragglo_init_kernel<<<std::min<int>((nFrames + 7) / 8, d.numSMs * 16), 256, 0, st>>>(a);

@@ -457,3 +457,77 @@ __global__ void __launch_bounds__(256) hieragglo_init_kernel(HaArgs a) {
 }
 
 }  // namespace b200
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cache consumers of the cluster post-processing (src/Cluster/BestReps.cpp:131-296, src/Cluster/Output.cpp:164-225,
+// src/Cluster/Algorithm_HierAgglo.cpp:353-408): sums of cached distances over the members of the clusters.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace b200 {
+
+__device__ __forceinline__ size_t cache_tri_idx(int n, int a, int b) {   // src/Matrix.h:110-122
+  if (a > b) { int t = a; a = b; b = t; }
+  return (size_t)n * (size_t)a - ((size_t)a * ((size_t)a + 1)) / 2 + (size_t)b - (size_t)a - 1;
+}
+
+/// One thread per listed member p of a cluster: cum[p] = sum over the other members q of d(p, q), added in list order in
+/// double exactly as the inner loop of BestReps::FindBestRepFrames_CumulativeDist does (so that equal candidates -- duplicate
+/// frames -- compare as in the reference); up[p] / up2[p] = sums of d and d^2 over the members AFTER p (the contribution of
+/// row p to the within-cluster average and its standard deviation, Output.cpp:195-225).
+__global__ void __launch_bounds__(128) cache_cluster_sums_kernel(const float* __restrict__ tri, int n, const int* __restrict__ members,
+                                                                 const int* __restrict__ offsets, const int* __restrict__ clusterOf,
+                                                                 int total, double* cum, double* up, double* up2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int c = clusterOf[p], lo = offsets[c], hi = offsets[c + 1], i = members[p];
+  double s = 0.0, u = 0.0, u2 = 0.0;
+  for (int q = lo; q < hi; ++q) {
+    if (q == p) continue;
+    const double d = (double)tri[cache_tri_idx(n, i, members[q])];
+    s = __dadd_rn(s, d);
+    if (q > p) { u = __dadd_rn(u, d); u2 = __dadd_rn(u2, __dmul_rn(d, d)); }
+  }
+  cum[p] = s;
+  if (up) up[p] = u;
+  if (up2) up2[p] = u2;
+}
+
+/// Linkage between every pair of clusters from ONE pass over the cache triangle (Algorithm_HierAgglo::ClusterDistance for
+/// all pairs: the reference walks the frame pairs of every cluster pair, N^2/2 cache reads through virtual calls).
+/// label[f] = cluster of cached frame f or -1 (not in a cluster / sieved out and excluded).  table[c1 * K + c2], c1 < c2:
+/// minimum and maximum as ordered bits, sum in double, count.
+struct LinkCell { unsigned int mn, mx; unsigned long long cnt; double sum; };
+__global__ void __launch_bounds__(256) cache_cluster_links_kernel(const float* __restrict__ tri, int n, const int* __restrict__ label,
+                                                                  int K, LinkCell* table) {
+  extern __shared__ unsigned char smem_links[];
+  LinkCell* loc = reinterpret_cast<LinkCell*>(smem_links);
+  const bool useSmem = (size_t)K * K * sizeof(LinkCell) <= 40960;
+  if (useSmem) {
+    for (int x = threadIdx.x; x < K * K; x += blockDim.x) { loc[x].mn = 0xffffffffu; loc[x].mx = 0u; loc[x].cnt = 0ull; loc[x].sum = 0.0; }
+    __syncthreads();
+  }
+  LinkCell* tgt = useSmem ? loc : table;
+  for (int i = blockIdx.x; i < n - 1; i += gridDim.x) {
+    const int ci = label[i];
+    if (ci < 0) continue;
+    const size_t base = (size_t)n * (size_t)i - ((size_t)i * ((size_t)i + 1)) / 2 - (size_t)i - 1;   // + j
+    for (int j = i + 1 + threadIdx.x; j < n; j += blockDim.x) {
+      const int cj = label[j];
+      if (cj < 0 || cj == ci) continue;
+      const float v = tri[base + j];
+      LinkCell* cell = tgt + (ci < cj ? (size_t)ci * K + cj : (size_t)cj * K + ci);
+      const unsigned int o = ha_ord(v);
+      atomicMin(&cell->mn, o); atomicMax(&cell->mx, o);
+      atomicAdd(&cell->cnt, 1ull); atomicAdd(&cell->sum, (double)v);
+    }
+  }
+  if (useSmem) {
+    __syncthreads();
+    for (int x = threadIdx.x; x < K * K; x += blockDim.x) {
+      if (loc[x].cnt == 0ull) continue;
+      atomicMin(&table[x].mn, loc[x].mn); atomicMax(&table[x].mx, loc[x].mx);
+      atomicAdd(&table[x].cnt, loc[x].cnt); atomicAdd(&table[x].sum, loc[x].sum);
+    }
+  }
+}
+
+}  // namespace b200

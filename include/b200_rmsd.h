@@ -195,6 +195,29 @@ int b200_rmsavgcorr(const float* crd, size_t frameStrideFloats, int nFrames, con
 int b200_hieragglo(const float* tri, int nFrames, int linkage, int targetClusters, double epsilon,
                    int* mergeInto, int* mergeFrom, float* findMin, int* nCalls, int* nMerges);
 
+/* ---- cluster: consumers of the pairwise cache in the post-processing --------------------------------------------
+ * Between begin and end the cache triangle (DataSet_PairwiseCache_MEM::Ptr(), nCached frames) stays on device 0 and the
+ * calls of this section and b200_hieragglo that pass the same `tri` skip the upload (Cluster::Control::Run,
+ * src/Cluster/Control.cpp:755-830: clustering, best representatives and the summary read the same, unchanging cache).
+ * end(NULL) drops any. */
+int b200_cache_resident_begin(const float* tri, int nCached);
+int b200_cache_resident_end(const float* tri);
+/* Sums of cached distances over the members of every cluster.  members: cache indices of the frames of all clusters,
+ * concatenated in list order; cluster c owns members[offsets[c] .. offsets[c+1]).  cumOut[p] = sum over the other members
+ * q of its cluster of d(p, q), added in list order in double exactly like the inner loop of
+ * BestReps::FindBestRepFrames_CumulativeDist (src/Cluster/BestReps.cpp:157-166, :243-257); upOut[p] / up2Out[p] (nullable)
+ * = sums of d and d*d over the members after p: summed over p they are the numerators of the within-cluster average and
+ * its standard deviation (Cluster::Output::Summary, src/Cluster/Output.cpp:195-225). */
+int b200_cache_cluster_sums(const float* tri, int nCached, const int* members, const int* offsets, int nClusters,
+                            double* cumOut, double* upOut, double* up2Out);
+/* Linkage between every two clusters in ONE pass over the triangle (Algorithm_HierAgglo::ClusterDistance for all cluster
+ * pairs, src/Cluster/Algorithm_HierAgglo.cpp:353-408, as Cluster::Output::Summary needs them, Output.cpp:164-172):
+ * label[f] = cluster of cached frame f, or -1 for a frame that takes no part (not clustered, or sieved out and excluded).
+ * Outputs are nClusters x nClusters row-major, entries [c1*nClusters + c2] with c1 < c2: minimum, maximum, sum and
+ * count of the cached distances between members of c1 and c2 (the sum is accumulated in double, in no fixed order). */
+int b200_cache_cluster_links(const float* tri, int nCached, const int* label, int nClusters,
+                             double* minOut, double* maxOut, double* sumOut, long long* countOut);
+
 /* ---- device-resident variants (benchmarks, pipelines that keep COORDS in HBM)
  * All pointers are DEVICE pointers on the current device; `stream` is a
  * cudaStream_t (NULL = default stream); asynchronous w.r.t. the host.

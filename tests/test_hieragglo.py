@@ -141,6 +141,55 @@ def test_gpu_tight_cluster_long_rescan_lists(b200, oracle):
                 assert_same(got, want, (linkage, target, eps, team))
 
 
+@pytest.mark.gpu
+def test_gpu_cache_consumers(b200):
+    """Sums over cluster members (BestReps cumulative distance: sequential, in list order, bit-equal to the reference's
+    inner loop; the within-cluster numerators of Summary) and the linkage tables between clusters from one pass over the
+    triangle; with and without the cache announced as resident."""
+    rng = np.random.default_rng(500)
+    n = 700
+    tri = cache_from_points(rng, n, dup=6)
+    sq = np.zeros((n, n), np.float32)
+    sq[np.triu_indices(n, 1)] = tri
+    sq = sq + sq.T
+    perm = rng.permutation(n)
+    lists = [perm[:300], perm[300:301], perm[301:303], perm[303:650]]          # 50 frames in no cluster
+    def want_sums():
+        cum, up, up2 = [], [], []
+        for m in lists:
+            for a, i in enumerate(m):
+                s = u = u2 = 0.0
+                for b_, j in enumerate(m):
+                    if b_ == a:
+                        continue
+                    d = float(sq[i, j])
+                    s += d
+                    if b_ > a:
+                        u += d; u2 += d * d
+                cum.append(s); up.append(u); up2.append(u2)
+        return np.array(cum), np.array(up), np.array(up2)
+    wc, wu, wu2 = want_sums()
+    label = np.full(n, -1, np.int32)
+    for c, m in enumerate(lists):
+        label[m] = c
+    for resident in (False, True):
+        t = b200.cache_resident_begin(tri, n) if resident else tri
+        cum, up, up2 = b200.cache_cluster_sums(t, n, lists)
+        assert np.array_equal(cum, wc) and np.array_equal(up, wu) and np.array_equal(up2, wu2)
+        mn, mx, sm, cnt = b200.cache_cluster_links(t, n, label, len(lists))
+        for c1 in range(len(lists)):
+            for c2 in range(c1 + 1, len(lists)):
+                blk = sq[np.ix_(lists[c1], lists[c2])].astype(np.float64)
+                assert cnt[c1, c2] == blk.size and mn[c1, c2] == blk.min() and mx[c1, c2] == blk.max()
+                assert abs(sm[c1, c2] - blk.sum()) <= 1e-9 * blk.sum()
+        got = b200.hieragglo(t, n, 1, 5, None)                                  # the resident copy is only read
+        if resident:
+            b200.cache_resident_end(t)
+            assert_same(got, first, "resident cache")
+        else:
+            first = got
+
+
 def partition(merges, n):
     """Cluster label (lowest member) of every frame after replaying the merges."""
     parent = np.arange(n)
