@@ -288,3 +288,45 @@ int Cpptraj::B200::RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mas
   mprintf("\tB200: %zu window sizes over %zu frames on the device in %.4f s.\n", windows.size(), crd.Size(), t_call.Total());
   return 0;
 }
+
+int Cpptraj::B200::CacheClusterSums(const float* triangle, int nCached, std::vector<int> const& members,
+                                    std::vector<int> const& offsets, std::vector<double>& cum, std::vector<double>* up,
+                                    std::vector<double>* up2)
+{
+  if (Init()) return 1;
+  cum.assign( members.size(), 0.0 );
+  if (up != 0) up->assign( members.size(), 0.0 );
+  if (up2 != 0) up2->assign( members.size(), 0.0 );
+  if (members.empty() || offsets.size() < 2) return 0;
+  int err = b200_cache_cluster_sums(triangle, nCached, &members[0], &offsets[0], (int)offsets.size() - 1, &cum[0],
+                                    (up != 0 ? &(*up)[0] : 0), (up2 != 0 ? &(*up2)[0] : 0));
+  if (err) return b200_err("cluster sums over the cache");
+  return 0;
+}
+
+int Cpptraj::B200::CacheClusterLinks(const float* triangle, int nCached, std::vector<int> const& label, int K,
+                                     std::vector<double>& mn, std::vector<double>& mx, std::vector<double>& sum,
+                                     std::vector<long long>& count)
+{
+  if (Init()) return 1;
+  size_t K2 = (size_t)K * (size_t)K;
+  mn.assign(K2, 0.0); mx.assign(K2, 0.0); sum.assign(K2, 0.0); count.assign(K2, 0);
+  if (K < 1 || (int)label.size() != nCached) return 1;
+  int err = b200_cache_cluster_links(triangle, nCached, &label[0], K, &mn[0], &mx[0], &sum[0], &count[0]);
+  if (err) return b200_err("cluster linkage over the cache");
+  return 0;
+}
+
+int Cpptraj::B200::ResidentCache::Begin(const float* triangle, int nCached) {
+  if (Init()) return 1;
+  if (tri_ != 0) { b200_cache_resident_end( tri_ ); tri_ = 0; }
+  if (triangle == 0 || nCached < 2) return 0;
+  if (b200_cache_resident_begin(triangle, nCached)) {
+    mprintf("Warning: B200: pairwise cache not kept on the device (%s); calls will upload it.\n", b200_last_error());
+    return 1;
+  }
+  tri_ = triangle;
+  return 0;
+}
+
+Cpptraj::B200::ResidentCache::~ResidentCache() { if (tri_ != 0) b200_cache_resident_end( tri_ ); }

@@ -71,6 +71,33 @@ int RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<
   */
 int HierAgglo(const float* triangle, int nCached, int linkage, int targetClusters, double epsilon,
               std::vector<int>& mergeInto, std::vector<int>& mergeFrom, std::vector<float>& findMin);
+/** Sums of cached distances over cluster members (BestReps cumulative distance, Cluster/BestReps.cpp:157-166,243-257; the
+  * within-cluster average of Output::Summary, Cluster/Output.cpp:195-225).  \a members: cache indices of all clusters'
+  * frames concatenated in list order, \a offsets: start of every cluster (+ the end).  \a cum[p]: sum of the distances of
+  * member p to the other members of its cluster, added in list order; \a up / \a up2 (may be 0): sums of d and d*d over
+  * the members after p.
+  */
+int CacheClusterSums(const float* triangle, int nCached, std::vector<int> const& members, std::vector<int> const& offsets,
+                     std::vector<double>& cum, std::vector<double>* up, std::vector<double>* up2);
+/** Minimum, maximum, sum and count of the cached distances between every two clusters (Algorithm_HierAgglo::ClusterDistance
+  * for all pairs, Cluster/Algorithm_HierAgglo.cpp:353-408).  \a label[f]: cluster index of cached frame f or -1.  Tables
+  * are K x K row-major, entries c1 < c2.
+  */
+int CacheClusterLinks(const float* triangle, int nCached, std::vector<int> const& label, int K, std::vector<double>& mn,
+                      std::vector<double>& mx, std::vector<double>& sum, std::vector<long long>& count);
+/** Keeps an in-memory pairwise cache on the device while it exists (clustering, best representatives and the summary
+  * read the same, unchanging triangle: Cluster/Control.cpp:770-1019).
+  */
+class ResidentCache {
+  public:
+    ResidentCache() : tri_(0) {}
+    ~ResidentCache();
+    int Begin(const float* triangle, int nCached);
+  private:
+    ResidentCache(ResidentCache const&);
+    ResidentCache& operator=(ResidentCache const&);
+    const float* tri_;
+};
 /** Keeps the selected span of a COORDS set on the device while it exists (Cluster::Control::Run, Cluster/Control.cpp:690-830):
   * the centroid / frame-to-centroid calls of a clustering run then skip the upload.  The frames must not change meanwhile.
   */

@@ -97,17 +97,20 @@ cluster crd1 @CA hieragglo epsilon 2.5 averagelinkage rms out hs.out summary hs.
 """, [("hs.out", "table"), ("hs.summary.dat", "text")]),
     # src/Cluster/Algorithm_HierAgglo.cpp:97-245: the whole merge loop on the device (b200_hieragglo) for the three
     # linkages, stopping on the cluster count, on epsilon, and on whichever comes first; the epsilon-vs-clusters file
-    # lists every FindMin value in order, the info file every cluster's frames
+    # lists every FindMin value in order, the info file every cluster's frames; the summaries carry what the post-processing
+    # reads from the cache: best representatives by cumulative distance (with and without sieved frames), within-cluster
+    # averages and standard deviations, average linkage to the other clusters
     "cluster_hier_linkages": ("""noprogress
 parm {D}/tz2.parm7
 trajin {D}/tz2.crd
-cluster L1 @CA hieragglo clusters 4 linkage rms out hl.single.dat info hl.single.info epsilonplot hl.single.eps
+cluster L1 @CA hieragglo clusters 4 linkage rms out hl.single.dat info hl.single.info epsilonplot hl.single.eps summary hl.single.summary savenreps 3
 cluster L2 @CA hieragglo epsilon 1.8 averagelinkage rms out hl.avg.dat summary hl.avg.summary epsilonplot hl.avg.eps
-cluster L3 :2-12 hieragglo clusters 6 epsilon 3.0 complete rms mass out hl.complete.dat info hl.complete.info epsilonplot hl.complete.eps
-cluster L4 @CA hieragglo clusters 3 averagelinkage rms nofit sieve 3 out hl.sieve.dat info hl.sieve.info
-""", [("hl.single.dat", "table"), ("hl.single.info", "text"), ("hl.single.eps", "table"), ("hl.avg.dat", "table"),
-      ("hl.avg.summary", "text"), ("hl.avg.eps", "table"), ("hl.complete.dat", "table"), ("hl.complete.info", "text"),
-      ("hl.complete.eps", "table"), ("hl.sieve.dat", "table"), ("hl.sieve.info", "text")]),
+cluster L3 :2-12 hieragglo clusters 6 epsilon 3.0 complete rms mass out hl.complete.dat info hl.complete.info epsilonplot hl.complete.eps summary hl.complete.summary
+cluster L4 @CA hieragglo clusters 3 averagelinkage rms nofit sieve 3 out hl.sieve.dat info hl.sieve.info summary hl.sieve.summary
+""", [("hl.single.dat", "table"), ("hl.single.info", "text"), ("hl.single.eps", "table"), ("hl.single.summary", "text"),
+      ("hl.avg.dat", "table"), ("hl.avg.summary", "text"), ("hl.avg.eps", "table"), ("hl.complete.dat", "table"),
+      ("hl.complete.info", "text"), ("hl.complete.eps", "table"), ("hl.complete.summary", "text"), ("hl.sieve.dat", "table"),
+      ("hl.sieve.info", "text"), ("hl.sieve.summary", "text")]),
     # src/Cluster/Cmatrix_Binary.cpp:12-21: the cache filled on the device written by the reference's own binary writer
     # (savepairdist), read back (readdata) and clustered on the device again from the loaded cache
     "cluster_cmatrix_roundtrip": ("""noprogress
