@@ -808,10 +808,12 @@ def cpptraj_leg(cfg, cpu_seconds):
     cores = host_cores()
     omp_env = dict(os.environ, OMP_NUM_THREADS=str(cores))
     cl_pats = {"pairwise_s": r"Pairwise Calc\.\s*:\s*([0-9.]+) s", "clustering_s": r"TIME:\s+Clustering\s*:\s*([0-9.]+) s",
-               "analyses_s": r"TIME: Analyses took ([0-9.]+) seconds", "device_merges_s": r"initial clusters on the device in ([0-9.]+) s"}
-    cl_deck = "noprogress\nparm t.pdb\ntrajin t.binpos 1 %d\ncluster C1 @CA hieragglo clusters 10 averagelinkage rms\nrun\n"
+               "analyses_s": r"TIME: Analyses took ([0-9.]+) seconds", "device_merges_s": r"initial clusters on the device in ([0-9.]+) s",
+               "cluster_init_s": r"Cluster Init\.\s*:\s*([0-9.]+) s", "cluster_post_s": r"Cluster Post\.\s*:\s*([0-9.]+) s",
+               "best_rep_s": r"Find best rep\.\s*:\s*([0-9.]+) s", "summary_s": r"Summary calc\s*:\s*([0-9.]+) s"}
+    cl_deck = "noprogress\nparm t.pdb\ntrajin t.binpos 1 %d\ncluster C1 @CA hieragglo clusters 10 averagelinkage rms summary cl.summary.dat\nrun\n"
     nB, nO = nF, min(nF, 1500)
-    out["cluster_hieragglo"] = {"deck": "cluster C1 @CA hieragglo clusters 10 averagelinkage rms (in-memory pairwise cache)",
+    out["cluster_hieragglo"] = {"deck": "cluster C1 @CA hieragglo clusters 10 averagelinkage rms summary cl.summary.dat (in-memory pairwise cache)",
                                 "cpptraj_b200": dict(run_deck(b200_bin, cl_deck % nB, dict(os.environ), cl_pats), frames=nB)}
     if os.path.exists(omp_bin):
         out["cluster_hieragglo"]["cpptraj_omp"] = dict(run_deck(omp_bin, cl_deck % nO, omp_env, cl_pats), frames=nO, threads=cores,
