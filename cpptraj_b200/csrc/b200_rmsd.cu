@@ -573,6 +573,12 @@ int run_pair_i8_band(const Device& d, const I8Set& A, const I8Set& B, int rowLo,
   a.out = out; a.outBase = outBase; a.ldo = ldo; a.dbgS = dbgS;
   { const char* e = getenv("B200_I8_DEBUG_MODE"); a.dbgMode = e ? atoi(e) : 0; }
   a.dbgClk = g_dbgClk;
+  a.dbgRing = nullptr;
+  if (a.dbgMode == 7) {
+    static long long* ring = nullptr;
+    if (!ring) CU(cudaMalloc(&ring, (size_t)160 * 4 * 10 * 448 * sizeof(long long)));
+    a.dbgRing = ring;
+  }
   return i8_cta_group() == 2 ? run_pair_i8_band_t<2>(d, a, rowLo, rowHi, tri, st) : run_pair_i8_band_t<1>(d, a, rowLo, rowHi, tri, st);
 }
 

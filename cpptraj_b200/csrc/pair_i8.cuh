@@ -386,7 +386,10 @@ struct PairI8Args {
   long long* dbgClk;   // nullable: per-CTA cycle counters [16] (timing experiments)
   int dbgMode;         // 0 normal; timing experiments: 1 no per-pair solve, 2 drain only frees TMEM,
                        // 3 = 2 + no operand loads, 4 = 2 + every CTA streams the same A rows, 5 = 2 + no MMAs,
-                       // 6 = solve warps only recycle the exchange buffer
+                       // 6 = solve warps only recycle the exchange buffer,
+                       // 7 = no FP64 window, the solve warps only export the integer covariance to dbgRing (what a tensor SM
+                       //     would still do if the per-pair solve ran on other SMs)
+  long long* dbgRing;  // mode 7: 4 slots x 10 entries x 448 threads per CTA
 };
 
 /// Row super-tiles [it0, hi) of column tile jt hold at least one wanted pair.
@@ -641,7 +644,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       else mbar_wait(smem_u32(&accEmpty[b]), (uint32_t)(((n >> 1) & 1) ^ 1));
       // FP64 window: the solve warps finished the FP64 part of tile n-2 (they started it when tile n-1's MMAs completed)
       const long long cA = (DBG && dbgClk) ? clock64() : 0;
-      if (!(DBG && dbgMode >= 2 && dbgMode <= 5)) {
+      if (!(DBG && ((dbgMode >= 2 && dbgMode <= 5) || dbgMode == 7))) {
         if (I8_TPW == 1) { if (n >= 2) mbar_wait(smem_u32(fpDone), (uint32_t)(n & 1)); }
         else if (n >= 2 && (n & 1) == 0) mbar_wait(smem_u32(fpDone), (uint32_t)(((n >> 1) - 1) & 1));   // window k closes before tile 2k+2
       }
@@ -727,7 +730,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       // is integer work that would take every other issue slot of the four schedulers while the window's FP64
       // instructions want them: start it when this CTA's solve warps are through (there is slack: the drain of a tile
       // takes ~3600 cycles, the MMAs of the next one ~4100).
-      if (!(DBG && dbgMode >= 2 && dbgMode <= 5)) {
+      if (!(DBG && ((dbgMode >= 2 && dbgMode <= 5) || dbgMode == 7))) {
         if (I8_TPW == 1) { if (n >= 1) mbar_wait(smem_u32(fpLocal), (uint32_t)((n - 1) & 1)); }
         else if (n & 1) mbar_wait(smem_u32(fpLocal), (uint32_t)(((n - 1) >> 1) & 1));   // odd tiles complete as a window opens
       }
@@ -864,6 +867,12 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
 #pragma unroll
           for (int q = 0; q < 3; ++q)   // fold the A digits: exact int64 (|S| < 2^63 for < 131072 atoms)
             SI[3 * p + q] = src[9 * p + q] + (src[9 * p + 3 + q] << 8) + (src[9 * p + 6 + q] << 16);
+        if (DBG && dbgMode == 7) {
+          long long* ring = a.dbgRing + ((size_t)(blockIdx.x * 4 + (n & 3)) * 10) * 448 + (u * 32 + lane);
+#pragma unroll
+          for (int x = 0; x < 9; ++x) __stcg(ring + x * 448, SI[x]);
+          __stcg(ring + 9 * 448, valid ? (((long long)i << 32) | (long long)j) : -1ll);
+        }
 #pragma unroll
         for (int x = 0; x < 9; ++x) S[x] = __ll2double_rn(SI[x]);   // I2F.F64.S64: conversion pipe, not the FP64 pipe
       } else {
@@ -875,6 +884,7 @@ __global__ void __launch_bounds__(I8_THREADS, 1) pair_i8_kernel(PairI8Args a) {
       asm volatile("" ::"d"(S[0]), "d"(S[1]), "d"(S[2]), "d"(S[3]), "d"(S[4]), "d"(S[5]), "d"(S[6]), "d"(S[7]), "d"(S[8]) : "memory");
       __syncwarp();
       if (lane == 0) { mbar_arrive(smem_u32(&xEmpty[2 * h])); mbar_arrive(smem_u32(&xEmpty[2 * h + 1])); }
+      if (DBG && dbgMode == 7) { ++n; it = itN; jt = jtN; have = hasNext; continue; }
       if (DBG && a.dbgS && valid) {
 #pragma unroll
         for (int x = 0; x < 9; ++x) a.dbgS[((size_t)i * a.nCols + j) * 9 + x] = S[x];
