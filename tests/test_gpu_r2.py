@@ -136,6 +136,32 @@ def test_pageable_and_pinned_host_buffers_agree(b200, oracle):
     assert maxdiff(full, oracle.rms2d_full(c[:300], sel, c[1000:1400], sel)) <= TOL
 
 
+def test_whole_frame_selection_takes_the_linear_upload(b200, oracle):
+    """Pinned COORDS whose selected span is the whole frame (span == frame stride) are uploaded by one linear DMA per chunk,
+    any other layout by a pitched copy: same bits either way, and the oracle's values; one-vs-many likewise."""
+    import torch
+    nf, na = 1600, 96
+    c, m, sel = synth_case(77, nf, na)                       # stride == 3 * na: whole frames
+    pc = torch.from_numpy(c).pin_memory()
+    got = b200.rms2d_tri(pc.numpy(), sel, mass=m[sel])
+    assert b200.last_pair_engine()[0] == 2
+    wide = np.zeros((nf, 3 * na + 5), np.float32); wide[:, : 3 * na] = c     # same frames, 5 floats of padding per frame
+    pw = torch.from_numpy(wide).pin_memory()
+    assert np.array_equal(b200.rms2d_tri(pw.numpy(), sel, mass=m[sel]), got)
+    assert np.array_equal(b200.rms2d_tri(c, sel, mass=m[sel]), got)         # pageable
+    sub = np.r_[0:25, 790:815, nf - 25:nf]
+    want = oracle.rms2d_tri(c[sub], sel, mass=m[sel])
+    sq = np.zeros((nf, nf), np.float32); sq[np.triu_indices(nf, 1)] = got
+    assert np.abs(sq[np.ix_(sub, sub)][np.triu_indices(len(sub), 1)].astype(np.float64) - want).max() <= TOL
+    ref_raw = c[3].reshape(-1, 3)[sel].astype(np.float64)
+    w = m[sel]
+    ref = ref_raw - (w[:, None] * ref_raw).sum(0) / w.sum()      # the action hands over a centred reference
+    r_lin = b200.rmsd_1vN(pc.numpy(), sel, ref, mass=w)[0]
+    r_pitch = b200.rmsd_1vN(pw.numpy(), sel, ref, mass=w)[0]
+    assert np.array_equal(r_lin, r_pitch)
+    assert np.abs(r_lin - oracle.rmsd_1vN(c, sel, ref_raw, mass=w)).max() <= TOL
+
+
 def test_shards_agree_on_the_fixed_point_grid(b200, oracle):
     """Every shard of a matrix takes its scale from the same (top) frames: the shards of a 4-way split, computed one
     after the other, reproduce the single-shard result bit for bit; pinning fewer bits changes the result within the
