@@ -3,7 +3,7 @@ timing mode of the kernel (B200_I8_DEBUG_MODE: 0 product, 7 tensor SMs only expo
 per-pair solve --, 2 MMAs + operand stream alone) while NVML samples SM clock and board power every 10 ms, and reads the
 kernel's own cycle counters (clock64 in the MMA warp) for one step next to its CUDA-event time: cycles / time = the SM
 clock the kernel actually ran at.  Last: the tcgen05 kind::i8 issue probe (operands fixed in shared memory) sustained.
-usage (GPU box): python tools/power_probe.py [frames] [atoms] [seconds]"""
+usage (GPU box): [B200_PROBE_MODES=0,7,2] python tools/power_probe.py [frames] [atoms] [seconds]"""
 import os, sys, time, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -27,7 +27,7 @@ def timed(n):
     for _ in range(n): step()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
-for mode in (0, 7, 2):
+for mode in [int(x) for x in os.environ.get("B200_PROBE_MODES", "0,7,2").split(",")]:
     os.environ["B200_I8_DEBUG_MODE"] = str(mode)
     for _ in range(3): step()
     torch.cuda.synchronize(); time.sleep(0.5)           # let the board cool to idle clocks / power
