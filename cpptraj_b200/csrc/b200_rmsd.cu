@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cmath>
 #include <cstdarg>
@@ -50,6 +51,18 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ------------------------------------------------------------------ buffers
+// B200_ALLOC_TRACE=1: what a call spent in cudaMalloc / cudaMallocHost (the fixed cost of a process's first call)
+struct AllocTrace {
+  std::atomic<long long> devNs{0}, pinNs{0}, devBytes{0}, pinBytes{0};
+  bool on = getenv("B200_ALLOC_TRACE") != nullptr;
+  static long long now() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  void report(const char* what, long long callNs) {
+    if (!on) return;
+    fprintf(stderr, "B200_ALLOC_TRACE %s: %.4f s in the call; cudaMalloc %.4f s (%.1f MB), cudaMallocHost %.4f s (%.1f MB)\n", what, callNs * 1e-9,
+            devNs.exchange(0) * 1e-9, devBytes.exchange(0) / 1e6, pinNs.exchange(0) * 1e-9, pinBytes.exchange(0) / 1e6);
+  }
+};
+AllocTrace g_allocTrace;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -59,7 +72,9 @@ struct DevBuf {
     p = nullptr; cap = 0;
     // grow a little beyond the request to avoid re-allocation churn
     size_t want = bytes + bytes / 8 + 256;
+    const long long t0 = g_allocTrace.on ? AllocTrace::now() : 0;
     cudaError_t e = cudaMalloc(&p, want);
+    if (g_allocTrace.on) { g_allocTrace.devNs += AllocTrace::now() - t0; g_allocTrace.devBytes += (long long)want; }
     if (e != cudaSuccess) { cudaGetLastError(); return fail(B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e)); }
     cap = want;
     return B200_OK;
@@ -73,7 +88,9 @@ struct PinBuf {
     if (bytes <= cap) return B200_OK;
     if (p) cudaFreeHost(p);
     p = nullptr; cap = 0;
+    const long long t0 = g_allocTrace.on ? AllocTrace::now() : 0;
     cudaError_t e = cudaMallocHost(&p, bytes);
+    if (g_allocTrace.on) { g_allocTrace.pinNs += AllocTrace::now() - t0; g_allocTrace.pinBytes += (long long)bytes; }
     if (e != cudaSuccess) { cudaGetLastError(); return fail(B200_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
     cap = bytes;
     return B200_OK;
@@ -1373,13 +1390,16 @@ int b200_rms2d_tri(const float* crd, size_t frameStrideFloats, int nFramesTotal,
   // fixed-point grid (and engine) for the whole matrix
   ExtentShare share;
   share.parties = nd;
-  return for_each_device([&](int i) -> int {
+  const long long t0 = g_allocTrace.on ? AllocTrace::now() : 0;
+  rc = for_each_device([&](int i) -> int {
     int r0 = 0, r1 = 0;
     int r = shard_rows(nFrames, i, nd, &r0, &r1);
     if (r) { if (nd > 1) share.abandon(); return r; }
     return host_tri_on_device(g_devs[i], crd, frameStrideFloats, nFramesTotal, frameIdx, nFrames, atomIdx, nAtoms, mass, fit,
                               r0, r1, outTri, nd > 1 ? &share : nullptr);
   });
+  g_allocTrace.report("b200_rms2d_tri", g_allocTrace.on ? AllocTrace::now() - t0 : 0);
+  return rc;
 }
 
 }  // extern "C"
