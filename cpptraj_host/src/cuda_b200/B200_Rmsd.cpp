@@ -91,6 +91,55 @@ int Cpptraj::B200::Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask,
   return err ? b200_err("rms2d") : 0;
 }
 
+/// The selected atoms of every frame of \a set, frame after frame, as float.
+static void b200_pack_selected(DataSet_Coords& set, AtomMask const& mask, std::vector<float>& buf) {
+  Frame frm;
+  frm.SetupFrameFromMask( mask, set.Top().Atoms() );
+  const size_t n3 = (size_t)3 * (size_t)mask.Nselected();
+  buf.resize( set.Size() * n3 );
+  for (size_t idx = 0; idx != set.Size(); idx++) {
+    set.GetFrame( (int)idx, frm, mask );
+    const double* x = frm.xAddress();
+    float* dst = &buf[idx * n3];
+    for (size_t i = 0; i != n3; i++) dst[i] = (float)x[i];
+  }
+}
+
+int Cpptraj::B200::Rms2dPacked(DataSet_Coords& tgt, AtomMask const& tgtMask, std::vector<double> const& tgtMass,
+                               DataSet_Coords& ref, AtomMask const& refMask, std::vector<double> const& refMass,
+                               bool fullMatrix, bool fit, DataSet_MatrixFlt& out)
+{
+  if (Init()) return 1;
+  const int nsel = tgtMask.Nselected();
+  if (nsel != refMask.Nselected()) {
+    mprinterr("Error: B200 RMSD: # target atoms (%i) != # reference atoms (%i)\n", nsel, refMask.Nselected());
+    return 1;
+  }
+  if (tgt.Size() < 1 || nsel < 1) return 0;
+  Timer t_read;
+  t_read.Start();
+  std::vector<float> tbuf, rbuf;
+  b200_pack_selected( tgt, tgtMask, tbuf );
+  if (fullMatrix) b200_pack_selected( ref, refMask, rbuf );
+  t_read.Stop();
+  std::vector<int> ident( (size_t)nsel );
+  for (int i = 0; i < nsel; i++) ident[i] = i;
+  const size_t n3 = (size_t)3 * (size_t)nsel;
+  float* mat = static_cast<float*>( out.MatrixPtr() );
+  Timer t_call;
+  t_call.Start();
+  int err;
+  if (!fullMatrix)
+    err = b200_rms2d_tri(&tbuf[0], n3, (int)tgt.Size(), 0, (int)tgt.Size(), &ident[0], nsel, ptr_or_null(tgtMass), fit ? 1 : 0, mat);
+  else
+    err = b200_rms2d_full(&tbuf[0], n3, (int)tgt.Size(), &ident[0], &rbuf[0], n3, (int)ref.Size(), &ident[0],
+                          nsel, ptr_or_null(tgtMass), ptr_or_null(refMass), fit ? 1 : 0, mat);
+  t_call.Stop();
+  if (!err) mprintf("\tB200 RMSD path: %zu x %zu frames, %i atoms: selected atoms read once in %.4f s, %.4f s in the library.\n",
+                    tgt.Size(), ref.Size(), nsel, t_read.Total(), t_call.Total());
+  return err ? b200_err("rms2d") : 0;
+}
+
 int Cpptraj::B200::CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
                              bool fit, Cluster::Cframes const& framesToCache, float* triangle)
 {

@@ -8,6 +8,7 @@
   */
 #include <vector>
 #include <cstddef>
+class DataSet_Coords;
 class DataSet_Coords_CRD;
 class DataSet_MatrixFlt;
 class DataSet_double;
@@ -30,6 +31,14 @@ std::vector<double> MassesOf(Frame const&);
 int Rms2d(DataSet_Coords_CRD const& tgt, AtomMask const& tgtMask, std::vector<double> const& tgtMass,
           DataSet_Coords_CRD const& ref, AtomMask const& refMask, std::vector<double> const& refMass,
           bool fullMatrix, bool fit, DataSet_MatrixFlt& out);
+/** The same for COORDS-group sets that are NOT in-memory float arrays -- DataSet::TRAJ (frames stay on disk: `loadtraj`,
+  * `2drms ... reftraj <file>`), reference frames, FRAMES sets: the reference reads every target frame once PER REFERENCE
+  * FRAME (Analysis_Rms2d.cpp:270-274); here the selected atoms of every frame are read ONCE, stored as float (what
+  * createcrd / loadcrd would hold, CompactFrameArray.cpp:200-214) and handed to the same library calls.
+  */
+int Rms2dPacked(DataSet_Coords& tgt, AtomMask const& tgtMask, std::vector<double> const& tgtMass,
+                DataSet_Coords& ref, AtomMask const& refMask, std::vector<double> const& refMass,
+                bool fullMatrix, bool fit, DataSet_MatrixFlt& out);
 /** Pairwise-cache fill (MetricArray::calcFrameDistances, Cluster/MetricArray.cpp:766-801) for a single Metric_RMS.
   * \a triangle is DataSet_PairwiseCache_MEM::Ptr() after SetupCache sized it for framesToCache.size() frames.
   */

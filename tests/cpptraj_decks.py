@@ -49,7 +49,7 @@ rms ToPrevious :2-12@CA previous out Previous.dat
     # data set that reads the RMSD set while it is being filled (filter), and the modified coordinates written out
     "crdaction_rms": ("""noprogress
 parm {D}/tz2.parm7
-loadcrd {D}/tz2.crd name CRD
+loadcrd {D}/tz2.crd 3 60 2 name CRD
 crdaction CRD rms R1 first @CA,C,N out crd_rms.dat savematrices matricesout crd_rmat.dat
 crdaction CRD rms R2 first :2-12@CA nofit mass out crd_rms_nofit.dat crdframes 3,90,4
 crdout CRD fitted.crd
@@ -64,7 +64,7 @@ trajout aligned.crd
     # src/Exec_CrdTransform.cpp:75-134: iterative RMS refinement (every iteration fits all frames to a new average)
     "crdtransform_rmsrefine": ("""noprogress
 parm {D}/tz2.parm7
-loadcrd {D}/tz2.crd name CRD
+loadcrd {D}/tz2.crd 3 60 2 name CRD
 crdtransform CRD name REFINED rmsrefine mask @CA rmstol 0.0005
 crdout REFINED refined.crd
 """, [("refined.crd", "crd")]),
@@ -143,4 +143,24 @@ reference {D}/tz2.crd 100 [late]
 cluster C1 @CA clusters 5 rms out ar.out summary ar.summary.dat assignrefs refcut 2.0 refmask @CA
 cluster C2 :2-12 clusters 4 rms mass summary ar.mass.summary.dat assignrefs refcut 1.0 refmask :2-12@CA,C,N
 """, [("ar.out", "table"), ("ar.summary.dat", "text"), ("ar.mass.summary.dat", "text")]),
+    # src/Analysis_Rms2d.cpp:92-110,247-287 with sets that are NOT in-memory COORDS: a TRAJ set (loadtraj: frames stay on disk),
+    # a reference trajectory given as a file name (test/Test_2DRMS/RunTest.sh:33-46, ASCII instead of NetCDF), different
+    # target / reference masks inside a TRAJ set, an in-memory target against a TRAJ reference.  (Golden made with ONE
+    # thread: the reference reads a TRAJ target from inside its OpenMP loop.)
+    "rms2d_traj_sets": ("""noprogress
+parm {D}/tz2.parm7
+loadtraj name TZ2 {D}/tz2.crd 1 48
+2drms crdset TZ2 :3-7 out traj_tri.dat
+2drms crdset TZ2 :2-12@CA,C,N mass out traj_mass.dat
+2drms crdset TZ2 :3-7 out traj_reftraj.dat reftraj {D}/tz2.crd
+2drms crdset TZ2 :2 :11 nofit out traj_nofit_masks.dat
+loadcrd {D}/tz2.crd 3 60 2 name CRD
+2drms crdset CRD :3-7 out crd_reftraj.dat reftraj TZ2
+precision traj_tri.dat 12 6
+precision traj_mass.dat 12 6
+precision traj_reftraj.dat 12 6
+precision traj_nofit_masks.dat 12 6
+precision crd_reftraj.dat 12 6
+""", [("traj_tri.dat", "table"), ("traj_mass.dat", "table"), ("traj_reftraj.dat", "table"), ("traj_nofit_masks.dat", "table"),
+      ("crd_reftraj.dat", "table")]),
 }
