@@ -152,6 +152,31 @@ int Cpptraj::B200::CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask
   return 0;
 }
 
+int Cpptraj::B200::CacheFillPacked(DataSet_Coords& crd, AtomMask const& mask, std::vector<double> const& mass,
+                                   bool fit, Cluster::Cframes const& framesToCache, float* triangle)
+{
+  if (Init()) return 1;
+  if (framesToCache.size() < 2) return 0;
+  const int nsel = mask.Nselected();
+  const size_t n3 = (size_t)3 * (size_t)nsel;
+  Frame frm;
+  frm.SetupFrameFromMask( mask, crd.Top().Atoms() );
+  std::vector<float> buf( framesToCache.size() * n3 );
+  size_t row = 0;
+  for (Cluster::Cframes::const_iterator f = framesToCache.begin(); f != framesToCache.end(); ++f, ++row) {
+    crd.GetFrame( *f, frm, mask );
+    const double* x = frm.xAddress();
+    float* dst = &buf[row * n3];
+    for (size_t i = 0; i != n3; i++) dst[i] = (float)x[i];
+  }
+  std::vector<int> ident( (size_t)nsel );
+  for (int i = 0; i < nsel; i++) ident[i] = i;
+  if (b200_rms2d_tri(&buf[0], n3, (int)framesToCache.size(), 0, (int)framesToCache.size(), &ident[0], nsel, ptr_or_null(mass),
+                     fit ? 1 : 0, triangle))
+    return b200_err("pairwise cache");
+  return 0;
+}
+
 int Cpptraj::B200::ClosestCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
                                     bool fit, Cluster::Cframes const& frames,
                                     std::vector<Frame const*> const& centroidFrames,

@@ -44,6 +44,10 @@ int Rms2dPacked(DataSet_Coords& tgt, AtomMask const& tgtMask, std::vector<double
   */
 int CacheFill(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass,
               bool fit, Cluster::Cframes const& framesToCache, float* triangle);
+/// The same for a set that is not an in-memory float array (DataSet::TRAJ ...): the selected atoms of the frames to cache are
+/// read once (the reference reads two frames from the set per pair, Cluster/Metric_RMS.cpp:53-63).
+int CacheFillPacked(DataSet_Coords& crd, AtomMask const& mask, std::vector<double> const& mass,
+                    bool fit, Cluster::Cframes const& framesToCache, float* triangle);
 /** Frame-to-centroid RMSDs for a single Metric_RMS (Metric_RMS::FrameCentroidDist, Cluster/Metric_RMS.cpp:75-81), all
   * frames of \a frames at once: the body of List::AddFramesByCentroid (Cluster/List.cpp:160-207) and of the k-means
   * assignment step.  \a centroidFrames: Centroid_Coord::Cframe() of every cluster, in cluster order.

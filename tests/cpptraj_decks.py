@@ -49,7 +49,7 @@ rms ToPrevious :2-12@CA previous out Previous.dat
     # data set that reads the RMSD set while it is being filled (filter), and the modified coordinates written out
     "crdaction_rms": ("""noprogress
 parm {D}/tz2.parm7
-loadcrd {D}/tz2.crd 3 60 2 name CRD
+loadcrd {D}/tz2.crd name CRD
 crdaction CRD rms R1 first @CA,C,N out crd_rms.dat savematrices matricesout crd_rmat.dat
 crdaction CRD rms R2 first :2-12@CA nofit mass out crd_rms_nofit.dat crdframes 3,90,4
 crdout CRD fitted.crd
@@ -64,7 +64,7 @@ trajout aligned.crd
     # src/Exec_CrdTransform.cpp:75-134: iterative RMS refinement (every iteration fits all frames to a new average)
     "crdtransform_rmsrefine": ("""noprogress
 parm {D}/tz2.parm7
-loadcrd {D}/tz2.crd 3 60 2 name CRD
+loadcrd {D}/tz2.crd name CRD
 crdtransform CRD name REFINED rmsrefine mask @CA rmstol 0.0005
 crdout REFINED refined.crd
 """, [("refined.crd", "crd")]),
@@ -163,4 +163,13 @@ precision traj_nofit_masks.dat 12 6
 precision crd_reftraj.dat 12 6
 """, [("traj_tri.dat", "table"), ("traj_mass.dat", "table"), ("traj_reftraj.dat", "table"), ("traj_nofit_masks.dat", "table"),
       ("crd_reftraj.dat", "table")]),
+    # src/Cluster/MetricArray.cpp:766-801 on a TRAJ set (frames on disk): the cache fill reads the selected atoms of the frames
+    # to cache once and runs on the device, the merge loop and the cache consumers too; centroids (single-frame reads) stay
+    # on the reference's code.  (Golden made with ONE thread.)
+    "cluster_traj_set": ("""noprogress
+parm {D}/tz2.parm7
+loadtraj name TZ2 {D}/tz2.crd
+cluster T1 crdset TZ2 @CA hieragglo clusters 5 averagelinkage rms out ct.dat summary ct.summary.dat info ct.info
+cluster T2 crdset TZ2 :2-12 hieragglo clusters 4 complete rms mass sieve 3 out ct2.dat summary ct2.summary.dat
+""", [("ct.dat", "table"), ("ct.summary.dat", "text"), ("ct.info", "text"), ("ct2.dat", "table"), ("ct2.summary.dat", "text")]),
 }
