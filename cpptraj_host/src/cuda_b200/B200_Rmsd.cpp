@@ -363,6 +363,34 @@ int Cpptraj::B200::RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mas
   return 0;
 }
 
+int Cpptraj::B200::RmsAvgCorrPacked(DataSet_Coords& crd, AtomMask const& mask, std::vector<double> const& mass,
+                                    Frame const* fixedRef, std::vector<int> const& windows, std::vector<double>& avg,
+                                    std::vector<double>& sd)
+{
+  if (Init()) return 1;
+  avg.assign( windows.size(), 0.0 );
+  sd.assign( windows.size(), 0.0 );
+  if (windows.empty() || crd.Size() < 1) return 0;
+  const int nsel = mask.Nselected();
+  if (fixedRef != 0 && fixedRef->Natom() != nsel) {
+    mprinterr("Error: B200 RMSD: # target atoms (%i) != # reference atoms (%i)\n", nsel, fixedRef->Natom());
+    return 1;
+  }
+  std::vector<float> buf;
+  b200_pack_selected( crd, mask, buf );
+  std::vector<int> ident( (size_t)nsel );
+  for (int i = 0; i < nsel; i++) ident[i] = i;
+  Timer t_call;
+  t_call.Start();
+  int err = b200_rmsavgcorr(&buf[0], (size_t)3 * (size_t)nsel, (int)crd.Size(), &ident[0], nsel, ptr_or_null(mass),
+                            (fixedRef != 0 ? fixedRef->xAddress() : 0), &windows[0], (int)windows.size(), &avg[0], &sd[0]);
+  t_call.Stop();
+  if (err) return b200_err("rmsavgcorr");
+  mprintf("\tB200: %zu window sizes over %zu frames (selected atoms read once) on the device in %.4f s.\n", windows.size(),
+          crd.Size(), t_call.Total());
+  return 0;
+}
+
 int Cpptraj::B200::CacheClusterSums(const float* triangle, int nCached, std::vector<int> const& members,
                                     std::vector<int> const& offsets, std::vector<double>& cum, std::vector<double>* up,
                                     std::vector<double>* up2)

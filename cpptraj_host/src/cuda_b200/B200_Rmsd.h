@@ -76,6 +76,10 @@ int BuildCentroids(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vec
   */
 int RmsAvgCorr(DataSet_Coords_CRD const& crd, AtomMask const& mask, std::vector<double> const& mass, Frame const* fixedRef,
                std::vector<int> const& windows, std::vector<double>& avg, std::vector<double>& sd);
+/// The same for a set that is not an in-memory float array (TRAJ ...): the selected atoms of every frame are read once (the
+/// reference reads every frame again for every window size, Analysis_RmsAvgCorr.cpp:246-249).
+int RmsAvgCorrPacked(DataSet_Coords& crd, AtomMask const& mask, std::vector<double> const& mass, Frame const* fixedRef,
+                     std::vector<int> const& windows, std::vector<double>& avg, std::vector<double>& sd);
 /** Hierarchical agglomerative clustering on an in-memory pairwise cache (Algorithm_HierAgglo::DoClustering /
   * MergeClosest, Cluster/Algorithm_HierAgglo.cpp:97-245, with the DynamicMatrix bookkeeping): all merges run on the
   * device in one launch.  \a triangle: DataSet_PairwiseCache_MEM::Ptr() for \a nCached frames; \a linkage in

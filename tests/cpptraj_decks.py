@@ -172,4 +172,13 @@ loadtraj name TZ2 {D}/tz2.crd
 cluster T1 crdset TZ2 @CA hieragglo clusters 5 averagelinkage rms out ct.dat summary ct.summary.dat info ct.info
 cluster T2 crdset TZ2 :2-12 hieragglo clusters 4 complete rms mass sieve 3 out ct2.dat summary ct2.summary.dat
 """, [("ct.dat", "table"), ("ct.summary.dat", "text"), ("ct.info", "text"), ("ct2.dat", "table"), ("ct2.summary.dat", "text")]),
+    # src/Analysis_RmsAvgCorr.cpp:176-316 on a TRAJ set (frames on disk; the reference reads every frame again for every
+    # window size): selected atoms read once, every window size on the device.  (Golden made with ONE thread.)
+    "rmsavgcorr_traj_set": ("""noprogress
+parm {D}/tz2.parm7
+loadtraj name TZ2 {D}/tz2.crd
+reference {D}/tz2.crd 5
+rmsavgcorr TF crdset TZ2 :2-12@CA out tac.first.dat first
+rmsavgcorr TR crdset TZ2 :2-12@CA,C,N out tac.ref.dat reference mass offset 4
+""", [("tac.first.dat", "table"), ("tac.ref.dat", "table")]),
 }
