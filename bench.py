@@ -847,6 +847,38 @@ def cpptraj_leg(cfg, cpu_seconds):
             if out["rmsavgcorr"]["cpptraj_b200"].get("value"):
                 out["rmsavgcorr"]["ratio"] = out["rmsavgcorr"]["cpptraj_b200"]["value"] / o["value"]
         out["rmsavgcorr"]["cpptraj_omp"] = o
+    # ---- BASELINE config 5 as a user runs it: 2drms of 100,000 x 1,000 (a 20 GB Matrix<float>) through the B200 binary, one
+    #      process from the trajectory file to the filled matrix; the unmodified binary's rate is the prefix run above
+    if not os.environ.get("B200_BENCH_NO_BIG_CPPTRAJ"):
+        try:
+            c5 = CONFIGS["cfg5"]
+            nF5, nA5 = c5["frames"], c5["atoms"]
+            del rec, crd
+            big = np.zeros(nF5, dtype=[("n", "<i4"), ("xyz", "<f4", (3 * nA5,))])
+            big["n"] = nA5
+            gen_trajectory(c5["seed"], nF5, nA5, big["xyz"])
+            with open(os.path.join(w, "t5.binpos"), "wb") as f:
+                f.write(b"fxyz")
+                big.tofile(f)
+            del big
+            pats = {"analyses_s": r"TIME: Analyses took ([0-9.]+) seconds", "library_call_s": r"atoms: ([0-9.]+) s in the library",
+                    "device_setup_s": r"\(set-up ([0-9.]+) s", "trajectory_s": r"Trajectory Process : ([0-9.]+) s",
+                    "total_execution_s": r"TIME: Total execution time: ([0-9.]+) seconds"}
+            r5 = run_deck(b200_bin, "noprogress\nparm t.pdb\ntrajin t5.binpos\n2drms @CA R2D\nrun\n", dict(os.environ), pats)
+            pairs5 = nF5 * (nF5 - 1) // 2
+            leg5 = {"deck": "2drms @CA R2D on %d frames x %d atoms (binpos, %.1f GB), result: a %.0f GB Matrix<float> in pageable memory" % (
+                        nF5, nA5, nF5 * (12 * nA5 + 4) / 1e9, pairs5 * 4 / 1e9), "cpptraj_b200": dict(r5, frames=nF5), "unit": UNIT}
+            if r5.get("analyses_s"):
+                leg5["cpptraj_b200"]["value"] = pairs5 / r5["analyses_s"]
+                if r5.get("library_call_s"):
+                    leg5["cpptraj_b200"]["value_library_call"] = pairs5 / r5["library_call_s"]
+                if out.get("cpptraj_omp", {}).get("value"):
+                    leg5["ratio"] = leg5["cpptraj_b200"]["value"] / out["cpptraj_omp"]["value"]
+                    leg5["ratio_how"] = ("pairs / 'TIME: Analyses took' of cpptraj.B200 on the whole matrix over the rate of the UNMODIFIED "
+                                         "cpptraj.OMP on a prefix of the cfg2 file (its cost is linear in pairs)")
+            out["cfg5_size"] = leg5
+        except Exception as e:       # (disk or memory of the box: the leg is optional)
+            out["cfg5_size"] = {"error": repr(e)}
     for f in os.listdir(w):
         os.remove(os.path.join(w, f))
     os.rmdir(w)
