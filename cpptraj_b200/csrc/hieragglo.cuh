@@ -119,25 +119,37 @@ __device__ __forceinline__ HaMin2 ha_m2_warp(HaMin2 m) {
 }
 __device__ __forceinline__ float ha_lb_of(unsigned int sec) { return sec == 0xffffffffu ? __int_as_float(0x7f800000) : ha_unord(sec); }
 
-/// One row's minimum and second minimum over the clusters still present, by one warp (the row is contiguous).
-__device__ __forceinline__ HaMin2 ha_warp_row_min(const HaArgs& a, int row, int lane) {
+#ifndef B200_HA_RESCAN_U
+#define B200_HA_RESCAN_U 8    // re-scans of whole rows: loads in flight per thread (a row of 50,000 clusters is 250 KB: latency, not bandwidth; 12 and 16 spill)
+#endif
+constexpr int HA_UR = B200_HA_RESCAN_U;
+
+/// Minimum and second minimum of this thread's share of one row (clusters still present; the row is contiguous): elements
+/// first, first + step, ...; U loads of the row and of the merged-away flags in flight.
+template <int U>
+__device__ __forceinline__ HaMin2 ha_row_part_min(const HaArgs& a, int row, int first, int step) {
   const int n = a.n;
   const float* R = a.D + (size_t)row * n;
   HaMin2 m; m.best = ~0ull; m.sec = 0xffffffffu;
-  for (int j0 = lane; j0 < n; j0 += 32 * HA_U) {
-    float v[HA_U]; unsigned char ig[HA_U];
+  for (int j0 = first; j0 < n; j0 += step * U) {
+    float v[U]; unsigned char ig[U];
 #pragma unroll
-    for (int u = 0; u < HA_U; ++u) {
-      const int j = j0 + 32 * u;
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + step * u;
       const bool in = j < n && j != row;
       ig[u] = in ? a.ign[j] : (unsigned char)1;
       v[u] = in ? R[j] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < HA_U; ++u)
-      if (!ig[u]) ha_m2_add(m, ha_key(v[u], j0 + 32 * u));
+    for (int u = 0; u < U; ++u)
+      if (!ig[u]) ha_m2_add(m, ha_key(v[u], j0 + step * u));
   }
-  return ha_m2_warp(m);
+  return m;
+}
+/// One row's minimum and second minimum by one warp.
+template <int U = HA_U>
+__device__ __forceinline__ HaMin2 ha_warp_row_min(const HaArgs& a, int row, int lane) {
+  return ha_m2_warp(ha_row_part_min<U>(a, row, lane, 32));
 }
 
 /// DynamicMatrix::updateClosestIdx (DynamicMatrix.h:43-62) for every row of a list (lowest index among the minima over
@@ -146,16 +158,37 @@ __device__ __forceinline__ HaMin2 ha_warp_row_min(const HaArgs& a, int row, int 
 /// and was the closest of many): one warp per row, all warps of the team side by side.
 __device__ __forceinline__ void ha_team_rescan(const HaArgs& a, const int* list, int nList, int tid, int nThr, ha_u64* sm) {
   const int n = a.n;
-  if (nList > 8) {
+  const int nCta = nThr / (int)blockDim.x, cta = tid / (int)blockDim.x;
+  unsigned int* smSec = reinterpret_cast<unsigned int*>(sm + 34);
+  if (nList > 25 * nCta) {
+    // very long lists: one warp per row, all warps of the team side by side
     const int lane = threadIdx.x & 31, nWarps = nThr >> 5;
     for (int e = tid >> 5; e < nList; e += nWarps) {
       const int row = list[e];
-      const HaMin2 m = ha_warp_row_min(a, row, lane);
+      const HaMin2 m = ha_warp_row_min<HA_UR>(a, row, lane);
       if (lane == 0) { a.rkey[row] = m.best; a.rlb[row] = m.sec; }
     }
     return;
   }
-  unsigned int* smSec = reinterpret_cast<unsigned int*>(sm + 34);
+  if (nList > 1 && nCta > 1) {
+    // a handful to a few hundred rows: one CTA per row, the CTAs of the team side by side (a row costs a few dependent
+    // rounds of loads whoever scans it: what counts is how many rows are scanned at the same time)
+    for (int e = cta; e < nList; e += nCta) {
+      const int row = list[e];
+      HaMin2 m = ha_m2_warp(ha_row_part_min<HA_UR>(a, row, (int)threadIdx.x, (int)blockDim.x));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = m.best; smSec[threadIdx.x >> 5] = m.sec; }
+      __syncthreads();
+      if (threadIdx.x < 32) {
+        HaMin2 t;
+        const bool have = threadIdx.x < (blockDim.x >> 5);
+        t.best = have ? sm[threadIdx.x] : ~0ull; t.sec = have ? smSec[threadIdx.x] : 0xffffffffu;
+        t = ha_m2_warp(t);
+        if (threadIdx.x == 0) { a.rkey[row] = t.best; a.rlb[row] = t.sec; }
+      }
+    }
+    return;
+  }
   for (int e = 0; e < nList; ++e) {
     const int row = list[e];
     const float* R = a.D + (size_t)row * n;
@@ -217,11 +250,26 @@ __device__ __forceinline__ void ha_tie_replay(const HaArgs& a, int C1, int C2) {
   }
   if (c < 0) { if (lane == 0) { a.closest[C1] = -1; a.cmin[C1] = __int_as_float(0x7f800000); } return; }
   float vc = a.vnew[c], oc = a.oold[c];
-  for (int base = 0; base < n; base += 32) {
+  constexpr int TR_U = 4;   // 32-cluster groups whose loads are issued together (they do not depend on the replay's state)
+  for (int base0 = 0; base0 < n; base0 += 32 * TR_U) {
+    bool validU[TR_U]; float vU[TR_U], oU[TR_U];
+#pragma unroll
+    for (int u = 0; u < TR_U; ++u) {
+      const int k = base0 + 32 * u + lane;
+      const bool in = k < n && k != C1;
+      const unsigned char ig = in ? a.ign[k] : (unsigned char)1;
+      vU[u] = in ? a.vnew[k] : 0.f;
+      oU[u] = in ? a.oold[k] : 0.f;
+      validU[u] = !ig;
+    }
+#pragma unroll
+    for (int u = 0; u < TR_U; ++u) {
+    const int base = base0 + 32 * u;
+    if (base >= n) break;
     const int k = base + lane;
-    const bool valid = k < n && k != C1 && !a.ign[k];
-    const float v = valid ? a.vnew[k] : 0.f;
-    const float o = valid ? a.oold[k] : 0.f;
+    const bool valid = validU[u];
+    const float v = valid ? vU[u] : 0.f;
+    const float o = valid ? oU[u] : 0.f;
     int start = 0;
     for (;;) {
       const float cur = (c < k) ? vc : oc;   // element c of the half-updated row as SetCdist(C1,k) sees it
@@ -246,6 +294,7 @@ __device__ __forceinline__ void ha_tie_replay(const HaArgs& a, int C1, int C2) {
       vc = a.vnew[c]; oc = a.oold[c];
       start = L + 1;
       if (start >= 32) break;
+    }
     }
   }
   if (lane == 0) { a.closest[C1] = c; a.cmin[C1] = a.vnew[c]; a.lb2[C1] = a.vnew[c]; }

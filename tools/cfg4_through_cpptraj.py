@@ -38,5 +38,5 @@ t0 = time.perf_counter()
 r = subprocess.run([binary, "-i", "in"], cwd=w, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
 print("cpptraj.B200 exit %d, wall %.1f s" % (r.returncode, time.perf_counter() - t0))
 for line in r.stdout.splitlines():
-    if re.search(r"TIME|B200|Error|Warning|clusters|Caching|Estimated", line): print(line)
+    if re.search(r"TIME|B200|Error|Warning|clusters|Caching|Estimated|hieragglo", line): print(line)
 if os.path.exists(os.path.join(w, "s.dat")): print(open(os.path.join(w, "s.dat")).read())
