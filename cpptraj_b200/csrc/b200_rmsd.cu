@@ -2205,7 +2205,17 @@ int b200_rmsd_build_centroids(const float* crd, size_t frameStrideFloats, int nF
   a.offsets = (const int*)d.idxB.p; a.atomIdx = (const int*)d.idxA.p; a.nAtoms = nAtoms;
   a.mass = mass ? (const double*)d.massA.p : nullptr; a.fit = fit ? 1 : 0; a.out = (double*)d.planesB.p;
   COUNT_LAUNCH();
-  centroid_build_kernel<<<nClusters, CENT_THREADS, 0, st>>>(a);
+  const size_t centSmem = (size_t)3 * (size_t)nAtoms * sizeof(double);
+  if (centSmem <= (size_t)200 * 1024) {   // the running sum in shared memory
+    static std::atomic<size_t> granted[64];
+    if (granted[d.id & 63].load(std::memory_order_acquire) < centSmem) {
+      CU(cudaFuncSetAttribute(centroid_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      granted[d.id & 63].store((size_t)200 * 1024, std::memory_order_release);
+    }
+    centroid_build_kernel<true><<<nClusters, CENT_THREADS, centSmem, st>>>(a);
+  } else {
+    centroid_build_kernel<false><<<nClusters, CENT_THREADS, 0, st>>>(a);
+  }
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(centroidsOut, d.planesB.p, outBytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));

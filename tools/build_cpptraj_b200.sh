@@ -36,7 +36,7 @@ place_glue
 if [ "$MODE" == "--check" ]; then
   cd "$OUT/src"
   for f in cuda_b200/B200_Rmsd.cpp Analysis_Rms2d.cpp Analysis_RmsAvgCorr.cpp Action_Rmsd.cpp Action_Align.cpp Exec_CrdTransform.cpp Exec_CrdAction.cpp Cluster/MetricArray.cpp Cluster/List.cpp \
-           Cluster/Node.cpp Cluster/BestReps.cpp Cluster/Algorithm_Kmeans.cpp Cluster/Algorithm_HierAgglo.cpp Cluster/Results_Coords.cpp Cluster/Output.cpp Cluster/Control.cpp; do
+           Cluster/Node.cpp Cluster/BestReps.cpp Cluster/Algorithm_Kmeans.cpp Cluster/Algorithm_HierAgglo.cpp Cluster/Results_Coords.cpp Cluster/Output.cpp Cluster/Control.cpp Cluster/PseudoF.cpp; do
     /usr/bin/g++ -std=c++11 -fsyntax-only -fopenmp -DCUDA_B200 -DNO_MATHLIB -DNONETCDF -I. -Icuda_b200 "$f"
     echo "syntax ok: $f"
   done

@@ -8,7 +8,7 @@ SCR=${1:-/tmp/cpptraj_b200_build}; REF=${2:-/root/reference}
 HERE=$(cd "$(dirname "$0")/.." && pwd)
 FILES="configure cmake-cpptraj/CudaConfig.cmake src/CMakeLists.txt src/Makefile src/Matrix.h src/Action_Align.cpp src/Action_Align.h src/Exec_CrdTransform.cpp src/Action_Rmsd.cpp src/Action_Rmsd.h src/Analysis_Rms2d.cpp src/Analysis_RmsAvgCorr.cpp
        src/Exec_CrdAction.cpp src/DataSet_Coords_CRD.h src/Cluster/Algorithm_HierAgglo.cpp src/Cluster/Algorithm_HierAgglo.h src/Cluster/Algorithm_Kmeans.cpp src/Cluster/BestReps.cpp src/Cluster/BestReps.h src/Cluster/Output.cpp src/Cluster/Control.cpp src/Cluster/Control.h
-       src/Cluster/List.cpp src/Cluster/MetricArray.cpp src/Cluster/MetricArray.h src/Cluster/Results_Coords.cpp src/Cluster/Metric_RMS.h src/Cluster/Node.cpp src/Cluster/Node.h"
+       src/Cluster/List.cpp src/Cluster/MetricArray.cpp src/Cluster/MetricArray.h src/Cluster/Results_Coords.cpp src/Cluster/Metric_RMS.h src/Cluster/Node.cpp src/Cluster/Node.h src/Cluster/PseudoF.cpp"
 OUT="$HERE/cpptraj_host/reference.patch"
 : > "$OUT"
 for f in $FILES; do
