@@ -107,3 +107,20 @@ def test_cpptraj_host_glue_compiles_against_reference():
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:]
     assert r.stdout.count("syntax ok") == 18   # the glue, sixteen patched reference sources, configure
+
+
+def test_every_cpptraj_deck_has_its_goldens():
+    """tests/cpptraj_decks.py and tests/golden/cpptraj/ (outputs of the UNMODIFIED reference, tools/make_golden_cpptraj.py)
+    stay in step: every output a deck lists has a non-empty golden, and no golden directory is orphaned."""
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    from cpptraj_decks import DECKS
+    gold = os.path.join(here, "golden", "cpptraj")
+    for name, (text, outs) in DECKS.items():
+        assert "{D}" in text and outs, name
+        for fname, kind in outs:
+            p = os.path.join(gold, name, fname)
+            assert os.path.isfile(p) and os.path.getsize(p) > 0, "missing golden %s/%s" % (name, fname)
+            assert kind in ("table", "crd", "text", "cmatrix"), (name, fname, kind)
+    assert sorted(os.listdir(gold)) == sorted(DECKS), "golden directories and decks differ"
